@@ -1,0 +1,404 @@
+// gla_oracle.cpp -- CPU ORACLE for the Householder-QR / Cholesky-update hot path.
+//
+// *** TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product. ***
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+// legs may load this library, and only as the checker / reported CPU baseline.
+//
+// PARITY STATUS: "parity unpinned" for the two Julia-stdlib routines reflector! and the
+// left reflectorApply! -- they are NOT in /root/reference (they live in Julia's
+// un-vendored, un-pinned stdlib LinearAlgebra: Project.toml:13 `julia = "1.6"`, no
+// Manifest), and no Julia runtime exists in this image, so the reference itself cannot
+// be executed to generate vectors.  They are restated from their published semantics
+// (stdlib/LinearAlgebra/src/generic.jl, Julia 1.9-1.12 form)
+// and pinned by the hand-derived known-answer vectors in tests/golden/kat.json and by
+// LAPACK cross-checks (row-phase normalised).  Everything that IS in the reference tree
+// is restated function by function below with its file:line.
+//
+// The algorithms are restated from the reference's behaviour; no reference source text
+// is copied.  Column-major storage, 0-based indices here vs 1-based in the reference.
+//
+// Build: g++ -O3 -march=x86-64-v3 -fopenmp -shared -fPIC gla_oracle.cpp -o libgla_oracle.so
+
+#include <cmath>
+#include <complex>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+
+namespace {
+
+using i64 = int64_t;
+using zd = std::complex<double>;
+
+template <class T> struct Num { using real = T; };
+template <> struct Num<zd> { using real = double; };
+
+inline float cj(float x) { return x; }
+inline double cj(double x) { return x; }
+inline zd cj(zd x) { return std::conj(x); }
+inline float re(float x) { return x; }
+inline double re(double x) { return x; }
+inline double re(zd x) { return x.real(); }
+inline float abs2(float x) { return x * x; }
+inline double abs2(double x) { return x * x; }
+inline double abs2(zd x) { return x.real() * x.real() + x.imag() * x.imag(); }
+
+// ---------------------------------------------------------------------------------
+// Julia stdlib LinearAlgebra.reflector!(x)          call site: src/qr.jl:96
+//   xi = x[1]; nrm = norm(x); nrm == 0 -> tau = 0 (x untouched)
+//   nu = copysign(nrm, real(xi)); xi += nu; x[1] = -nu; x[2:] /= xi; tau = xi/nu
+// norm(x) is restated as sqrt(sum abs2) (Julia's generic_norm2 fast path / <=1.8 form);
+// the scaled variants differ only for over/underflowing data.
+// ---------------------------------------------------------------------------------
+template <class T>
+T reflector(T* x, i64 n) {
+  using R = typename Num<T>::real;
+  if (n == 0) return T(0);
+  T xi = x[0];
+  R ss = 0;
+  for (i64 i = 0; i < n; ++i) ss += abs2(x[i]);
+  R nrm = std::sqrt(ss);
+  if (nrm == R(0)) return T(0);
+  R nu = std::copysign(nrm, re(xi));
+  xi += nu;
+  x[0] = T(-nu);
+  for (i64 i = 1; i < n; ++i) x[i] /= xi;
+  return xi / nu;
+}
+
+// ---------------------------------------------------------------------------------
+// Julia stdlib left LinearAlgebra.reflectorApply!(x, tau, A)   call site: src/qr.jl:102
+//   A <- (I - conj(tau) v v^H) A,  v = [1; x[2:]]
+// ---------------------------------------------------------------------------------
+template <class T>
+void reflector_apply_left(const T* x, T tau, T* A, i64 m, i64 n, i64 lda) {
+  for (i64 j = 0; j < n; ++j) {
+    T* a = A + j * lda;
+    T s = a[0];
+    for (i64 i = 1; i < m; ++i) s += cj(x[i]) * a[i];
+    s = cj(tau) * s;
+    a[0] -= s;
+    for (i64 i = 1; i < m; ++i) a[i] -= x[i] * s;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// right reflectorApply!(A, x, tau)                  src/qr.jl:19-42
+//   row by row: s = tau*(A[i,1] + sum_j>=2 A[i,j] x[j]); A[i,1] -= s; A[i,j] -= s*conj(x[j])
+// returns -2 (second dimension mismatch) like the DimensionMismatch at :21-27
+// ---------------------------------------------------------------------------------
+template <class T>
+int reflector_apply_right(T* A, i64 m, i64 n, i64 lda, const T* x, i64 lenx, T tau) {
+  if (lenx != n) return -2;
+  for (i64 i = 0; i < m; ++i) {
+    T s = A[i];
+    for (i64 j = 1; j < n; ++j) s += A[i + j * lda] * x[j];
+    s = s * tau;
+    A[i] -= s;
+    for (i64 j = 1; j < n; ++j) A[i + j * lda] -= s * cj(x[j]);
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// qrUnblocked!(A, tau)                              src/qr.jl:86-111
+// (the reference's recursion on view(A,2:m,2:n) is a column loop)
+// ---------------------------------------------------------------------------------
+template <class T>
+void qr_unblocked(T* A, i64 m, i64 n, i64 lda, T* tau) {
+  i64 k = 0;
+  while (true) {
+    T* a = A + k + k * lda;
+    i64 mk = m - k, nk = n - k;
+    T t1 = reflector(a, mk);                                  // :94-98
+    tau[k] = t1;
+    if (nk > 1) reflector_apply_left(a, t1, a + lda, mk, nk - 1, lda);   // :101-103
+    if (mk > 1 && nk > 1) { ++k; continue; }                  // :106-108
+    break;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// getindex(::QR2, Tuple{:QBlocked})  -> compact-WY T   src/qr.jl:64-83
+//   S[i,j] = tau_i * (conj?(F[j,i]) + dot(F[j+1:m,i], F[j+1:m,j])),  i<j
+//   inv!(UnitUpperTriangular(S)); T[j,j] = tau_j; T[i,j] *= tau_j
+// literal != 0 reproduces the reference text exactly (F[j,i] without conj, :72), which
+// is only correct for real element types (SURVEY.md finding 3).
+// ---------------------------------------------------------------------------------
+template <class T>
+void build_T(const T* F, i64 m, i64 n, i64 ldf, const T* tau, T* Tm, i64 ldt, int literal) {
+  i64 k = std::min(m, n);
+  std::vector<T> U((size_t)k * k, T(0));
+  for (i64 j = 0; j < k; ++j)
+    for (i64 i = 0; i < j; ++i) {
+      T d = T(0);
+      for (i64 l = j + 1; l < m; ++l) d += cj(F[l + i * ldf]) * F[l + j * ldf];
+      T fji = literal ? F[j + i * ldf] : cj(F[j + i * ldf]);
+      U[i + j * k] = tau[i] * (fji + d);                       // :70-74
+    }
+  // X = inv(I + U), U strictly upper.  Column j: X[:,j] = e_j - X[:,0:j] * U[0:j,j]   (:75)
+  std::vector<T> X((size_t)k * k, T(0));
+  for (i64 j = 0; j < k; ++j) {
+    X[j + j * k] = T(1);
+    for (i64 l = 0; l < j; ++l) {
+      T u = U[l + j * k];
+      if (u == T(0)) continue;
+      for (i64 i = 0; i <= l; ++i) X[i + j * k] -= X[i + l * k] * u;
+    }
+  }
+  for (i64 j = 0; j < k; ++j) {                                // :76-81
+    for (i64 i = 0; i < k; ++i) Tm[i + j * ldt] = T(0);
+    for (i64 i = 0; i < j; ++i) Tm[i + j * ldt] = X[i + j * k] * tau[j];
+    Tm[j + j * ldt] = tau[j];
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// lmul!(H, A, M) / lmul!(H', A, M) for HouseholderBlock   src/householder.jl:82-115,119-157
+//   M = V1^H A1 + V2^H A2;  M = T M (or T^H M for the adjoint);  A2 -= V2 M;  A1 -= V1 M
+// with V1 = unit-lower top b x b of V, V2 the rows below.  The unit-lower product in the
+// last step is the reference's own generic lmul!(UnitLowerTriangular, B, alpha)
+// (src/juliaBLAS.jl:154-166), rows bottom-up.  Columns of A are independent -> OpenMP,
+// standing in for the multithreaded BLAS the reference's trmm/gemm calls would use.
+// returns -1 on row mismatch (DimensionMismatch at :87 / :129)
+// ---------------------------------------------------------------------------------
+template <class T>
+int block_apply(const T* V, i64 mV, i64 nV, i64 ldv, const T* Tm, i64 ldt, T* A, i64 mA, i64 nA,
+                i64 lda, int adjoint) {
+  if (mV != mA) return -1;
+  i64 b = std::min(mV, nV);
+#pragma omp parallel
+  {
+    std::vector<T> Mc(b), M2(b);
+#pragma omp for schedule(static)
+    for (i64 j = 0; j < nA; ++j) {
+      T* a = A + j * lda;
+      // M = V1^H * A1 (unit lower, conj-transposed => upper unit):  M[i] = a[i] + sum_{l>i} conj(V[l,i]) a[l]
+      for (i64 i = 0; i < b; ++i) {
+        T s = a[i];
+        const T* v = V + i * ldv;
+        for (i64 l = i + 1; l < b; ++l) s += cj(v[l]) * a[l];
+        // M += V2^H * A2
+        for (i64 l = b; l < mA; ++l) s += cj(v[l]) * a[l];
+        Mc[i] = s;
+      }
+      // M = T M  (upper)  or  T^H M (lower)
+      if (!adjoint) {
+        for (i64 i = 0; i < b; ++i) {
+          T s = T(0);
+          for (i64 l = i; l < b; ++l) s += Tm[i + l * ldt] * Mc[l];
+          M2[i] = s;
+        }
+      } else {
+        for (i64 i = 0; i < b; ++i) {
+          T s = T(0);
+          for (i64 l = 0; l <= i; ++l) s += cj(Tm[l + i * ldt]) * Mc[l];
+          M2[i] = s;
+        }
+      }
+      // A2 -= V2 M
+      for (i64 l = 0; l < b; ++l) {
+        const T* v = V + l * ldv;
+        T ml = M2[l];
+        for (i64 i = b; i < mA; ++i) a[i] -= v[i] * ml;
+      }
+      // M = -V1 M (unit lower, rows bottom-up), A1 += M
+      for (i64 i = b - 1; i >= 0; --i) {
+        T s = -M2[i];
+        for (i64 l = 0; l < i; ++l) s += -V[i + l * ldv] * M2[l];
+        a[i] += s;
+      }
+    }
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// qrBlocked!(A, blocksize, tau, work)               src/qr.jl:113-146
+// ---------------------------------------------------------------------------------
+template <class T>
+void qr_blocked(T* A, i64 m, i64 n, i64 lda, T* tau, i64 bs, int literal) {
+  i64 k = 0;
+  std::vector<T> Tm((size_t)bs * bs);
+  while (true) {
+    T* Ak = A + k + k * lda;
+    i64 mk = m - k, nk = n - k;
+    i64 nb = std::min(nk, bs);
+    qr_unblocked(Ak, mk, nb, lda, tau + k);                   // :123-125
+    if (nk > bs) {                                            // :128-133
+      build_T(Ak, mk, nb, lda, tau + k, Tm.data(), bs, literal);
+      block_apply(Ak, mk, nb, lda, Tm.data(), bs, Ak + bs * lda, mk, nk - bs, lda, 1);
+    }
+    if (mk > bs && nk > bs) { k += bs; continue; }            // :136-143
+    break;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// rankUpdate!(C::Hermitian, A, alpha::Real) generic rank-k  src/juliaBLAS.jl:89-112, 'L' branch
+//   for k, for j, for i>=j: C[i,j] += A[i,k]*alpha*conj(A[j,k])
+// (this is the method cholRecursive! actually hits, SURVEY.md finding 4)
+// ---------------------------------------------------------------------------------
+template <class T>
+void rank_update_lower(T* C, i64 n, i64 ldc, const T* A, i64 kk, i64 lda, typename Num<T>::real alpha) {
+  for (i64 k = 0; k < kk; ++k)
+    for (i64 j = 0; j < n; ++j) {
+      T ajc = cj(A[j + k * lda]);
+      for (i64 i = j; i < n; ++i) C[i + j * ldc] += A[i + k * lda] * alpha * ajc;
+    }
+}
+// Same sums, j-outermost so columns can go to different threads (bitwise identical result:
+// every C[i,j] still accumulates its k terms in increasing k).
+template <class T>
+void rank_update_lower_mt(T* C, i64 n, i64 ldc, const T* A, i64 kk, i64 lda, typename Num<T>::real alpha) {
+#pragma omp parallel for schedule(dynamic, 8)
+  for (i64 j = 0; j < n; ++j)
+    for (i64 k = 0; k < kk; ++k) {
+      T ajc = cj(A[j + k * lda]);
+      for (i64 i = j; i < n; ++i) C[i + j * ldc] += A[i + k * lda] * alpha * ajc;
+    }
+}
+
+// rank-1 Hermitian generic  src/juliaBLAS.jl:53-63 ('L')
+template <class T>
+void rank1_update_lower(T* C, i64 n, i64 ldc, const T* a, typename Num<T>::real alpha) {
+  for (i64 j = 0; j < n; ++j) {
+    T ajc = cj(a[j]);
+    for (i64 i = j; i < n; ++i) C[i + j * ldc] += a[i] * alpha * ajc;
+  }
+}
+
+// rdiv!(A21, LowerTriangular(A11)')  (stdlib -> trsm Right/Lower/ConjTrans/NonUnit)  call site src/cholesky.jl:48
+//   X <- X * L^{-H}:  column j of X: x_j = (x_j - sum_{l<j} x_l conj(L[j,l])) / conj(L[j,j])
+template <class T>
+void rdiv_lower_adjoint(T* X, i64 m, i64 n, i64 ldx, const T* L, i64 ldl) {
+#pragma omp parallel for schedule(static) if (m * n > 4096)
+  for (i64 r0 = 0; r0 < m; r0 += 64) {
+    i64 r1 = std::min(m, r0 + 64);
+    for (i64 j = 0; j < n; ++j) {
+      T* xj = X + j * ldx;
+      for (i64 l = 0; l < j; ++l) {
+        T c = cj(L[j + l * ldl]);
+        const T* xl = X + l * ldx;
+        for (i64 i = r0; i < r1; ++i) xj[i] -= xl[i] * c;
+      }
+      T d = cj(L[j + j * ldl]);
+      for (i64 i = r0; i < r1; ++i) xj[i] /= d;
+    }
+  }
+}
+
+// cholUnblocked!(A, Val{:L})                        src/cholesky.jl:3-15
+template <class T>
+int chol_unblocked(T* A, i64 n, i64 lda, i64 off) {
+  for (i64 k = 0; k < n; ++k) {
+    T* a = A + k + k * lda;
+    if (!(re(a[0]) > 0)) return (int)(off + k + 1);   // sqrt of a negative real throws DomainError
+    a[0] = std::sqrt(a[0]);
+    if (k + 1 < n) {
+      auto inv = typename Num<T>::real(1) / re(a[0]);
+      for (i64 i = 1; i < n - k; ++i) a[i] *= inv;
+      rank1_update_lower(a + 1 + lda, n - k - 1, lda, a + 1, typename Num<T>::real(-1));
+    }
+  }
+  return 0;
+}
+
+// cholBlocked!(A, Val{:L}, blocksize)               src/cholesky.jl:17-35
+template <class T>
+int chol_blocked(T* A, i64 n, i64 lda, i64 bs) {
+  for (i64 k = 0; k < n; k += bs) {
+    i64 nb = std::min(n - k, bs);
+    T* A11 = A + k + k * lda;
+    int info = chol_unblocked(A11, nb, lda, k);
+    if (info) return info;
+    if (n - k > bs) {
+      T* A21 = A11 + bs;
+      rdiv_lower_adjoint(A21, n - k - bs, bs, lda, A11, lda);
+      rank_update_lower_mt(A21 + bs * lda, n - k - bs, lda, A21, bs, lda, typename Num<T>::real(-1));
+    }
+  }
+  return 0;
+}
+
+// cholRecursive!(A, Val{:L}, cutoff)                src/cholesky.jl:37-55
+// NB the A11 branch drops `cutoff` (defaults to 1), exactly as :46 does.
+template <class T>
+int chol_recursive(T* A, i64 n, i64 lda, i64 cutoff, i64 off, int mt) {
+  if (n == 1) {
+    if (!(re(A[0]) > 0)) return (int)(off + 1);
+    A[0] = std::sqrt(A[0]);
+    return 0;
+  } else if (n < cutoff) {
+    return chol_unblocked(A, n, lda, off);
+  }
+  i64 n2 = n / 2;
+  int info = chol_recursive(A, n2, lda, 1, off, mt);
+  if (info) return info;
+  T* A21 = A + n2;
+  rdiv_lower_adjoint(A21, n - n2, n2, lda, A, lda);
+  T* A22 = A + n2 + n2 * lda;
+  if (mt) rank_update_lower_mt(A22, n - n2, lda, A21, n2, lda, typename Num<T>::real(-1));
+  else    rank_update_lower(A22, n - n2, lda, A21, n2, lda, typename Num<T>::real(-1));
+  return chol_recursive(A22, n - n2, lda, cutoff, off + n2, mt);
+}
+
+}  // namespace
+
+#define ORACLE_API extern "C" __attribute__((visibility("default")))
+
+#define DEFINE_TYPE(P, T, R)                                                                       \
+  ORACLE_API void oracle_##P##reflector(T* x, i64 n, T* tau) { *tau = reflector<T>(x, n); }        \
+  ORACLE_API void oracle_##P##reflector_apply_left(const T* x, const T* tau, T* A, i64 m, i64 n,  \
+                                                   i64 lda) {                                      \
+    reflector_apply_left<T>(x, *tau, A, m, n, lda);                                                \
+  }                                                                                                \
+  ORACLE_API int oracle_##P##reflector_apply_right(T* A, i64 m, i64 n, i64 lda, const T* x,        \
+                                                   i64 lenx, const T* tau) {                       \
+    return reflector_apply_right<T>(A, m, n, lda, x, lenx, *tau);                                  \
+  }                                                                                                \
+  ORACLE_API void oracle_##P##qr_unblocked(T* A, i64 m, i64 n, i64 lda, T* tau) {                  \
+    qr_unblocked<T>(A, m, n, lda, tau);                                                            \
+  }                                                                                                \
+  ORACLE_API void oracle_##P##qr_blocked(T* A, i64 m, i64 n, i64 lda, T* tau, i64 bs,              \
+                                         int literal) {                                            \
+    qr_blocked<T>(A, m, n, lda, tau, bs, literal);                                                 \
+  }                                                                                                \
+  ORACLE_API void oracle_##P##build_T(const T* F, i64 m, i64 n, i64 ldf, const T* tau, T* Tm,      \
+                                      i64 ldt, int literal) {                                      \
+    build_T<T>(F, m, n, ldf, tau, Tm, ldt, literal);                                          \
+  }                                                                                                \
+  ORACLE_API int oracle_##P##block_apply(const T* V, i64 mV, i64 nV, i64 ldv, const T* Tm,         \
+                                         i64 ldt, T* A, i64 mA, i64 nA, i64 lda, int adjoint) {    \
+    return block_apply<T>(V, mV, nV, ldv, Tm, ldt, A, mA, nA, lda, adjoint);                       \
+  }                                                                                                \
+  ORACLE_API void oracle_##P##qr_batched(T* A, i64 m, i64 n, i64 batch, T* tau, i64 bs) {          \
+    i64 k = std::min(m, n);                                                                        \
+    _Pragma("omp parallel for schedule(static)") for (i64 b = 0; b < batch; ++b)                   \
+        qr_blocked<T>(A + b * m * n, m, n, m, tau + b * k, bs, 0);                                 \
+  }                                                                                                \
+  ORACLE_API void oracle_##P##rank_update_lower(T* C, i64 n, i64 ldc, const T* A, i64 k, i64 lda,  \
+                                                R alpha, int mt) {                                 \
+    if (mt) rank_update_lower_mt<T>(C, n, ldc, A, k, lda, alpha);                                  \
+    else rank_update_lower<T>(C, n, ldc, A, k, lda, alpha);                                        \
+  }                                                                                                \
+  ORACLE_API void oracle_##P##rdiv_lower_adjoint(T* X, i64 m, i64 n, i64 ldx, const T* L,          \
+                                                 i64 ldl) {                                        \
+    rdiv_lower_adjoint<T>(X, m, n, ldx, L, ldl);                                                   \
+  }                                                                                                \
+  ORACLE_API int oracle_##P##chol_unblocked(T* A, i64 n, i64 lda) {                                \
+    return chol_unblocked<T>(A, n, lda, 0);                                                        \
+  }                                                                                                \
+  ORACLE_API int oracle_##P##chol_blocked(T* A, i64 n, i64 lda, i64 bs) {                          \
+    return chol_blocked<T>(A, n, lda, bs);                                                         \
+  }                                                                                                \
+  ORACLE_API int oracle_##P##chol_recursive(T* A, i64 n, i64 lda, i64 cutoff, int mt) {            \
+    return chol_recursive<T>(A, n, lda, cutoff, 0, mt);                                            \
+  }
+
+DEFINE_TYPE(s, float, float)
+DEFINE_TYPE(d, double, double)
+DEFINE_TYPE(z, zd, double)
+
+ORACLE_API int oracle_version() { return 1; }
