@@ -1,0 +1,143 @@
+// common.cuh -- scalar traits, error plumbing and small device helpers shared by all kernels.
+// B200 / sm_100a only.  No CPU fallback lives anywhere in this library.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace gla {
+
+using i64 = int64_t;
+
+// ------------------------------------------------------------------ complex<double>
+struct __align__(16) zd {
+  double x, y;
+};
+
+__host__ __device__ __forceinline__ zd make_zd(double a, double b) {
+  zd r;
+  r.x = a;
+  r.y = b;
+  return r;
+}
+
+// ------------------------------------------------------------------ scalar traits
+template <class T>
+struct Sc;
+
+template <>
+struct Sc<float> {
+  using real = float;
+  static constexpr bool is_complex = false;
+  __host__ __device__ static float zero() { return 0.f; }
+  __host__ __device__ static float one() { return 1.f; }
+  __host__ __device__ static float from_real(float r) { return r; }
+};
+template <>
+struct Sc<double> {
+  using real = double;
+  static constexpr bool is_complex = false;
+  __host__ __device__ static double zero() { return 0.; }
+  __host__ __device__ static double one() { return 1.; }
+  __host__ __device__ static double from_real(double r) { return r; }
+};
+template <>
+struct Sc<zd> {
+  using real = double;
+  static constexpr bool is_complex = true;
+  __host__ __device__ static zd zero() { return make_zd(0., 0.); }
+  __host__ __device__ static zd one() { return make_zd(1., 0.); }
+  __host__ __device__ static zd from_real(double r) { return make_zd(r, 0.); }
+};
+
+// real types
+__host__ __device__ __forceinline__ float cj(float a) { return a; }
+__host__ __device__ __forceinline__ double cj(double a) { return a; }
+__host__ __device__ __forceinline__ float re(float a) { return a; }
+__host__ __device__ __forceinline__ double re(double a) { return a; }
+__host__ __device__ __forceinline__ float abs2(float a) { return a * a; }
+__host__ __device__ __forceinline__ double abs2(double a) { return a * a; }
+// fma: acc + a*b
+__device__ __forceinline__ float fmad(float a, float b, float acc) { return fmaf(a, b, acc); }
+__device__ __forceinline__ double fmad(double a, double b, double acc) { return fma(a, b, acc); }
+__host__ __device__ __forceinline__ float scale_real(float a, float r) { return a * r; }
+__host__ __device__ __forceinline__ double scale_real(double a, double r) { return a * r; }
+__host__ __device__ __forceinline__ bool is_zero(float a) { return a == 0.f; }
+__host__ __device__ __forceinline__ bool is_zero(double a) { return a == 0.; }
+
+// complex
+__host__ __device__ __forceinline__ zd cj(zd a) { return make_zd(a.x, -a.y); }
+__host__ __device__ __forceinline__ double re(zd a) { return a.x; }
+__host__ __device__ __forceinline__ double abs2(zd a) { return a.x * a.x + a.y * a.y; }
+__host__ __device__ __forceinline__ zd operator+(zd a, zd b) { return make_zd(a.x + b.x, a.y + b.y); }
+__host__ __device__ __forceinline__ zd operator-(zd a, zd b) { return make_zd(a.x - b.x, a.y - b.y); }
+__host__ __device__ __forceinline__ zd operator-(zd a) { return make_zd(-a.x, -a.y); }
+__host__ __device__ __forceinline__ zd operator*(zd a, zd b) {
+  return make_zd(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__host__ __device__ __forceinline__ zd& operator+=(zd& a, zd b) {
+  a.x += b.x;
+  a.y += b.y;
+  return a;
+}
+__host__ __device__ __forceinline__ zd& operator-=(zd& a, zd b) {
+  a.x -= b.x;
+  a.y -= b.y;
+  return a;
+}
+__device__ __forceinline__ zd fmad(zd a, zd b, zd acc) {
+  acc.x = fma(a.x, b.x, acc.x);
+  acc.x = fma(-a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y);
+  acc.y = fma(a.y, b.x, acc.y);
+  return acc;
+}
+__host__ __device__ __forceinline__ zd scale_real(zd a, double r) { return make_zd(a.x * r, a.y * r); }
+__host__ __device__ __forceinline__ bool is_zero(zd a) { return a.x == 0. && a.y == 0.; }
+// 1/z (Smith-free: inputs here are xi = alpha + nu with |xi| >= ||x||, never tiny relative to parts)
+__host__ __device__ __forceinline__ zd zinv(zd a) {
+  double d = 1.0 / (a.x * a.x + a.y * a.y);
+  return make_zd(a.x * d, -a.y * d);
+}
+__host__ __device__ __forceinline__ float inv(float a) { return 1.f / a; }
+__host__ __device__ __forceinline__ double inv(double a) { return 1. / a; }
+__host__ __device__ __forceinline__ zd inv(zd a) { return zinv(a); }
+
+// ------------------------------------------------------------------ warp helpers
+template <class R>
+__device__ __forceinline__ R warp_sum(R v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ zd warp_sum(zd v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+    v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+  }
+  return v;
+}
+
+// ------------------------------------------------------------------ errors
+void set_error(int code, const char* what, const char* file, int line);
+int check_cuda(cudaError_t e, const char* file, int line);
+
+#define GLA_CUDA(call)                                                   \
+  do {                                                                   \
+    int _rc = ::gla::check_cuda((call), __FILE__, __LINE__);             \
+    if (_rc) return _rc;                                                 \
+  } while (0)
+#define GLA_TRY(call)       \
+  do {                      \
+    int _rc = (call);       \
+    if (_rc) return _rc;    \
+  } while (0)
+
+inline int ceil_div(i64 a, i64 b) { return (int)((a + b - 1) / b); }
+inline i64 round_up(i64 a, i64 b) { return (a + b - 1) / b * b; }
+
+int sm_count();  // of the current device (cached)
+
+}  // namespace gla

@@ -1,0 +1,42 @@
+// context.cu -- error plumbing and per-thread library state (no global mutable state besides
+// lazily cached device properties).
+#include "common.cuh"
+
+#include <mutex>
+
+namespace gla {
+
+static thread_local char g_err[512] = "";
+thread_local double g_last_ms = 0.0;
+
+void set_error(int code, const char* what, const char* file, int line) {
+  snprintf(g_err, sizeof(g_err), "gla error %d: %s (%s:%d)", code, what, file, line);
+}
+
+int check_cuda(cudaError_t e, const char* file, int line) {
+  if (e == cudaSuccess) return 0;
+  int code = 1000 + (int)e;
+  set_error(code, cudaGetErrorString(e), file, line);
+  (void)cudaGetLastError();  // clear sticky-less errors
+  return code;
+}
+
+const char* last_error() { return g_err; }
+
+int sm_count() {
+  static std::mutex mu;
+  static int cached[64];
+  static bool have[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  std::lock_guard<std::mutex> lk(mu);
+  if (!have[dev]) {
+    int n = 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+    cached[dev] = n;
+    have[dev] = true;
+  }
+  return cached[dev];
+}
+
+}  // namespace gla

@@ -1,0 +1,38 @@
+// gla_internal.cuh -- device-level entry points behind the C ABI (all take device pointers).
+#pragma once
+#include "common.cuh"
+
+namespace gla {
+
+const char* last_error();
+extern thread_local double g_last_ms;
+
+// K4: batched small QR (batched_qr.cu)
+template <class T>
+int geqr_batched_dev(T* dA, i64 m, i64 n, i64 batch, T* dtau, cudaStream_t st);
+
+// K1/K2/K3: blocked QR of one large matrix (qr_blocked.cu)
+template <class T>
+int geqr_blocked_dev(T* dA, i64 m, i64 n, i64 lda, T* dtau, i64 blocksize_hint, cudaStream_t st);
+// compact-WY T of all k=min(m,n) reflectors; dT is k x k (ldt)
+template <class T>
+int larft_dev(const T* dF, i64 m, i64 n, i64 ldf, const T* dtau, T* dT, i64 ldt, cudaStream_t st);
+// A <- Q A (adjoint=0) or Q^H A (adjoint=1)
+template <class T>
+int ormqr_blocked_dev(const T* dF, i64 mF, i64 nF, i64 ldf, const T* dtau, T* dA, i64 mA, i64 nA,
+                      i64 lda, int adjoint, cudaStream_t st);
+template <class T>
+int reflector_apply_right_dev(T* dA, i64 m, i64 n, i64 lda, const T* dx, T tau, cudaStream_t st);
+
+// K5: TSQR (tsqr.cu)
+int tsqr_local_dev(const double* dA, i64 m, i64 n, i64 lda, double* dR, i64 ldr, cudaStream_t st);
+int tsqr_combine_dev(const double* dRs, i64 count, i64 n, double* dR, i64 ldr, cudaStream_t st);
+
+// K6: Cholesky (chol.cu)
+template <class T>
+int potrf_recursive_L_dev(T* dA, i64 n, i64 lda, i64 cutoff, int* dinfo, cudaStream_t st);
+template <class T>
+int herk_lower_dev(T* dC, i64 n, i64 ldc, const T* dA, i64 k, i64 lda, typename Sc<T>::real alpha,
+                   cudaStream_t st);
+
+}  // namespace gla

@@ -1,0 +1,97 @@
+// smallqr.cuh -- CTA-level Householder QR of a matrix resident in shared memory.
+// Used by the generic batched kernel, by the TSQR leaves/tree nodes and by the blocked driver
+// for panels that fit one CTA.
+//
+// Per column k (reference qrUnblocked!, src/qr.jl:86-111; stdlib reflector!/reflectorApply!
+// call sites src/qr.jl:96,102):
+//   every warp recomputes ||A[k:,k]||^2 with a shuffle reduction (no block barrier for the norm),
+//   warp w then owns columns k+1+w, k+1+w+W, ...: dot with the UN-normalised pivot column,
+//   s = conj(tau)*(a_kc + conj(1/xi)*d), a_kc -= s, a_ic -= a_ik*(s/xi); the pivot column is
+//   scaled by 1/xi one step later (after the single __syncthreads of the step) by all threads.
+#pragma once
+#include "common.cuh"
+
+namespace gla {
+
+constexpr int SMALLQR_THREADS = 256;
+
+template <class T>
+struct ReflScalars {
+  typename Sc<T>::real nu;  // copysign(norm, re(alpha))
+  T tau;                    // xi / nu
+  T ixi;                    // 1 / xi
+  bool nonzero;
+};
+
+// scalars of LinearAlgebra.reflector! from alpha = x[1] and n2 = ||x||^2
+template <class T>
+__device__ __forceinline__ ReflScalars<T> reflector_scalars(T alpha, typename Sc<T>::real n2) {
+  using R = typename Sc<T>::real;
+  ReflScalars<T> r;
+  r.nonzero = n2 != R(0);
+  if (!r.nonzero) {
+    r.nu = R(0);
+    r.tau = Sc<T>::zero();
+    r.ixi = Sc<T>::one();
+    return r;
+  }
+  R nrm = sqrt(n2);
+  r.nu = copysign(nrm, re(alpha));
+  T xi = alpha + Sc<T>::from_real(r.nu);
+  r.tau = scale_real(xi, R(1) / r.nu);
+  r.ixi = inv(xi);
+  return r;
+}
+
+// A: shared memory, column-major m x n, leading dimension ld.  tau: global (may be nullptr).
+// All threads of the CTA must call; blockDim.x must be a multiple of 32.
+template <class T>
+__device__ void cta_qr_smem(T* sA, int m, int n, int ld, T* tau) {
+  using R = typename Sc<T>::real;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  const int kmax = m < n ? m : n;
+  T prev_ixi = Sc<T>::one();
+  R prev_nu = R(0);
+  bool prev_nonzero = false;
+  for (int k = 0; k <= kmax; ++k) {
+    __syncthreads();  // the single barrier of the step: updates of step k-1 are visible
+    // deferred finish of pivot column k-1 (nobody reads it any more): diagonal <- -nu, rows below *= 1/xi
+    if (prev_nonzero) {
+      T* col = sA + (k - 1) * ld;
+      for (int i = k + threadIdx.x; i < m; i += blockDim.x) col[i] = col[i] * prev_ixi;
+      if (threadIdx.x == 0) col[k - 1] = Sc<T>::from_real(-prev_nu);
+    }
+    if (k == kmax) break;
+    const T* ck = sA + k * ld;
+    R part = R(0);
+    for (int i = k + 1 + lane; i < m; i += 32) part += abs2(ck[i]);
+    part = warp_sum(part);
+    const T alpha = ck[k];
+    const R n2 = abs2(alpha) + part;
+    const ReflScalars<T> rs = reflector_scalars<T>(alpha, n2);
+    prev_nonzero = rs.nonzero;
+    prev_ixi = rs.ixi;
+    prev_nu = rs.nu;
+    if (tau && threadIdx.x == 0) tau[k] = rs.tau;
+    if (rs.nonzero) {
+      const T ctau = cj(rs.tau);
+      const T cixi = cj(rs.ixi);
+      for (int c = k + 1 + warp; c < n; c += nwarps) {
+        T* cc = sA + c * ld;
+        T d = Sc<T>::zero();
+        for (int i = k + 1 + lane; i < m; i += 32) d = fmad(cj(ck[i]), cc[i], d);
+        d = warp_sum(d);
+        const T s = ctau * (cc[k] + cixi * d);
+        const T t = s * rs.ixi;
+        for (int i = k + 1 + lane; i < m; i += 32) cc[i] = cc[i] - ck[i] * t;
+        __syncwarp();  // every lane has read cc[k] before lane 0 overwrites it
+        if (lane == 0) cc[k] = cc[k] - s;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+}  // namespace gla

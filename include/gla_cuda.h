@@ -1,0 +1,136 @@
+/* gla_cuda.h -- C ABI of libgla_cuda.so: the B200 (sm_100a) Householder-QR / Cholesky-update
+ * hot path of GenericLinearAlgebra.jl.
+ *
+ * Every entry point replaces one reference interface (citations are file:line into the
+ * reference tree, GenericLinearAlgebra.jl v0.4.0).  A Julia host reaches them with `ccall`
+ * (see INTEGRATION.md and genericlinearalgebra.jl_b200/julia/GLACuda.jl); the Python
+ * ctypes mirror used by tests/bench is genericlinearalgebra.jl_b200/glacuda.py.
+ *
+ * Conventions
+ *  - matrices are column-major with unit row stride, leading dimension `lda` in ELEMENTS,
+ *    complex is interleaved (re,im) == Julia ComplexF64 == C `double _Complex`;
+ *  - results are written in place exactly as the reference leaves them:
+ *      QR:   R in the upper triangle incl. diagonal, Householder vectors below it (implicit
+ *            unit leading 1), tau[0..min(m,n));  sign/tau convention of Julia's
+ *            LinearAlgebra.reflector!: R[k,k] = -copysign(||x||, Re x1), a length-1 column
+ *            is still reflected (tau = 2);
+ *      Chol: lower triangle incl. diagonal; the strict upper triangle is NOT touched;
+ *  - prefix s/d/z = Float32 / Float64 / ComplexF64;
+ *  - plain functions take HOST pointers and are synchronous (H2D, compute, D2H inside);
+ *    `_dev` twins take DEVICE pointers plus a cudaStream_t (passed as void*) and are
+ *    asynchronous on that stream;
+ *  - return value: 0 ok; -k = k-th argument illegal (shim throws DimensionMismatch /
+ *    ArgumentError); +k from potrf = leading minor k not positive definite (shim throws
+ *    DomainError, like sqrt of a negative real at src/cholesky.jl:40); >= 1000 = CUDA/NCCL
+ *    runtime failure, text via gla_last_error_string().
+ *  - there is NO CPU fallback anywhere in this library.
+ */
+#ifndef GLA_CUDA_H
+#define GLA_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define GLA_API __attribute__((visibility("default")))
+#else
+#define GLA_API
+#endif
+
+#define GLA_ERR_CUDA 1000
+#define GLA_ERR_NCCL 2000
+
+/* ---- library ------------------------------------------------------------------- */
+GLA_API int gla_version(void);                       /* 100*major + minor */
+GLA_API int gla_device_count(void);                  /* number of visible CUDA devices, <0 on error */
+GLA_API const char* gla_last_error_string(void);     /* thread-local text of the last >=1000 error */
+GLA_API int gla_set_device(int device);              /* device used by host-pointer entry points */
+/* average device time (ms) of the compute part of the last host-pointer call on this thread */
+GLA_API double gla_last_device_ms(void);
+
+/* ---- blocked Householder QR ------------------------------------------------------
+ * replaces GenericLinearAlgebra.qrBlocked!(A, blocksize, tau, work)   src/qr.jl:113-146
+ * (panel = qrUnblocked! src/qr.jl:86-111 with stdlib reflector!/reflectorApply! call sites
+ * src/qr.jl:96,102; T build src/qr.jl:64-83; trailing update src/householder.jl:119-157).
+ * `blocksize_hint` <= 0 lets the library choose; results do not depend on it beyond rounding. */
+GLA_API int gla_sgeqr_blocked(float* A, int64_t m, int64_t n, int64_t lda, float* tau, int64_t blocksize_hint);
+GLA_API int gla_dgeqr_blocked(double* A, int64_t m, int64_t n, int64_t lda, double* tau, int64_t blocksize_hint);
+GLA_API int gla_zgeqr_blocked(void* A, int64_t m, int64_t n, int64_t lda, void* tau, int64_t blocksize_hint);
+GLA_API int gla_sgeqr_blocked_dev(float* dA, int64_t m, int64_t n, int64_t lda, float* dtau, int64_t blocksize_hint, void* stream);
+GLA_API int gla_dgeqr_blocked_dev(double* dA, int64_t m, int64_t n, int64_t lda, double* dtau, int64_t blocksize_hint, void* stream);
+GLA_API int gla_zgeqr_blocked_dev(void* dA, int64_t m, int64_t n, int64_t lda, void* dtau, int64_t blocksize_hint, void* stream);
+
+/* ---- compact-WY T factor ---------------------------------------------------------
+ * replaces getindex(::QR2, Tuple{:QBlocked})   src/qr.jl:64-83  (with the conj the reference
+ * omits at :72 for complex types).  F = factors (m x n, V below the diagonal), tau[k],
+ * k = min(m,n); T is k x k upper triangular, ldt >= k, strict lower part set to zero. */
+GLA_API int gla_slarft(const float* F, int64_t m, int64_t n, int64_t ldf, const float* tau, float* T, int64_t ldt);
+GLA_API int gla_dlarft(const double* F, int64_t m, int64_t n, int64_t ldf, const double* tau, double* T, int64_t ldt);
+GLA_API int gla_zlarft(const void* F, int64_t m, int64_t n, int64_t ldf, const void* tau, void* T, int64_t ldt);
+
+/* ---- block reflector application ---------------------------------------------------
+ * replaces lmul!(H, A, M) (adjoint = 0, A <- Q A, src/householder.jl:82-115) and
+ * lmul!(H', A, M) (adjoint = 1, A <- Q^H A, src/householder.jl:119-157) where
+ * H = HouseholderBlock(F, T) built from all k = min(mF,nF) reflectors of F.
+ * returns -1..: DimensionMismatch when mF != mA (src/householder.jl:87,129). */
+GLA_API int gla_sormqr_blocked(const float* F, int64_t mF, int64_t nF, int64_t ldf, const float* tau, float* A, int64_t mA, int64_t nA, int64_t lda, int adjoint);
+GLA_API int gla_dormqr_blocked(const double* F, int64_t mF, int64_t nF, int64_t ldf, const double* tau, double* A, int64_t mA, int64_t nA, int64_t lda, int adjoint);
+GLA_API int gla_zormqr_blocked(const void* F, int64_t mF, int64_t nF, int64_t ldf, const void* tau, void* A, int64_t mA, int64_t nA, int64_t lda, int adjoint);
+
+/* ---- right reflector application ---------------------------------------------------
+ * replaces reflectorApply!(A, x, tau)   src/qr.jl:19-42   A <- A (I - tau v v^H), v = [1; x[2:]]
+ * returns -5 when lenx != n (DimensionMismatch at src/qr.jl:21-27). tau passed by pointer. */
+GLA_API int gla_sreflector_apply_right(float* A, int64_t m, int64_t n, int64_t lda, const float* x, int64_t lenx, const float* tau);
+GLA_API int gla_dreflector_apply_right(double* A, int64_t m, int64_t n, int64_t lda, const double* x, int64_t lenx, const double* tau);
+GLA_API int gla_zreflector_apply_right(void* A, int64_t m, int64_t n, int64_t lda, const void* x, int64_t lenx, const void* tau);
+
+/* ---- batched small QR --------------------------------------------------------------
+ * `batch` independent qrBlocked! problems (src/qr.jl:113-146 per matrix); matrices are
+ * contiguous, column-major, stride m*n elements; tau has stride min(m,n).
+ * 32x32 real runs register-resident, one matrix per warp; other shapes with
+ * m*n*sizeof(T) <= 96 KiB run one matrix per CTA in shared memory. */
+GLA_API int gla_sgeqr_batched(float* A, int64_t m, int64_t n, int64_t batch, float* tau);
+GLA_API int gla_dgeqr_batched(double* A, int64_t m, int64_t n, int64_t batch, double* tau);
+GLA_API int gla_zgeqr_batched(void* A, int64_t m, int64_t n, int64_t batch, void* tau);
+GLA_API int gla_sgeqr_batched_dev(float* dA, int64_t m, int64_t n, int64_t batch, float* dtau, void* stream);
+GLA_API int gla_dgeqr_batched_dev(double* dA, int64_t m, int64_t n, int64_t batch, double* dtau, void* stream);
+GLA_API int gla_zgeqr_batched_dev(void* dA, int64_t m, int64_t n, int64_t batch, void* dtau, void* stream);
+
+/* ---- tall-skinny QR (R factor only) -------------------------------------------------
+ * the R that qrBlocked! (src/qr.jl:113-146) would leave in the upper triangle of a tall
+ * m x n matrix (n <= 64), computed by a TSQR tree.  R (n x n, ldr >= n, upper, strict lower
+ * zeroed) is normalised to the reference's sign convention row by row only in the sense
+ * documented in DESIGN.md ("TSQR sign"): diag(R) <= 0 is NOT guaranteed to match the
+ * sequential Householder signs; parity tests compare after row-phase normalisation.
+ *   gla_dtsqr_local_dev : one row block -> its n x n R factor (no communication)
+ *   gla_dtsqr_combine_dev: `count` stacked R factors (each n x n, ld n) -> one R
+ *   gla_dtsqr           : host pointers, single GPU. */
+GLA_API int gla_dtsqr_local_dev(const double* dA, int64_t m, int64_t n, int64_t lda, double* dR, int64_t ldr, void* stream);
+GLA_API int gla_dtsqr_combine_dev(const double* dRstack, int64_t count, int64_t n, double* dR, int64_t ldr, void* stream);
+GLA_API int gla_dtsqr(const double* A, int64_t m, int64_t n, int64_t lda, double* R, int64_t ldr);
+
+/* ---- recursive Cholesky, lower ------------------------------------------------------
+ * replaces cholRecursive!(A, Val{:L}, cutoff)   src/cholesky.jl:37-55
+ * (trsm = rdiv!(A21, LowerTriangular(A11)') at :48; rank-k update = rankUpdate! at :51 ->
+ * src/juliaBLAS.jl:89-112).  `cutoff` is accepted as a hint. */
+GLA_API int gla_spotrf_recursive_L(float* A, int64_t n, int64_t lda, int64_t cutoff);
+GLA_API int gla_dpotrf_recursive_L(double* A, int64_t n, int64_t lda, int64_t cutoff);
+GLA_API int gla_zpotrf_recursive_L(void* A, int64_t n, int64_t lda, int64_t cutoff);
+GLA_API int gla_spotrf_recursive_L_dev(float* dA, int64_t n, int64_t lda, int64_t cutoff, int* dinfo, void* stream);
+GLA_API int gla_dpotrf_recursive_L_dev(double* dA, int64_t n, int64_t lda, int64_t cutoff, int* dinfo, void* stream);
+GLA_API int gla_zpotrf_recursive_L_dev(void* dA, int64_t n, int64_t lda, int64_t cutoff, int* dinfo, void* stream);
+
+/* ---- Hermitian rank-k update, lower ---------------------------------------------------
+ * replaces rankUpdate!(Hermitian(C,:L), A, alpha)   src/juliaBLAS.jl:89-112
+ * C (n x n, lower triangle only) += alpha * A * A^H,  A is n x k.  alpha is real. */
+GLA_API int gla_ssyrk_lower(float* C, int64_t n, int64_t ldc, const float* A, int64_t k, int64_t lda, float alpha);
+GLA_API int gla_dsyrk_lower(double* C, int64_t n, int64_t ldc, const double* A, int64_t k, int64_t lda, double alpha);
+GLA_API int gla_zherk_lower(void* C, int64_t n, int64_t ldc, const void* A, int64_t k, int64_t lda, double alpha);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLA_CUDA_H */
