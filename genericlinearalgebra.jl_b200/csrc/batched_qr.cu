@@ -264,11 +264,7 @@ static int launch_reg32(R* dA, R* dtau, i64 batch, cudaStream_t st) {
   constexpr int WARPS = 4;
   size_t smem = (size_t)WARPS * Reg32Cfg<R>::TILE * sizeof(R);
   auto kern = batched_qr32_reg_kernel<R, WARPS>;
-  static thread_local bool configured = false;
-  if (!configured) {
-    GLA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  GLA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
   GLA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem));
   if (occ < 1) occ = 1;

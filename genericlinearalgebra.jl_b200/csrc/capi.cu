@@ -99,6 +99,116 @@ int geqr_batched_host(T* A, i64 m, i64 n, i64 batch, T* tau) {
   return 0;
 }
 
+// ------------------------------------------------------------------ device copy of a host matrix
+// ld is padded to an even number of elements (16-byte column alignment for TMA / vector access)
+template <class T>
+struct DevMatrix {
+  DevBuf buf;
+  i64 ld = 0;
+  T* p() { return buf.as<T>(); }
+  int upload(const T* h, i64 ldh, i64 m, i64 n, cudaStream_t st) {
+    ld = round_up(m > 0 ? m : 1, 16 / sizeof(T) > 2 ? 16 / sizeof(T) : 2);
+    GLA_TRY(buf.alloc((size_t)ld * (n > 0 ? n : 1) * sizeof(T)));
+    return h2d_matrix<T>(p(), ld, h, ldh, m, n, st);
+  }
+  int download(T* h, i64 ldh, i64 m, i64 n, cudaStream_t st) { return d2h_matrix<T>(h, ldh, p(), ld, m, n, st); }
+};
+
+template <class T>
+int geqr_blocked_host(T* A, i64 m, i64 n, i64 lda, T* tau, i64 hint) {
+  if (m < 0) return -2;
+  if (n < 0) return -3;
+  if (lda < (m > 1 ? m : 1)) return -4;
+  if (m == 0 || n == 0) return 0;
+  if (!A) return -1;
+  if (!tau) return -5;
+  const i64 k = m < n ? m : n;
+  Stream st;
+  GLA_TRY(st.create());
+  DevMatrix<T> dA;
+  DevBuf dtau;
+  GLA_TRY(dA.upload(A, lda, m, n, st.s));
+  GLA_TRY(dtau.alloc(k * sizeof(T)));
+  GLA_CUDA(cudaMemsetAsync(dtau.p, 0, k * sizeof(T), st.s));
+  Event e0, e1;
+  GLA_TRY(e0.create());
+  GLA_TRY(e1.create());
+  GLA_CUDA(cudaEventRecord(e0.e, st.s));
+  GLA_TRY(geqr_blocked_dev<T>(dA.p(), m, n, dA.ld, dtau.as<T>(), hint, st.s));
+  GLA_CUDA(cudaEventRecord(e1.e, st.s));
+  GLA_TRY(dA.download(A, lda, m, n, st.s));
+  GLA_CUDA(cudaMemcpyAsync(tau, dtau.p, k * sizeof(T), cudaMemcpyDeviceToHost, st.s));
+  GLA_CUDA(cudaStreamSynchronize(st.s));
+  float ms = 0;
+  GLA_CUDA(cudaEventElapsedTime(&ms, e0.e, e1.e));
+  g_last_ms = ms;
+  return 0;
+}
+
+template <class T>
+int larft_host(const T* F, i64 m, i64 n, i64 ldf, const T* tau, T* Tm, i64 ldt) {
+  if (m < 0) return -2;
+  if (n < 0) return -3;
+  if (ldf < (m > 1 ? m : 1)) return -4;
+  const i64 k = m < n ? m : n;
+  if (k == 0) return 0;
+  if (ldt < k) return -7;
+  Stream st;
+  GLA_TRY(st.create());
+  DevMatrix<T> dF, dT;
+  DevBuf dtau;
+  GLA_TRY(dF.upload(F, ldf, m, n, st.s));
+  GLA_TRY(dtau.alloc(k * sizeof(T)));
+  GLA_CUDA(cudaMemcpyAsync(dtau.p, tau, k * sizeof(T), cudaMemcpyHostToDevice, st.s));
+  dT.ld = round_up(k, 2);
+  GLA_TRY(dT.buf.alloc((size_t)dT.ld * k * sizeof(T)));
+  GLA_TRY(larft_dev<T>(dF.p(), m, n, dF.ld, dtau.as<T>(), dT.p(), dT.ld, st.s));
+  GLA_TRY(dT.download(Tm, ldt, k, k, st.s));
+  GLA_CUDA(cudaStreamSynchronize(st.s));
+  return 0;
+}
+
+template <class T>
+int ormqr_host(const T* F, i64 mF, i64 nF, i64 ldf, const T* tau, T* A, i64 mA, i64 nA, i64 lda, int adjoint) {
+  if (mF < 0) return -2;
+  if (nF < 0) return -3;
+  if (mA != mF) return -7;
+  if (nA < 0) return -8;
+  const i64 k = mF < nF ? mF : nF;
+  if (k == 0 || nA == 0 || mA == 0) return 0;
+  Stream st;
+  GLA_TRY(st.create());
+  DevMatrix<T> dF, dA;
+  DevBuf dtau;
+  GLA_TRY(dF.upload(F, ldf, mF, nF, st.s));
+  GLA_TRY(dA.upload(A, lda, mA, nA, st.s));
+  GLA_TRY(dtau.alloc(k * sizeof(T)));
+  GLA_CUDA(cudaMemcpyAsync(dtau.p, tau, k * sizeof(T), cudaMemcpyHostToDevice, st.s));
+  GLA_TRY(ormqr_blocked_dev<T>(dF.p(), mF, nF, dF.ld, dtau.as<T>(), dA.p(), mA, nA, dA.ld, adjoint, st.s));
+  GLA_TRY(dA.download(A, lda, mA, nA, st.s));
+  GLA_CUDA(cudaStreamSynchronize(st.s));
+  return 0;
+}
+
+template <class T>
+int reflector_apply_right_host(T* A, i64 m, i64 n, i64 lda, const T* x, i64 lenx, const T* tau) {
+  if (m < 0) return -2;
+  if (n < 0) return -3;
+  if (lenx != n) return -5;  // DimensionMismatch, src/qr.jl:21-27
+  if (m == 0 || n == 0) return 0;
+  Stream st;
+  GLA_TRY(st.create());
+  DevMatrix<T> dA;
+  DevBuf dx;
+  GLA_TRY(dA.upload(A, lda, m, n, st.s));
+  GLA_TRY(dx.alloc(n * sizeof(T)));
+  GLA_CUDA(cudaMemcpyAsync(dx.p, x, n * sizeof(T), cudaMemcpyHostToDevice, st.s));
+  GLA_TRY(reflector_apply_right_dev<T>(dA.p(), m, n, dA.ld, dx.as<T>(), *tau, st.s));
+  GLA_TRY(dA.download(A, lda, m, n, st.s));
+  GLA_CUDA(cudaStreamSynchronize(st.s));
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -144,5 +254,31 @@ int gla_zgeqr_batched_dev(void* dA, int64_t m, int64_t n, int64_t batch, void* d
   return geqr_batched_dev<zd>(static_cast<zd*>(dA), m, n, batch, static_cast<zd*>(dtau),
                               static_cast<cudaStream_t>(stream));
 }
+
+// ---- blocked QR
+#define ZP(p) static_cast<zd*>(p)
+#define ZCP(p) static_cast<const zd*>(p)
+#define STREAM(s) static_cast<cudaStream_t>(s)
+int gla_sgeqr_blocked(float* A, int64_t m, int64_t n, int64_t lda, float* tau, int64_t hint) { return geqr_blocked_host<float>(A, m, n, lda, tau, hint); }
+int gla_dgeqr_blocked(double* A, int64_t m, int64_t n, int64_t lda, double* tau, int64_t hint) { return geqr_blocked_host<double>(A, m, n, lda, tau, hint); }
+int gla_zgeqr_blocked(void* A, int64_t m, int64_t n, int64_t lda, void* tau, int64_t hint) { return geqr_blocked_host<zd>(ZP(A), m, n, lda, ZP(tau), hint); }
+int gla_sgeqr_blocked_dev(float* dA, int64_t m, int64_t n, int64_t lda, float* dtau, int64_t hint, void* stream) { return geqr_blocked_dev<float>(dA, m, n, lda, dtau, hint, STREAM(stream)); }
+int gla_dgeqr_blocked_dev(double* dA, int64_t m, int64_t n, int64_t lda, double* dtau, int64_t hint, void* stream) { return geqr_blocked_dev<double>(dA, m, n, lda, dtau, hint, STREAM(stream)); }
+int gla_zgeqr_blocked_dev(void* dA, int64_t m, int64_t n, int64_t lda, void* dtau, int64_t hint, void* stream) { return geqr_blocked_dev<zd>(ZP(dA), m, n, lda, ZP(dtau), hint, STREAM(stream)); }
+
+// ---- T factor
+int gla_slarft(const float* F, int64_t m, int64_t n, int64_t ldf, const float* tau, float* T, int64_t ldt) { return larft_host<float>(F, m, n, ldf, tau, T, ldt); }
+int gla_dlarft(const double* F, int64_t m, int64_t n, int64_t ldf, const double* tau, double* T, int64_t ldt) { return larft_host<double>(F, m, n, ldf, tau, T, ldt); }
+int gla_zlarft(const void* F, int64_t m, int64_t n, int64_t ldf, const void* tau, void* T, int64_t ldt) { return larft_host<zd>(ZCP(F), m, n, ldf, ZCP(tau), ZP(T), ldt); }
+
+// ---- block reflector application
+int gla_sormqr_blocked(const float* F, int64_t mF, int64_t nF, int64_t ldf, const float* tau, float* A, int64_t mA, int64_t nA, int64_t lda, int adjoint) { return ormqr_host<float>(F, mF, nF, ldf, tau, A, mA, nA, lda, adjoint); }
+int gla_dormqr_blocked(const double* F, int64_t mF, int64_t nF, int64_t ldf, const double* tau, double* A, int64_t mA, int64_t nA, int64_t lda, int adjoint) { return ormqr_host<double>(F, mF, nF, ldf, tau, A, mA, nA, lda, adjoint); }
+int gla_zormqr_blocked(const void* F, int64_t mF, int64_t nF, int64_t ldf, const void* tau, void* A, int64_t mA, int64_t nA, int64_t lda, int adjoint) { return ormqr_host<zd>(ZCP(F), mF, nF, ldf, ZCP(tau), ZP(A), mA, nA, lda, adjoint); }
+
+// ---- right reflector application
+int gla_sreflector_apply_right(float* A, int64_t m, int64_t n, int64_t lda, const float* x, int64_t lenx, const float* tau) { return reflector_apply_right_host<float>(A, m, n, lda, x, lenx, tau); }
+int gla_dreflector_apply_right(double* A, int64_t m, int64_t n, int64_t lda, const double* x, int64_t lenx, const double* tau) { return reflector_apply_right_host<double>(A, m, n, lda, x, lenx, tau); }
+int gla_zreflector_apply_right(void* A, int64_t m, int64_t n, int64_t lda, const void* x, int64_t lenx, const void* tau) { return reflector_apply_right_host<zd>(ZP(A), m, n, lda, ZCP(x), lenx, ZCP(tau)); }
 
 }  // extern "C"

@@ -120,6 +120,9 @@ __device__ __forceinline__ zd warp_sum(zd v) {
   return v;
 }
 
+constexpr int GLA_ERR_DRIVER = 1900;   // driver entry point / tensor-map encode failure
+constexpr int GLA_ERR_INTERNAL = 1901; // internal invariant violated
+
 // ------------------------------------------------------------------ errors
 void set_error(int code, const char* what, const char* file, int line);
 int check_cuda(cudaError_t e, const char* file, int line);

@@ -1,0 +1,397 @@
+// gemm.cu -- K3: the TN contraction behind every trailing update (see gemm.cuh).
+//
+// Float64 fast path (gemm_tn_dmma_kernel):
+//   * operands arrive by TMA: one cp.async.bulk.tensor.2d per operand per stage, box = 16 doubles of
+//     K (128 B, the swizzle span) x BM / BN rows, CU_TENSOR_MAP_SWIZZLE_128B, completion on an
+//     mbarrier (complete_tx); a dedicated producer warp runs STAGES slabs ahead of the consumers and
+//     re-arms a slot when every consumer warp has arrived on its `empty` barrier;
+//   * consumers issue mma.sync.aligned.m8n8k4.f64 (SASS DMMA.8x8x4) on 32x32 warp tiles, fragments
+//     read straight from the swizzled tile with LDS.64.  MMA row g of block b is mapped to tile row
+//     16*(b/2) + 2g + (b%2): with that interleave the 16 lanes of a half-warp hit 16 distinct 8-byte
+//     slots of the 128 B swizzle span (conflict free), and each thread ends up owning 2 consecutive
+//     rows x 4 consecutive columns of C, so the epilogue is 16-byte coalesced read-modify-write of
+//     full 128 B lines with no shared-memory staging;
+//   * out-of-range rows / K tails are zero-filled by TMA, the epilogue masks M/N edges.
+#include "gemm.cuh"
+
+#include <cuda.h>
+#include <mutex>
+
+namespace gla {
+
+// ------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
+// ------------------------------------------------------------------------------- DMMA + TMA kernel
+template <int BM, int BN, int STAGES>
+struct DmmaCfg {
+  static constexpr int WM = BM / 32, WN = BN / 32, NCW = WM * WN;
+  static constexpr int THREADS = NCW * 32 + 32;
+  static constexpr int STAGE_BYTES = (BM + BN) * 128;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 1024;
+};
+
+template <int BM, int BN, int STAGES>
+__global__ void __maxnreg__(112)
+    gemm_tn_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                        double* __restrict__ C, i64 ldc, int M, int N, int K, int klen, i64 split_stride,
+                        double alpha, int beta_one, int lower_only, int vec_ok) {
+  using Cfg = DmmaCfg<BM, BN, STAGES>;
+  constexpr int WM = Cfg::WM, NCW = Cfg::NCW;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* sA = base;
+  unsigned char* sB = base + STAGES * BM * 128;
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  if (lower_only && n0 >= m0 + BM) return;  // tile strictly above the diagonal
+  const int kbeg = blockIdx.z * klen;
+  const int kend = (kbeg + klen < K) ? kbeg + klen : K;
+  const int nk = (kend - kbeg + 15) >> 4;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], NCW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == NCW) {  // ---- TMA producer warp
+    if (lane == 0) {
+      for (int it = 0; it < nk; ++it) {
+        const int s = it % STAGES;
+        if (it >= STAGES) mbar_wait(&empty[s], ((it / STAGES) - 1) & 1);
+        mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+        tma_load_2d(sA + s * BM * 128, &tmA, kbeg + it * 16, m0, &full[s]);
+        tma_load_2d(sB + s * BN * 128, &tmB, kbeg + it * 16, n0, &full[s]);
+      }
+    }
+    return;
+  }
+
+  // ---- consumers: 32x32 warp tile = 4 x 4 DMMA blocks
+  const int wm = warp % WM, wn = warp / WM;
+  const int g = lane >> 2, t = lane & 3;
+  double acc[4][4][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+  // byte offset of tile row for DMMA block b, lane row g:  row = 16*(b/2) + 2g + (b%2)
+  int rowoff[4], key[4];
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const int r = 16 * (b >> 1) + 2 * g + (b & 1);
+    rowoff[b] = r * 128;
+    key[b] = r & 7;
+  }
+  const int tlo = (t & 1) << 3, thi = t >> 1;
+
+  for (int it = 0; it < nk; ++it) {
+    const int s = it % STAGES;
+    mbar_wait(&full[s], (it / STAGES) & 1);
+    const unsigned char* pa = sA + s * BM * 128 + wm * 32 * 128;
+    const unsigned char* pb = sB + s * BN * 128 + wn * 32 * 128;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double a[4], b[4];
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        const int off = rowoff[x] + ((((2 * j + thi) ^ key[x]) << 4) | tlo);
+        a[x] = *reinterpret_cast<const double*>(pa + off);
+        b[x] = *reinterpret_cast<const double*>(pb + off);
+      }
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) dmma884(acc[x][y], a[x], b[y]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
+
+  // ---- epilogue: thread owns rows i0,i0+1 x 4 consecutive columns per (P,Q)
+  double* Cz = C + (i64)blockIdx.z * split_stride;
+#pragma unroll
+  for (int P = 0; P < 2; ++P) {
+    const int i0 = m0 + wm * 32 + 16 * P + 2 * g;
+    if (i0 >= M) continue;
+    const bool two = i0 + 1 < M;
+#pragma unroll
+    for (int Q = 0; Q < 2; ++Q) {
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {  // column within the 4: cc = 2c + e
+        const int c = cc >> 1, e = cc & 1;
+        const int j = n0 + wn * 32 + 16 * Q + 4 * t + cc;
+        if (j >= N) continue;
+        double v0 = alpha * acc[2 * P][2 * Q + e][c];
+        double v1 = alpha * acc[2 * P + 1][2 * Q + e][c];
+        double* p = Cz + (i64)j * ldc + i0;
+        const bool w0 = !lower_only || i0 >= j;
+        const bool w1 = two && (!lower_only || i0 + 1 >= j);
+        if (vec_ok && w0 && w1) {
+          double2* pv = reinterpret_cast<double2*>(p);
+          if (beta_one) {
+            double2 o = *pv;
+            v0 += o.x;
+            v1 += o.y;
+          }
+          *pv = make_double2(v0, v1);
+        } else {
+          if (w0) p[0] = beta_one ? p[0] + v0 : v0;
+          if (w1) p[1] = beta_one ? p[1] + v1 : v1;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------- generic FMA kernel
+// 64x64 tile, 16-deep K slabs, 256 threads, 4x4 outputs per thread.
+template <class T>
+__global__ void __launch_bounds__(256)
+    gemm_tn_fma_kernel(const T* __restrict__ At, i64 ldat, const T* __restrict__ B, i64 ldb, T* __restrict__ C,
+                       i64 ldc, int M, int N, int K, int klen, i64 split_stride, typename Sc<T>::real alpha,
+                       int beta_one, int conj_a, int lower_only) {
+  __shared__ T sA[16][64 + 1];
+  __shared__ T sB[16][64 + 1];
+  const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+  if (lower_only && n0 >= m0 + 64) return;
+  const int kbeg = blockIdx.z * klen;
+  const int kend = (kbeg + klen < K) ? kbeg + klen : K;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // tx -> rows (M), ty -> cols (N)
+  T acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = Sc<T>::zero();
+  const int lk = threadIdx.x & 15, lr = threadIdx.x >> 4;  // loader: k index, row group
+  for (int k0 = kbeg; k0 < kend; k0 += 16) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = lr + 16 * r;
+      const int k = k0 + lk;
+      T va = Sc<T>::zero(), vb = Sc<T>::zero();
+      if (k < kend && m0 + i < M) va = At[(i64)(m0 + i) * ldat + k];
+      if (k < kend && n0 + i < N) vb = B[(i64)(n0 + i) * ldb + k];
+      sA[lk][i] = conj_a ? cj(va) : va;
+      sB[lk][i] = vb;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      T a[4], b[4];
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        a[x] = sA[k][tx + 16 * x];
+        b[x] = sB[k][ty + 16 * x];
+      }
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) acc[x][y] = fmad(a[x], b[y], acc[x][y]);
+    }
+    __syncthreads();
+  }
+  T* Cz = C + (i64)blockIdx.z * split_stride;
+#pragma unroll
+  for (int y = 0; y < 4; ++y) {
+    const int j = n0 + ty + 16 * y;
+    if (j >= N) continue;
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+      const int i = m0 + tx + 16 * x;
+      if (i >= M) continue;
+      if (lower_only && i < j) continue;
+      T v = scale_real(acc[x][y], alpha);
+      T* p = Cz + (i64)j * ldc + i;
+      *p = beta_one ? *p + v : v;
+    }
+  }
+}
+
+template <class T>
+__global__ void sum_splits_kernel(T* __restrict__ out, i64 ldo, const T* __restrict__ part, i64 ldp, i64 stride,
+                                  int nsplit, i64 M, i64 N) {
+  const i64 total = M * N;
+  for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
+    const i64 j = e / M, i = e - j * M;
+    T s = part[j * ldp + i];
+    for (int z = 1; z < nsplit; ++z) s = s + part[(i64)z * stride + j * ldp + i];
+    out[j * ldo + i] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------- host side
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static std::mutex mu;
+  static EncodeTiledFn fn = nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// K x R column-major f64 operand (K contiguous), box = 16 x rows
+int make_map(CUtensorMap* tm, const double* base, i64 K, i64 R, i64 ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error(GLA_ERR_DRIVER, "cuTensorMapEncodeTiled entry point unavailable", __FILE__, __LINE__);
+    return GLA_ERR_DRIVER;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)R};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+  cuuint32_t box[2] = {16, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[128];
+    snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled failed (CUresult %d, K=%lld R=%lld ld=%lld)", (int)r,
+             (long long)K, (long long)R, (long long)ld);
+    set_error(GLA_ERR_DRIVER, msg, __FILE__, __LINE__);
+    return GLA_ERR_DRIVER;
+  }
+  return 0;
+}
+
+template <int BM, int BN, int STAGES>
+int launch_dmma(const GemmTN<double>& g, int klen, cudaStream_t st) {
+  using Cfg = DmmaCfg<BM, BN, STAGES>;
+  CUtensorMap tmA, tmB;
+  GLA_TRY(make_map(&tmA, g.At, g.K, g.M, g.ldat, BM));
+  GLA_TRY(make_map(&tmB, g.B, g.K, g.N, g.ldb, BN));
+  auto kern = gemm_tn_dmma_kernel<BM, BN, STAGES>;
+  GLA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+  dim3 grid((unsigned)ceil_div(g.M, BM), (unsigned)ceil_div(g.N, BN), (unsigned)g.nsplit);
+  const int vec_ok = ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0 && (g.ldc & 1) == 0 &&
+                      ((g.split_stride & 1) == 0)) ? 1 : 0;
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmA, tmB, g.C, g.ldc, (int)g.M, (int)g.N, (int)g.K, klen,
+                                              g.split_stride, g.alpha, g.nsplit > 1 ? 0 : g.beta_one,
+                                              g.lower_only, vec_ok);
+  GLA_CUDA(cudaGetLastError());
+  return 0;
+}
+
+bool tma_ok(const GemmTN<double>& g) {
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return al(g.At) && al(g.B) && (g.ldat & 1) == 0 && (g.ldb & 1) == 0 && g.K >= 1 && g.M < (1ll << 31) &&
+         g.N < (1ll << 31) && g.K < (1ll << 31) && g.ldat * 8 < (1ll << 40) && g.ldb * 8 < (1ll << 40);
+}
+
+}  // namespace
+
+int choose_nsplit(i64 M, i64 N, i64 K, int bm, int bn) {
+  const i64 tiles = (i64)ceil_div(M, bm) * ceil_div(N, bn);
+  const int target = 2 * sm_count();
+  i64 ns = tiles >= target ? 1 : (target + tiles - 1) / tiles;
+  const i64 max_by_k = K / 256 > 0 ? K / 256 : 1;
+  if (ns > max_by_k) ns = max_by_k;
+  if (ns > 64) ns = 64;
+  return (int)(ns < 1 ? 1 : ns);
+}
+
+template <class T>
+static int launch_fma(const GemmTN<T>& g, int klen, cudaStream_t st) {
+  dim3 grid((unsigned)ceil_div(g.M, 64), (unsigned)ceil_div(g.N, 64), (unsigned)g.nsplit);
+  gemm_tn_fma_kernel<T><<<grid, 256, 0, st>>>(g.At, g.ldat, g.B, g.ldb, g.C, g.ldc, (int)g.M, (int)g.N, (int)g.K, klen,
+                                              g.split_stride, g.alpha, g.nsplit > 1 ? 0 : g.beta_one, g.conj_a,
+                                              g.lower_only);
+  GLA_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int slice_len(i64 K, int nsplit) {
+  i64 klen = (K + nsplit - 1) / nsplit;
+  klen = (klen + 15) / 16 * 16;
+  return (int)klen;
+}
+
+template <>
+int gemm_tn<double>(const GemmTN<double>& g, cudaStream_t st) {
+  if (g.M <= 0 || g.N <= 0) return 0;
+  const int klen = slice_len(g.K > 0 ? g.K : 1, g.nsplit);
+  if (g.K > 0 && tma_ok(g)) {
+    // 8 consumer warps (32x32 each) + 1 TMA warp, 4 x 24 KB stages -> two CTAs per SM
+    if (g.M <= 64) return launch_dmma<64, 128, 4>(g, klen, st);
+    return launch_dmma<128, 64, 4>(g, klen, st);
+  }
+  return launch_fma<double>(g, klen, st);
+}
+template <>
+int gemm_tn<float>(const GemmTN<float>& g, cudaStream_t st) {
+  if (g.M <= 0 || g.N <= 0) return 0;
+  return launch_fma<float>(g, slice_len(g.K > 0 ? g.K : 1, g.nsplit), st);
+}
+template <>
+int gemm_tn<zd>(const GemmTN<zd>& g, cudaStream_t st) {
+  if (g.M <= 0 || g.N <= 0) return 0;
+  return launch_fma<zd>(g, slice_len(g.K > 0 ? g.K : 1, g.nsplit), st);
+}
+
+template <class T>
+int sum_splits(T* out, i64 ldo, const T* part, i64 ldp, i64 stride, int nsplit, i64 M, i64 N, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return 0;
+  i64 total = M * N;
+  int grid = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  sum_splits_kernel<T><<<grid, 256, 0, st>>>(out, ldo, part, ldp, stride, nsplit, M, N);
+  GLA_CUDA(cudaGetLastError());
+  return 0;
+}
+template int sum_splits<float>(float*, i64, const float*, i64, i64, int, i64, i64, cudaStream_t);
+template int sum_splits<double>(double*, i64, const double*, i64, i64, int, i64, i64, cudaStream_t);
+template int sum_splits<zd>(zd*, i64, const zd*, i64, i64, int, i64, i64, cudaStream_t);
+
+}  // namespace gla

@@ -1,0 +1,630 @@
+// qr_blocked.cu -- K1 (panel), K2 (compact-WY T) and the driver of the blocked Householder QR.
+//
+// Reference semantics: qrBlocked! src/qr.jl:113-146 = per panel  qrUnblocked! (src/qr.jl:86-111,
+// stdlib reflector!/reflectorApply! call sites :96/:102)  ->  T build (src/qr.jl:64-83, with the conj
+// the reference omits at :72)  ->  trailing update A2 <- (I - V T^H V^H) A2 (src/householder.jl:119-157).
+//
+// GPU structure per panel of NB = 64 columns:
+//   qr_panel_kernel   cooperative, P CTAs each holding a row slab of the panel in shared memory;
+//                     ONE grid-wide reduction per column: every CTA publishes the partial dots
+//                     d_c = sum_{i>j} conj(a_ij) a_ic of the un-normalised pivot column with every
+//                     remaining panel column (c = j gives the tail norm^2), the owner of row j
+//                     publishes that row; after the barrier every CTA reduces the partials in the
+//                     same fixed order (bitwise identical, deterministic), derives nu, tau, 1/xi and
+//                     applies  a_ic -= a_ij * (s_c/xi),  s_c = conj(tau) (a_jc + conj(1/xi) d_c).
+//                     It also emits the clean reflector block Vc (unit diagonal, zeros above) and
+//                     its transpose VcT, the K-contiguous operands of the trailing contractions.
+//   gemm_tn (x3)      G = Vc^H Vc (split-K), W = Vc^H A2 (split-K), A2 -= Vc (T^H W): FP64 tensor
+//                     pipe fed by TMA (gemm.cu)
+//   larft_finish      T = (I + diag(tau) striu(G))^-1 diag(tau) in one CTA (shared memory)
+//   apply_t           W2 = T^H * sum(split-K partials of W)
+#include "gemm.cuh"
+#include "gla_internal.cuh"
+#include "smallqr.cuh"
+
+#include <cooperative_groups.h>
+
+namespace gla {
+
+constexpr int NB = 64;             // panel width
+constexpr int PANEL_THREADS = 256;
+constexpr int TPC = PANEL_THREADS / NB;  // threads per panel column
+constexpr int PANEL_MAX_CTAS = 64;
+
+template <class T>
+struct PanelArgs {
+  T* A;        // panel origin (row k0, col k0)
+  i64 lda;
+  int mk, nb;  // panel rows, panel columns (<= NB)
+  T* tau;      // tau + k0
+  T* Vc;       // mk x kk clean reflectors (ld = ldvc)
+  i64 ldvc;
+  T* VcT;      // kk x mk (ld = NB)
+  T* partial;  // [2][P][NB]
+  T* rowj;     // [2][NB]
+  unsigned* counter;
+  int rows_per;  // rows per CTA
+  int resident;  // slab lives in shared memory
+  int lds;       // slab leading dimension when resident
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target, int nctas) {
+  __syncthreads();
+  if (nctas > 1 && threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    while (ld_acquire_u32(counter) < target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <class T>
+__device__ __forceinline__ T ldcg(const T* p) {
+  return __ldcg(p);
+}
+template <>
+__device__ __forceinline__ zd ldcg<zd>(const zd* p) {
+  double2 v = __ldcg(reinterpret_cast<const double2*>(p));
+  return make_zd(v.x, v.y);
+}
+
+template <class T>
+__device__ __forceinline__ T shfl_xor_t(T v, int m) {
+  return __shfl_xor_sync(0xffffffffu, v, m);
+}
+template <>
+__device__ __forceinline__ zd shfl_xor_t<zd>(zd v, int m) {
+  return make_zd(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
+}
+
+template <class T>
+__global__ void __launch_bounds__(PANEL_THREADS, 1) qr_panel_kernel(PanelArgs<T> a) {
+  using R = typename Sc<T>::real;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ T sh_d[NB];
+  __shared__ T sh_row[NB];
+  const int P = gridDim.x, p = blockIdx.x;
+  const int r0 = p * a.rows_per;
+  const int r1 = (r0 + a.rows_per < a.mk) ? r0 + a.rows_per : a.mk;
+  const int rows = r1 > r0 ? r1 - r0 : 0;
+  const int tid = threadIdx.x;
+  const int c = tid / TPC, q = tid % TPC;  // column, row phase
+  const int kk = a.mk < a.nb ? a.mk : a.nb;
+
+  // slab S(i_local, col)
+  T* S;
+  i64 ld;
+  if (a.resident) {
+    S = reinterpret_cast<T*>(smem_raw);
+    ld = a.lds;
+    for (int col = 0; col < a.nb; ++col)
+      for (int i = tid; i < rows; i += PANEL_THREADS) S[i + col * ld] = a.A[(i64)col * a.lda + r0 + i];
+  } else {
+    S = a.A + r0;
+    ld = a.lda;
+  }
+  __syncthreads();
+
+  T prev_ixi = Sc<T>::one();
+  R prev_nu = R(0);
+  bool prev_nonzero = false;
+  unsigned bar_target = 0;
+
+  for (int j = 0; j <= kk; ++j) {
+    // ---- deferred finish of pivot column j-1: rows below the diagonal *= 1/xi, diagonal <- -nu
+    if (j > 0 && prev_nonzero) {
+      T* col = S + (i64)(j - 1) * ld;
+      int lo = j - r0;  // first local row with global index >= j
+      if (lo < 0) lo = 0;
+      for (int i = lo + tid; i < rows; i += PANEL_THREADS) col[i] = col[i] * prev_ixi;
+      if (tid == 0 && j - 1 >= r0 && j - 1 < r1) col[j - 1 - r0] = Sc<T>::from_real(-prev_nu);
+    }
+    if (j == kk) break;
+    const int buf = j & 1;
+    const T* piv = S + (i64)j * ld;
+    int lo = j + 1 - r0;  // first local row strictly below the diagonal
+    if (lo < 0) lo = 0;
+    const bool active = c >= j && c < a.nb;
+    // ---- partial dots with the un-normalised pivot column
+    T d = Sc<T>::zero();
+    if (active) {
+      const T* cc = S + (i64)c * ld;
+      T d1 = Sc<T>::zero();
+      int i = lo + q;
+      for (; i + TPC < rows; i += 2 * TPC) {
+        d = fmad(cj(piv[i]), cc[i], d);
+        d1 = fmad(cj(piv[i + TPC]), cc[i + TPC], d1);
+      }
+      if (i < rows) d = fmad(cj(piv[i]), cc[i], d);
+      d = d + d1;
+    }
+#pragma unroll
+    for (int o = 1; o < TPC; o <<= 1) d = d + shfl_xor_t<T>(d, o);
+    if (P > 1) {
+      if (active && q == 0) a.partial[((i64)buf * P + p) * NB + c] = d;
+      if (active && q == 1 && j >= r0 && j < r1) a.rowj[buf * NB + c] = S[(j - r0) + (i64)c * ld];
+      bar_target += P;
+      grid_barrier(a.counter, bar_target, P);
+      // ---- fixed-order reduction of the partials (identical in every CTA)
+      T sum = Sc<T>::zero();
+      if (active) {
+        for (int pp = q; pp < P; pp += TPC) sum = sum + ldcg<T>(a.partial + ((i64)buf * P + pp) * NB + c);
+      }
+#pragma unroll
+      for (int o = 1; o < TPC; o <<= 1) sum = sum + shfl_xor_t<T>(sum, o);
+      if (active && q == 0) {
+        sh_d[c] = sum;
+        sh_row[c] = ldcg<T>(a.rowj + buf * NB + c);
+      }
+    } else {
+      if (active && q == 0) {
+        sh_d[c] = d;
+        sh_row[c] = S[j + (i64)c * ld];
+      }
+    }
+    __syncthreads();
+    const T alpha = sh_row[j];
+    const R n2 = abs2(alpha) + re(sh_d[j]);
+    const ReflScalars<T> rs = reflector_scalars<T>(alpha, n2);
+    prev_nonzero = rs.nonzero;
+    prev_ixi = rs.ixi;
+    prev_nu = rs.nu;
+    if (p == 0 && tid == 0) a.tau[j] = rs.tau;
+    if (rs.nonzero && active && c > j) {
+      const T s = cj(rs.tau) * (sh_row[c] + cj(rs.ixi) * sh_d[c]);
+      const T t = s * rs.ixi;
+      T* cc = S + (i64)c * ld;
+      for (int i = lo + q; i < rows; i += TPC) cc[i] = cc[i] - piv[i] * t;
+      if (q == 0 && j >= r0 && j < r1) cc[j - r0] = cc[j - r0] - s;
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+
+  // ---- write back: panel (if staged), clean reflectors Vc and VcT
+  if (a.resident) {
+    for (int col = 0; col < a.nb; ++col)
+      for (int i = tid; i < rows; i += PANEL_THREADS) a.A[(i64)col * a.lda + r0 + i] = S[i + col * ld];
+  }
+  for (int col = 0; col < kk; ++col)
+    for (int i = tid; i < rows; i += PANEL_THREADS) {
+      const int gi = r0 + i;
+      T v = gi < col ? Sc<T>::zero() : (gi == col ? Sc<T>::one() : S[i + (i64)col * ld]);
+      a.Vc[(i64)col * a.ldvc + gi] = v;
+    }
+  for (int e = tid; e < rows * kk; e += PANEL_THREADS) {
+    const int col = e % kk, i = e / kk;
+    const int gi = r0 + i;
+    T v = gi < col ? Sc<T>::zero() : (gi == col ? Sc<T>::one() : S[i + (i64)col * ld]);
+    a.VcT[(i64)gi * NB + col] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------- clean V from factors
+// Vc (mk x kk, ldvc) and VcT (kk x mk, ld NB) from the factored panel F (unit lower trapezoid)
+template <class T>
+__global__ void extract_v_kernel(const T* __restrict__ F, i64 ldf, int mk, int kk, T* __restrict__ Vc, i64 ldvc,
+                                 T* __restrict__ VcT) {
+  const i64 total = (i64)mk * kk;
+  for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
+    const int col = (int)(e / mk), i = (int)(e - (i64)col * mk);
+    T v = i < col ? Sc<T>::zero() : (i == col ? Sc<T>::one() : F[(i64)col * ldf + i]);
+    Vc[(i64)col * ldvc + i] = v;
+    VcT[(i64)i * NB + col] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------- K2: T from G
+// G partials: nsplit slices of kk x kk (ld = kk, stride gstride).  T (kk x kk, ldt) upper.
+//   U = diag(tau) striu(G);  X = (I + U)^-1;  T = X diag(tau)          (src/qr.jl:70-81)
+template <class T>
+__global__ void __launch_bounds__(256) larft_finish_kernel(const T* __restrict__ Gp, i64 gstride, int nsplit, int kk,
+                                                           const T* __restrict__ tau, T* __restrict__ Tm, i64 ldt) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  typedef T Row[NB + 1];
+  Row* U = reinterpret_cast<Row*>(smem_raw);
+  Row* X = U + NB;
+  T* st = reinterpret_cast<T*>(X + NB);
+  const int tid = threadIdx.x;
+  if (tid < kk) st[tid] = tau[tid];
+  __syncthreads();
+  for (int e = tid; e < kk * kk; e += blockDim.x) {
+    const int j = e / kk, i = e - j * kk;
+    T g = Sc<T>::zero();
+    if (i < j) {
+      g = Gp[(i64)j * kk + i];
+      for (int z = 1; z < nsplit; ++z) g = g + Gp[(i64)z * gstride + (i64)j * kk + i];
+      g = st[i] * g;
+    }
+    U[i][j] = g;
+    X[i][j] = (i == j) ? Sc<T>::one() : Sc<T>::zero();
+  }
+  __syncthreads();
+  // column recurrence X[:,j] = e_j - X[:,0:j] U[0:j,j]; 4 threads share one row i
+  const int i = tid >> 2, part = tid & 3;
+  for (int j = 1; j < kk; ++j) {
+    T s = Sc<T>::zero();
+    if (i < j) {
+      for (int l = i + part; l < j; l += 4) s = fmad(X[i][l], U[l][j], s);
+    }
+    s = s + shfl_xor_t<T>(s, 1);
+    s = s + shfl_xor_t<T>(s, 2);
+    if (i < j && part == 0) X[i][j] = -s;
+    __syncthreads();
+  }
+  for (int e = tid; e < kk * kk; e += blockDim.x) {
+    const int j = e / kk, ii = e - j * kk;
+    Tm[(i64)j * ldt + ii] = ii <= j ? X[ii][j] * st[j] : Sc<T>::zero();
+  }
+}
+
+// W2(kk x nA, ld NB) = op(T) * sum_z Wp[z]   op = T^H (adjoint apply, Q^H A) or T (Q A)
+template <class T>
+__global__ void __launch_bounds__(256) apply_t_kernel(const T* __restrict__ Wp, i64 wstride, int nsplit, int kk,
+                                                      i64 nA, const T* __restrict__ Tm, i64 ldt, int adjoint,
+                                                      T* __restrict__ W2) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  typedef T RowT[NB + 1];
+  typedef T RowW[32 + 1];
+  RowT* sT = reinterpret_cast<RowT*>(smem_raw);       // sT[i][l] = op(T)(i,l)
+  RowW* sW = reinterpret_cast<RowW*>(sT + NB);        // sW[l][jj]
+  const int tid = threadIdx.x;
+  for (int e = tid; e < kk * kk; e += blockDim.x) {
+    const int l = e / kk, i = e - l * kk;  // element (i,l) of op(T)
+    T v;
+    if (adjoint) v = (l <= i) ? cj(Tm[(i64)i * ldt + l]) : Sc<T>::zero();  // T^H(i,l) = conj(T(l,i))
+    else v = (i <= l) ? Tm[(i64)l * ldt + i] : Sc<T>::zero();
+    sT[i][l] = v;
+  }
+  const i64 j0 = (i64)blockIdx.x * 32;
+  for (int e = tid; e < kk * 32; e += blockDim.x) {
+    const int jj = e / kk, l = e - jj * kk;
+    T w = Sc<T>::zero();
+    if (j0 + jj < nA) {
+      w = Wp[(j0 + jj) * NB + l];
+      for (int z = 1; z < nsplit; ++z) w = w + Wp[(i64)z * wstride + (j0 + jj) * NB + l];
+    }
+    sW[l][jj] = w;
+  }
+  __syncthreads();
+  for (int e = tid; e < kk * 32; e += blockDim.x) {
+    const int jj = e / kk, i = e - jj * kk;
+    if (j0 + jj >= nA) continue;
+    T s = Sc<T>::zero();
+    const int lbeg = adjoint ? 0 : i, lend = adjoint ? i + 1 : kk;
+    for (int l = lbeg; l < lend; ++l) s = fmad(sT[i][l], sW[l][jj], s);
+    W2[(j0 + jj) * NB + i] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------- workspace
+template <class T>
+struct QrWork {
+  T* Vc = nullptr;
+  i64 ldvc = 0;
+  T* VcT = nullptr;
+  T* Gp = nullptr;   // split-K partials of G
+  T* Tm = nullptr;   // NB x NB
+  T* Wp = nullptr;   // split-K partials of W
+  T* W2 = nullptr;   // NB x nA
+  T* partial = nullptr;
+  T* rowj = nullptr;
+  unsigned* counter = nullptr;
+  void* block = nullptr;
+  cudaStream_t st = nullptr;
+  i64 wp_elems = 0;
+
+  int alloc(i64 m, i64 nA_max, int max_wsplit, cudaStream_t stream) {
+    st = stream;
+    ldvc = round_up(m, 2);
+    auto al = [](i64 bytes) { return round_up(bytes, 256); };
+    const i64 s_vc = al(ldvc * NB * sizeof(T));
+    const i64 s_vct = al((i64)NB * m * sizeof(T));
+    const i64 s_gp = al((i64)64 * NB * NB * sizeof(T));
+    const i64 s_tm = al((i64)NB * NB * sizeof(T));
+    wp_elems = (i64)max_wsplit * NB * (nA_max > 0 ? nA_max : 1);
+    const i64 s_wp = al(wp_elems * sizeof(T));
+    const i64 s_w2 = al((i64)NB * (nA_max > 0 ? nA_max : 1) * sizeof(T));
+    const i64 s_part = al((i64)2 * 256 * NB * sizeof(T));
+    const i64 s_rowj = al((i64)2 * NB * sizeof(T));
+    const i64 s_cnt = 256;
+    const i64 total = s_vc + s_vct + s_gp + s_tm + s_wp + s_w2 + s_part + s_rowj + s_cnt;
+    GLA_CUDA(cudaMallocAsync(&block, total, st));
+    char* p = static_cast<char*>(block);
+    Vc = reinterpret_cast<T*>(p); p += s_vc;
+    VcT = reinterpret_cast<T*>(p); p += s_vct;
+    Gp = reinterpret_cast<T*>(p); p += s_gp;
+    Tm = reinterpret_cast<T*>(p); p += s_tm;
+    Wp = reinterpret_cast<T*>(p); p += s_wp;
+    W2 = reinterpret_cast<T*>(p); p += s_w2;
+    partial = reinterpret_cast<T*>(p); p += s_part;
+    rowj = reinterpret_cast<T*>(p); p += s_rowj;
+    counter = reinterpret_cast<unsigned*>(p);
+    return 0;
+  }
+  void release() {
+    if (block) cudaFreeAsync(block, st);
+    block = nullptr;
+  }
+};
+
+// ------------------------------------------------------------------------------- panel launch
+template <class T>
+static int launch_panel(T* A, i64 lda, i64 mk, int nb, T* tau, QrWork<T>& w, cudaStream_t st) {
+  PanelArgs<T> a;
+  a.A = A;
+  a.lda = lda;
+  a.mk = (int)mk;
+  a.nb = nb;
+  a.tau = tau;
+  a.Vc = w.Vc;
+  a.ldvc = w.ldvc;
+  a.VcT = w.VcT;
+  a.partial = w.partial;
+  a.rowj = w.rowj;
+  a.counter = w.counter;
+  const i64 smem_cap = 200 * 1024;
+  const i64 max_rows = (smem_cap / ((i64)nb * sizeof(T)) - 4) / 16 * 16;  // rows that fit one CTA
+  const int sms = sm_count();
+  i64 rows_per = round_up((mk + PANEL_MAX_CTAS - 1) / PANEL_MAX_CTAS, 16);
+  if (rows_per < 64) rows_per = 64;
+  int resident = 1;
+  if (rows_per > max_rows) {
+    rows_per = max_rows;
+    if ((mk + rows_per - 1) / rows_per > sms) {  // does not fit the chip: operate on global memory
+      resident = 0;
+      rows_per = round_up((mk + sms - 1) / sms, 16);
+    }
+  }
+  const int P = (int)((mk + rows_per - 1) / rows_per);
+  a.rows_per = (int)rows_per;
+  a.resident = resident;
+  a.lds = (int)(round_up(rows_per, 16) + 4);
+  size_t smem = resident ? (size_t)a.lds * nb * sizeof(T) : 0;
+  auto kern = qr_panel_kernel<T>;
+  GLA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_cap + 8 * 1024)));
+  GLA_CUDA(cudaMemsetAsync(w.counter, 0, sizeof(unsigned), st));
+  void* args[] = {&a};
+  if (P > 1) {
+    GLA_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(P), dim3(PANEL_THREADS), args, smem, st));
+  } else {
+    kern<<<1, PANEL_THREADS, smem, st>>>(a);
+    GLA_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+// T (kk x kk) of the clean reflector block in w.Vc with tau
+template <class T>
+static int build_T(QrWork<T>& w, i64 mk, int kk, const T* tau, cudaStream_t st) {
+  GemmTN<T> g;
+  g.At = w.Vc; g.ldat = w.ldvc;
+  g.B = w.Vc; g.ldb = w.ldvc;
+  g.C = w.Gp; g.ldc = kk;
+  g.M = kk; g.N = kk; g.K = mk;
+  g.conj_a = 1;
+  g.nsplit = choose_nsplit(kk, kk, mk, 64, 128);
+  g.split_stride = (i64)kk * kk + (((i64)kk * kk) & 1);
+  GLA_TRY(gemm_tn<T>(g, st));
+  const int smem = (2 * NB * (NB + 1) + NB) * (int)sizeof(T);
+  GLA_CUDA(cudaFuncSetAttribute(larft_finish_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  larft_finish_kernel<T><<<1, 256, smem, st>>>(w.Gp, g.split_stride, g.nsplit, kk, tau, w.Tm, NB);
+  GLA_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int wsplit_for(i64 kk, i64 nA, i64 mk) { return choose_nsplit(kk, nA, mk, 64, 128); }
+
+// A2 (mk x nA, lda) <- (I - Vc op(T) Vc^H) A2 with Vc/VcT/T in w
+template <class T>
+static int apply_block(QrWork<T>& w, i64 mk, int kk, T* A2, i64 lda, i64 nA, int adjoint, cudaStream_t st) {
+  if (nA <= 0) return 0;
+  GemmTN<T> g1;
+  g1.At = w.Vc; g1.ldat = w.ldvc;
+  g1.B = A2; g1.ldb = lda;
+  g1.C = w.Wp; g1.ldc = NB;
+  g1.M = kk; g1.N = nA; g1.K = mk;
+  g1.conj_a = 1;
+  g1.nsplit = wsplit_for(kk, nA, mk);
+  g1.split_stride = (i64)NB * nA;
+  if ((i64)g1.nsplit * NB * nA > w.wp_elems) g1.nsplit = (int)(w.wp_elems / ((i64)NB * nA));
+  if (g1.nsplit < 1) {
+    set_error(GLA_ERR_INTERNAL, "W workspace too small", __FILE__, __LINE__);
+    return GLA_ERR_INTERNAL;
+  }
+  GLA_TRY(gemm_tn<T>(g1, st));
+  const int smem_t = (NB * (NB + 1) + NB * 33) * (int)sizeof(T);
+  GLA_CUDA(cudaFuncSetAttribute(apply_t_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_t));
+  apply_t_kernel<T><<<(unsigned)ceil_div(nA, 32), 256, smem_t, st>>>(w.Wp, g1.split_stride, g1.nsplit, kk, nA, w.Tm, NB,
+                                                                adjoint, w.W2);
+  GLA_CUDA(cudaGetLastError());
+  GemmTN<T> g2;
+  g2.At = w.VcT; g2.ldat = NB;
+  g2.B = w.W2; g2.ldb = NB;
+  g2.C = A2; g2.ldc = lda;
+  g2.M = mk; g2.N = nA; g2.K = kk;
+  g2.alpha = -1;
+  g2.beta_one = 1;
+  GLA_TRY(gemm_tn<T>(g2, st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------- drivers
+template <class T>
+int geqr_blocked_dev(T* dA, i64 m, i64 n, i64 lda, T* dtau, i64 /*blocksize_hint*/, cudaStream_t st) {
+  if (m < 0) return -2;
+  if (n < 0) return -3;
+  if (lda < (m > 1 ? m : 1)) return -4;
+  if (m == 0 || n == 0) return 0;
+  QrWork<T> w;
+  // largest split-K factor any panel will ask for
+  int max_ws = 1;
+  for (i64 k0 = 0; k0 < (m < n ? m : n); k0 += NB) {
+    const i64 nA = n - k0 - NB;
+    if (nA <= 0) break;
+    const int s = wsplit_for(NB, nA, m - k0);
+    // workspace is sized for nA_max columns; a later, narrower panel may use a larger split
+    const i64 scaled = ((i64)s * nA + (n - NB) - 1) / ((n - NB) > 0 ? (n - NB) : 1);
+    if (scaled > max_ws) max_ws = (int)scaled;
+  }
+  GLA_TRY(w.alloc(m, n - NB, max_ws + 1, st));
+  int rc = 0;
+  for (i64 k0 = 0;; k0 += NB) {
+    const i64 mk = m - k0, nk = n - k0;
+    const int nb = (int)(nk < NB ? nk : NB);
+    const int kk = (int)(mk < nb ? mk : nb);
+    T* Ak = dA + k0 + k0 * lda;
+    if ((rc = launch_panel<T>(Ak, lda, mk, nb, dtau + k0, w, st))) break;
+    const i64 nA = nk - nb;
+    if (nA > 0) {
+      if ((rc = build_T<T>(w, mk, kk, dtau + k0, st))) break;
+      if ((rc = apply_block<T>(w, mk, kk, Ak + (i64)nb * lda, lda, nA, 1, st))) break;
+    }
+    if (!(mk > nb && nk > nb)) break;
+  }
+  w.release();
+  return rc;
+}
+
+template <class T>
+int ormqr_blocked_dev(const T* dF, i64 mF, i64 nF, i64 ldf, const T* dtau, T* dA, i64 mA, i64 nA, i64 lda,
+                      int adjoint, cudaStream_t st) {
+  if (mF != mA) return -7;  // DimensionMismatch (src/householder.jl:87,129)
+  if (mF < 0 || nF < 0 || nA < 0) return -2;
+  const i64 k = mF < nF ? mF : nF;
+  if (k == 0 || nA == 0) return 0;
+  QrWork<T> w;
+  int max_ws = 1;
+  for (i64 k0 = 0; k0 < k; k0 += NB) {
+    const int s = wsplit_for(NB, nA, mF - k0);
+    if (s > max_ws) max_ws = s;
+  }
+  GLA_TRY(w.alloc(mF, nA, max_ws, st));
+  int rc = 0;
+  const i64 npan = (k + NB - 1) / NB;
+  for (i64 ip = 0; ip < npan; ++ip) {
+    // Q^H A applies panels first to last, Q A last to first
+    const i64 k0 = (adjoint ? ip : npan - 1 - ip) * NB;
+    const i64 mk = mF - k0;
+    const int kk = (int)((k - k0) < NB ? (k - k0) : NB);
+    extract_v_kernel<T><<<(unsigned)ceil_div(mk * kk, 256) > 2048 ? 2048 : (unsigned)ceil_div(mk * kk, 256), 256, 0, st>>>(
+        dF + k0 + k0 * ldf, ldf, (int)mk, kk, w.Vc, w.ldvc, w.VcT);
+    if ((rc = check_cuda(cudaGetLastError(), __FILE__, __LINE__))) break;
+    if ((rc = build_T<T>(w, mk, kk, dtau + k0, st))) break;
+    if ((rc = apply_block<T>(w, mk, kk, dA + k0, lda, nA, adjoint, st))) break;
+  }
+  w.release();
+  return rc;
+}
+
+// ------------------------------------------------------------------------------- full-width T (API parity)
+// getindex(::QR2, Tuple{:QBlocked}) builds T for ALL k = min(m,n) reflectors (src/qr.jl:66-69).  The
+// factorisation itself never needs it (it works panel by panel); this exists for the drop-in API.
+template <class T>
+__global__ void clean_v_kernel(const T* __restrict__ F, i64 ldf, i64 m, i64 k, T* __restrict__ Vc, i64 ldv) {
+  const i64 total = m * k;
+  for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
+    const i64 col = e / m, i = e - col * m;
+    Vc[col * ldv + i] = i < col ? Sc<T>::zero() : (i == col ? Sc<T>::one() : F[col * ldf + i]);
+  }
+}
+
+// one CTA: Tm holds G = V^H V on entry.  U = diag(tau) striu(G); X = (I+U)^-1 by the column
+// recurrence X[:,j] = e_j - X[:,0:j] U[0:j,j]; T = X diag(tau).
+template <class T>
+__global__ void __launch_bounds__(1024)
+    larft_big_kernel(T* __restrict__ Tm, i64 ldt, int k, const T* __restrict__ tau, T* __restrict__ X) {
+  for (i64 e = threadIdx.x; e < (i64)k * k; e += blockDim.x) {
+    const int j = (int)(e / k), i = (int)(e - (i64)j * k);
+    Tm[(i64)j * ldt + i] = i < j ? tau[i] * Tm[(i64)j * ldt + i] : Sc<T>::zero();
+    X[(i64)j * k + i] = (i == j) ? Sc<T>::one() : Sc<T>::zero();
+  }
+  __syncthreads();
+  for (int j = 1; j < k; ++j) {
+    for (int i = threadIdx.x; i < j; i += blockDim.x) {
+      T acc = Sc<T>::zero();
+      for (int l = i; l < j; ++l) acc = fmad(X[(i64)l * k + i], Tm[(i64)j * ldt + l], acc);
+      X[(i64)j * k + i] = -acc;
+    }
+    __syncthreads();
+  }
+  for (i64 e = threadIdx.x; e < (i64)k * k; e += blockDim.x) {
+    const int j = (int)(e / k), i = (int)(e - (i64)j * k);
+    Tm[(i64)j * ldt + i] = i <= j ? X[(i64)j * k + i] * tau[j] : Sc<T>::zero();
+  }
+}
+
+template <class T>
+int larft_dev(const T* dF, i64 m, i64 n, i64 ldf, const T* dtau, T* dT, i64 ldt, cudaStream_t st) {
+  if (m < 0) return -2;
+  if (n < 0) return -3;
+  const i64 k = m < n ? m : n;
+  if (k == 0) return 0;
+  if (ldt < k) return -7;
+  const i64 ldv = round_up(m, 2);
+  T* Vc = nullptr;
+  T* X = nullptr;
+  GLA_CUDA(cudaMallocAsync(&Vc, (size_t)ldv * k * sizeof(T), st));
+  int rc = check_cuda(cudaMallocAsync(&X, (size_t)k * k * sizeof(T), st), __FILE__, __LINE__);
+  if (!rc) {
+    const unsigned grid = (unsigned)(ceil_div(m * k, 256) > 4096 ? 4096 : ceil_div(m * k, 256));
+    clean_v_kernel<T><<<grid, 256, 0, st>>>(dF, ldf, m, k, Vc, ldv);
+    rc = check_cuda(cudaGetLastError(), __FILE__, __LINE__);
+  }
+  if (!rc) {
+    GemmTN<T> g;
+    g.At = Vc; g.ldat = ldv;
+    g.B = Vc; g.ldb = ldv;
+    g.C = dT; g.ldc = ldt;
+    g.M = k; g.N = k; g.K = m;
+    g.conj_a = 1;
+    rc = gemm_tn<T>(g, st);
+  }
+  if (!rc) {
+    larft_big_kernel<T><<<1, 1024, 0, st>>>(dT, ldt, (int)k, dtau, X);
+    rc = check_cuda(cudaGetLastError(), __FILE__, __LINE__);
+  }
+  cudaFreeAsync(Vc, st);
+  if (X) cudaFreeAsync(X, st);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------- right reflector apply
+// A <- A (I - tau v v^H), v = [1; x[2:]]     (src/qr.jl:19-42), one thread per row
+template <class T>
+__global__ void reflector_apply_right_kernel(T* __restrict__ A, i64 m, i64 n, i64 lda, const T* __restrict__ x, T tau) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  T s = A[i];
+  for (i64 j = 1; j < n; ++j) s = fmad(A[i + j * lda], x[j], s);
+  s = s * tau;
+  A[i] = A[i] - s;
+  for (i64 j = 1; j < n; ++j) A[i + j * lda] = A[i + j * lda] - s * cj(x[j]);
+}
+
+template <class T>
+int reflector_apply_right_dev(T* dA, i64 m, i64 n, i64 lda, const T* dx, T tau, cudaStream_t st) {
+  if (m <= 0 || n <= 0) return 0;
+  reflector_apply_right_kernel<T><<<(unsigned)ceil_div(m, 128), 128, 0, st>>>(dA, m, n, lda, dx, tau);
+  GLA_CUDA(cudaGetLastError());
+  return 0;
+}
+
+#define INST(T)                                                                                             \
+  template int geqr_blocked_dev<T>(T*, i64, i64, i64, T*, i64, cudaStream_t);                               \
+  template int ormqr_blocked_dev<T>(const T*, i64, i64, i64, const T*, T*, i64, i64, i64, int, cudaStream_t); \
+  template int larft_dev<T>(const T*, i64, i64, i64, const T*, T*, i64, cudaStream_t);                      \
+  template int reflector_apply_right_dev<T>(T*, i64, i64, i64, const T*, T, cudaStream_t);
+INST(float)
+INST(double)
+INST(zd)
+
+}  // namespace gla

@@ -88,7 +88,7 @@ def _colmajor(A, what):
         raise DimensionMismatch(f"{what}: need a matrix")
     if A.size and A.strides[0] != A.itemsize:
         raise ArgumentError(f"{what}: need unit row stride (column-major, order='F')")
-    if A.size and (A.strides[1] % A.itemsize or A.strides[1] < A.itemsize * A.shape[0]):
+    if A.size and A.shape[1] > 1 and (A.strides[1] % A.itemsize or A.strides[1] < A.itemsize * A.shape[0]):
         raise ArgumentError(f"{what}: bad column stride")
     ld = A.strides[1] // A.itemsize if A.shape[1] > 1 else max(A.shape[0], 1)
     return max(ld, 1)
