@@ -209,6 +209,72 @@ int reflector_apply_right_host(T* A, i64 m, i64 n, i64 lda, const T* x, i64 lenx
   return 0;
 }
 
+template <class T>
+int potrf_host(T* A, i64 n, i64 lda, i64 cutoff) {
+  if (n < 0) return -2;
+  if (lda < (n > 1 ? n : 1)) return -3;
+  if (n == 0) return 0;
+  if (!A) return -1;
+  Stream st;
+  GLA_TRY(st.create());
+  DevMatrix<T> dA;
+  DevBuf dinfo;
+  GLA_TRY(dA.upload(A, lda, n, n, st.s));
+  GLA_TRY(dinfo.alloc(sizeof(int)));
+  Event e0, e1;
+  GLA_TRY(e0.create());
+  GLA_TRY(e1.create());
+  GLA_CUDA(cudaEventRecord(e0.e, st.s));
+  GLA_TRY(potrf_recursive_L_dev<T>(dA.p(), n, dA.ld, cutoff, dinfo.as<int>(), st.s));
+  GLA_CUDA(cudaEventRecord(e1.e, st.s));
+  int info = 0;
+  GLA_CUDA(cudaMemcpyAsync(&info, dinfo.p, sizeof(int), cudaMemcpyDeviceToHost, st.s));
+  GLA_CUDA(cudaStreamSynchronize(st.s));
+  float ms = 0;
+  GLA_CUDA(cudaEventElapsedTime(&ms, e0.e, e1.e));
+  g_last_ms = ms;
+  if (info != 0) return info;  // leading minor `info` not positive definite: A is left untouched on the host
+  GLA_TRY(dA.download(A, lda, n, n, st.s));
+  GLA_CUDA(cudaStreamSynchronize(st.s));
+  return 0;
+}
+
+template <class T>
+int herk_host(T* Cm, i64 n, i64 ldc, const T* A, i64 k, i64 lda, typename Sc<T>::real alpha) {
+  if (n < 0) return -2;
+  if (ldc < (n > 1 ? n : 1)) return -3;
+  if (k < 0) return -5;
+  if (lda < (n > 1 ? n : 1)) return -6;
+  if (n == 0 || k == 0) return 0;
+  Stream st;
+  GLA_TRY(st.create());
+  DevMatrix<T> dC, dA;
+  GLA_TRY(dC.upload(Cm, ldc, n, n, st.s));
+  GLA_TRY(dA.upload(A, lda, n, k, st.s));
+  GLA_TRY(herk_lower_dev<T>(dC.p(), n, dC.ld, dA.p(), k, dA.ld, alpha, st.s));
+  GLA_TRY(dC.download(Cm, ldc, n, n, st.s));
+  GLA_CUDA(cudaStreamSynchronize(st.s));
+  return 0;
+}
+
+int tsqr_host(const double* A, i64 m, i64 n, i64 lda, double* R, i64 ldr) {
+  if (m < 0) return -2;
+  if (n < 0 || n > 64) return -3;
+  if (lda < (m > 1 ? m : 1)) return -4;
+  if (ldr < (n > 1 ? n : 1)) return -6;
+  if (n == 0) return 0;
+  Stream st;
+  GLA_TRY(st.create());
+  DevMatrix<double> dA, dR;
+  GLA_TRY(dA.upload(A, lda, m, n, st.s));
+  dR.ld = n;
+  GLA_TRY(dR.buf.alloc((size_t)n * n * sizeof(double)));
+  GLA_TRY(tsqr_local_dev(dA.p(), m, n, dA.ld, dR.p(), n, st.s));
+  GLA_TRY(dR.download(R, ldr, n, n, st.s));
+  GLA_CUDA(cudaStreamSynchronize(st.s));
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -280,5 +346,23 @@ int gla_zormqr_blocked(const void* F, int64_t mF, int64_t nF, int64_t ldf, const
 int gla_sreflector_apply_right(float* A, int64_t m, int64_t n, int64_t lda, const float* x, int64_t lenx, const float* tau) { return reflector_apply_right_host<float>(A, m, n, lda, x, lenx, tau); }
 int gla_dreflector_apply_right(double* A, int64_t m, int64_t n, int64_t lda, const double* x, int64_t lenx, const double* tau) { return reflector_apply_right_host<double>(A, m, n, lda, x, lenx, tau); }
 int gla_zreflector_apply_right(void* A, int64_t m, int64_t n, int64_t lda, const void* x, int64_t lenx, const void* tau) { return reflector_apply_right_host<zd>(ZP(A), m, n, lda, ZCP(x), lenx, ZCP(tau)); }
+
+// ---- TSQR
+int gla_dtsqr_local_dev(const double* dA, int64_t m, int64_t n, int64_t lda, double* dR, int64_t ldr, void* stream) { return tsqr_local_dev(dA, m, n, lda, dR, ldr, STREAM(stream)); }
+int gla_dtsqr_combine_dev(const double* dRs, int64_t count, int64_t n, double* dR, int64_t ldr, void* stream) { return tsqr_combine_dev(dRs, count, n, dR, ldr, STREAM(stream)); }
+int gla_dtsqr(const double* A, int64_t m, int64_t n, int64_t lda, double* R, int64_t ldr) { return tsqr_host(A, m, n, lda, R, ldr); }
+
+// ---- recursive Cholesky
+int gla_spotrf_recursive_L(float* A, int64_t n, int64_t lda, int64_t cutoff) { return potrf_host<float>(A, n, lda, cutoff); }
+int gla_dpotrf_recursive_L(double* A, int64_t n, int64_t lda, int64_t cutoff) { return potrf_host<double>(A, n, lda, cutoff); }
+int gla_zpotrf_recursive_L(void* A, int64_t n, int64_t lda, int64_t cutoff) { return potrf_host<zd>(ZP(A), n, lda, cutoff); }
+int gla_spotrf_recursive_L_dev(float* dA, int64_t n, int64_t lda, int64_t cutoff, int* dinfo, void* stream) { return potrf_recursive_L_dev<float>(dA, n, lda, cutoff, dinfo, STREAM(stream)); }
+int gla_dpotrf_recursive_L_dev(double* dA, int64_t n, int64_t lda, int64_t cutoff, int* dinfo, void* stream) { return potrf_recursive_L_dev<double>(dA, n, lda, cutoff, dinfo, STREAM(stream)); }
+int gla_zpotrf_recursive_L_dev(void* dA, int64_t n, int64_t lda, int64_t cutoff, int* dinfo, void* stream) { return potrf_recursive_L_dev<zd>(ZP(dA), n, lda, cutoff, dinfo, STREAM(stream)); }
+
+// ---- Hermitian rank-k update
+int gla_ssyrk_lower(float* C, int64_t n, int64_t ldc, const float* A, int64_t k, int64_t lda, float alpha) { return herk_host<float>(C, n, ldc, A, k, lda, alpha); }
+int gla_dsyrk_lower(double* C, int64_t n, int64_t ldc, const double* A, int64_t k, int64_t lda, double alpha) { return herk_host<double>(C, n, ldc, A, k, lda, alpha); }
+int gla_zherk_lower(void* C, int64_t n, int64_t ldc, const void* A, int64_t k, int64_t lda, double alpha) { return herk_host<zd>(ZP(C), n, ldc, ZCP(A), k, lda, alpha); }
 
 }  // extern "C"

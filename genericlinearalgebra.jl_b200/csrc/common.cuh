@@ -120,6 +120,15 @@ __device__ __forceinline__ zd warp_sum(zd v) {
   return v;
 }
 
+template <class T>
+__device__ __forceinline__ T shfl_xor_t(T v, int m) {
+  return __shfl_xor_sync(0xffffffffu, v, m);
+}
+template <>
+__device__ __forceinline__ zd shfl_xor_t<zd>(zd v, int m) {
+  return make_zd(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
+}
+
 constexpr int GLA_ERR_DRIVER = 1900;   // driver entry point / tensor-map encode failure
 constexpr int GLA_ERR_INTERNAL = 1901; // internal invariant violated
 

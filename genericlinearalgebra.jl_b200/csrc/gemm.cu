@@ -60,13 +60,17 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
 template <int BM, int BN, int STAGES>
 struct DmmaCfg {
   static constexpr int WM = BM / 32, WN = BN / 32, NCW = WM * WN;
-  static constexpr int THREADS = NCW * 32 + 32;
+  static constexpr int THREADS = NCW * 32;
   static constexpr int STAGE_BYTES = (BM + BN) * 128;
   static constexpr int SMEM = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 1024;
 };
 
+// 256 threads = 8 consumer warps (no separate producer warp: with 9 warps the register file only
+// fits one CTA per SM); lane 0 of warp 0 also drives TMA, refilling the slot released one iteration
+// earlier so it almost never waits.  <= 128 registers -> two CTAs per SM, whose prologues/epilogues
+// overlap each other's main loops.
 template <int BM, int BN, int STAGES>
-__global__ void __maxnreg__(112)
+__global__ void __launch_bounds__(DmmaCfg<BM, BN, STAGES>::THREADS, 2)
     gemm_tn_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                         double* __restrict__ C, i64 ldc, int M, int N, int K, int klen, i64 split_stride,
                         double alpha, int beta_one, int lower_only, int vec_ok) {
@@ -81,41 +85,67 @@ __global__ void __maxnreg__(112)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  if (lower_only && n0 >= m0 + BM) return;  // tile strictly above the diagonal
+  if (lower_only == 1 && n0 >= m0 + BM) return;  // tile strictly above the diagonal
+  if (lower_only == 2 && m0 >= n0 + BN) return;  // tile strictly below the diagonal
   const int kbeg = blockIdx.z * klen;
   const int kend = (kbeg + klen < K) ? kbeg + klen : K;
   const int nk = (kend - kbeg + 15) >> 4;
+  const bool producer = threadIdx.x == 0;
 
-  if (threadIdx.x == 0) {
+  if (producer) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], NCW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  if (warp == NCW) {  // ---- TMA producer warp
-    if (lane == 0) {
-      for (int it = 0; it < nk; ++it) {
-        const int s = it % STAGES;
-        if (it >= STAGES) mbar_wait(&empty[s], ((it / STAGES) - 1) & 1);
-        mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
-        tma_load_2d(sA + s * BM * 128, &tmA, kbeg + it * 16, m0, &full[s]);
-        tma_load_2d(sB + s * BN * 128, &tmB, kbeg + it * 16, n0, &full[s]);
-      }
+    // prologue: fill the ring
+    for (int it = 0; it < STAGES && it < nk; ++it) {
+      mbar_expect_tx(&full[it], Cfg::STAGE_BYTES);
+      tma_load_2d(sA + it * BM * 128, &tmA, kbeg + it * 16, m0, &full[it]);
+      tma_load_2d(sB + it * BN * 128, &tmB, kbeg + it * 16, n0, &full[it]);
     }
-    return;
   }
 
-  // ---- consumers: 32x32 warp tile = 4 x 4 DMMA blocks
+  // ---- 32x32 warp tile = 4 x 4 DMMA blocks; thread owns rows i0,i0+1 x 4 consecutive columns per (P,Q)
   const int wm = warp % WM, wn = warp / WM;
   const int g = lane >> 2, t = lane & 3;
+  double* Cz = C + (i64)blockIdx.z * split_stride;
   double acc[4][4][2];
+  // C is folded into the accumulators up front (beta = 1), so its HBM latency hides behind the TMA
+  // prologue instead of trailing the main loop.  sgn = +-1 makes acc = sgn*C so that alpha = +-1
+  // needs no multiply at the end: C' = C + alpha*AB = alpha*(alpha*C + AB).
+  const bool preload = beta_one && (alpha == 1.0 || alpha == -1.0);
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int P = 0; P < 2; ++P) {
+    const int i0 = m0 + wm * 32 + 16 * P + 2 * g;
 #pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    for (int Q = 0; Q < 2; ++Q) {
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const int c = cc >> 1, e = cc & 1;
+        const int j = n0 + wn * 32 + 16 * Q + 4 * t + cc;
+        double v0 = 0.0, v1 = 0.0;
+        if (preload && j < N && i0 < M) {
+          const double* p = Cz + (i64)j * ldc + i0;
+          if (vec_ok && i0 + 1 < M) {
+            const double2 o = *reinterpret_cast<const double2*>(p);
+            v0 = o.x;
+            v1 = o.y;
+          } else {
+            v0 = p[0];
+            if (i0 + 1 < M) v1 = p[1];
+          }
+          v0 *= alpha;
+          v1 *= alpha;
+        }
+        acc[2 * P][2 * Q + e][c] = v0;
+        acc[2 * P + 1][2 * Q + e][c] = v1;
+      }
+    }
+  }
+  __syncthreads();  // barrier inits visible to all consumers
 
   // byte offset of tile row for DMMA block b, lane row g:  row = 16*(b/2) + 2g + (b%2)
   int rowoff[4], key[4];
@@ -129,6 +159,15 @@ __global__ void __maxnreg__(112)
 
   for (int it = 0; it < nk; ++it) {
     const int s = it % STAGES;
+    // refill the slot that was consumed in iteration it-1 with the slab of iteration it-1+STAGES
+    if (producer && it >= 1 && it - 1 + STAGES < nk) {
+      const int ps = (it - 1) % STAGES;
+      mbar_wait(&empty[ps], ((it - 1) / STAGES) & 1);
+      mbar_expect_tx(&full[ps], Cfg::STAGE_BYTES);
+      tma_load_2d(sA + ps * BM * 128, &tmA, kbeg + (it - 1 + STAGES) * 16, m0, &full[ps]);
+      tma_load_2d(sB + ps * BN * 128, &tmB, kbeg + (it - 1 + STAGES) * 16, n0, &full[ps]);
+    }
+    __syncwarp();
     mbar_wait(&full[s], (it / STAGES) & 1);
     const unsigned char* pa = sA + s * BM * 128 + wm * 32 * 128;
     const unsigned char* pb = sB + s * BN * 128 + wn * 32 * 128;
@@ -150,8 +189,7 @@ __global__ void __maxnreg__(112)
     if (lane == 0) mbar_arrive(&empty[s]);
   }
 
-  // ---- epilogue: thread owns rows i0,i0+1 x 4 consecutive columns per (P,Q)
-  double* Cz = C + (i64)blockIdx.z * split_stride;
+  // ---- epilogue
 #pragma unroll
   for (int P = 0; P < 2; ++P) {
     const int i0 = m0 + wm * 32 + 16 * P + 2 * g;
@@ -167,19 +205,20 @@ __global__ void __maxnreg__(112)
         double v0 = alpha * acc[2 * P][2 * Q + e][c];
         double v1 = alpha * acc[2 * P + 1][2 * Q + e][c];
         double* p = Cz + (i64)j * ldc + i0;
-        const bool w0 = !lower_only || i0 >= j;
-        const bool w1 = two && (!lower_only || i0 + 1 >= j);
+        const bool w0 = !lower_only || (lower_only == 1 ? i0 >= j : i0 <= j);
+        const bool w1 = two && (!lower_only || (lower_only == 1 ? i0 + 1 >= j : i0 + 1 <= j));
+        const bool add = beta_one && !preload;
         if (vec_ok && w0 && w1) {
           double2* pv = reinterpret_cast<double2*>(p);
-          if (beta_one) {
+          if (add) {
             double2 o = *pv;
             v0 += o.x;
             v1 += o.y;
           }
           *pv = make_double2(v0, v1);
         } else {
-          if (w0) p[0] = beta_one ? p[0] + v0 : v0;
-          if (w1) p[1] = beta_one ? p[1] + v1 : v1;
+          if (w0) p[0] = add ? p[0] + v0 : v0;
+          if (w1) p[1] = add ? p[1] + v1 : v1;
         }
       }
     }
@@ -196,7 +235,8 @@ __global__ void __launch_bounds__(256)
   __shared__ T sA[16][64 + 1];
   __shared__ T sB[16][64 + 1];
   const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
-  if (lower_only && n0 >= m0 + 64) return;
+  if (lower_only == 1 && n0 >= m0 + 64) return;
+  if (lower_only == 2 && m0 >= n0 + 64) return;
   const int kbeg = blockIdx.z * klen;
   const int kend = (kbeg + klen < K) ? kbeg + klen : K;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // tx -> rows (M), ty -> cols (N)
@@ -242,7 +282,8 @@ __global__ void __launch_bounds__(256)
     for (int x = 0; x < 4; ++x) {
       const int i = m0 + tx + 16 * x;
       if (i >= M) continue;
-      if (lower_only && i < j) continue;
+      if (lower_only == 1 && i < j) continue;
+      if (lower_only == 2 && i > j) continue;
       T v = scale_real(acc[x][y], alpha);
       T* p = Cz + (i64)j * ldc + i;
       *p = beta_one ? *p + v : v;

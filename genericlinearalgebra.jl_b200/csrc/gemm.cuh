@@ -30,7 +30,7 @@ struct GemmTN {
   typename Sc<T>::real alpha = 1;
   int beta_one = 0;     // 0: C = alpha*acc, 1: C += alpha*acc
   int conj_a = 0;       // complex only
-  int lower_only = 0;   // write only i >= j (Hermitian rank-k update of a lower triangle)
+  int lower_only = 0;   // triangle mask: 1 = write only i >= j (lower), 2 = only i <= j (upper)
   int nsplit = 1;       // split-K slices (beta_one must be 0 when > 1)
   i64 split_stride = 0; // elements between partial outputs
 };

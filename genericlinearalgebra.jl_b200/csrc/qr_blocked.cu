@@ -77,15 +77,6 @@ __device__ __forceinline__ zd ldcg<zd>(const zd* p) {
 }
 
 template <class T>
-__device__ __forceinline__ T shfl_xor_t(T v, int m) {
-  return __shfl_xor_sync(0xffffffffu, v, m);
-}
-template <>
-__device__ __forceinline__ zd shfl_xor_t<zd>(zd v, int m) {
-  return make_zd(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
-}
-
-template <class T>
 __global__ void __launch_bounds__(PANEL_THREADS, 1) qr_panel_kernel(PanelArgs<T> a) {
   using R = typename Sc<T>::real;
   extern __shared__ __align__(16) unsigned char smem_raw[];

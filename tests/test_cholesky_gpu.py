@@ -1,0 +1,94 @@
+"""K6 parity: cholRecursive!(A, Val{:L}) (reference src/cholesky.jl:37-55) and the generic Hermitian
+rank-k update (src/juliaBLAS.jl:89-112) through the C ABI vs the oracle; grid of test/cholesky.jl:8-27
+and test/juliaBLAS.jl:10-17."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.float32: 3e-5, np.float64: 1e-12, np.complex128: 1e-12}
+
+
+def _spd(rng, n, dtype, shift=0.0):
+    A = rng.random((n, n))
+    if dtype == np.complex128:
+        A = A + 1j * rng.random((n, n))
+    A = A.astype(dtype)
+    S = A.conj().T @ A + shift * np.eye(n, dtype=dtype)
+    return np.asfortranarray(S.astype(dtype))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex128])
+@pytest.mark.parametrize("cutoff", [1, 4])
+def test_reference_grid_n50(gla, oracle, dtype, cutoff):
+    """test/cholesky.jl: n = 50, AcA = A'A, A = rand(n,n); compared with LAPACK potrf and the oracle."""
+    rng = np.random.default_rng(123)
+    S = _spd(rng, 50, dtype, shift=1.0 if dtype == np.float32 else 0.0)
+    ref = oracle.chol_recursive(S, cutoff)
+    got = gla.cholRecursive_(S.copy(order="F"), "L", cutoff)
+    scale = np.max(np.abs(ref))
+    assert np.max(np.abs(np.tril(got) - np.tril(ref))) <= TOL[dtype] * scale * 50
+    L = np.linalg.cholesky(S.astype(np.complex128 if dtype == np.complex128 else np.float64))
+    assert np.max(np.abs(np.tril(got) - L)) <= TOL[dtype] * scale * 50
+    # the strict upper triangle is left untouched (src/cholesky.jl:54 returns LowerTriangular(A))
+    assert np.array_equal(np.triu(got, 1), np.triu(S, 1))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex128])
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 127, 200, 257, 640])
+def test_sizes_vs_oracle(gla, oracle, dtype, n):
+    rng = np.random.default_rng(n)
+    S = _spd(rng, n, dtype, shift=float(n))
+    ref = oracle.chol_recursive(S, 1, mt=True)
+    got = gla.cholRecursive_(S.copy(order="F"))
+    scale = np.max(np.abs(ref))
+    assert np.max(np.abs(np.tril(got) - np.tril(ref))) <= TOL[dtype] * scale * max(n, 10)
+    assert np.array_equal(np.triu(got, 1), np.triu(S, 1))
+
+
+def test_known_answer(gla):
+    A = np.asfortranarray(np.array([[4.0, 2.0], [2.0, 5.0]]))
+    got = gla.cholRecursive_(A)
+    assert np.array_equal(got, np.array([[2.0, 2.0], [1.0, 2.0]]))
+
+
+def test_not_positive_definite_raises_domain_error(gla):
+    A = np.asfortranarray(np.eye(100))
+    A[70, 70] = -1.0
+    with pytest.raises(gla.DomainError) as ei:
+        gla.cholRecursive_(A)
+    assert "71" in str(ei.value)
+    with pytest.raises(gla.DimensionMismatch):
+        gla.cholRecursive_(np.zeros((3, 4), order="F"))
+
+
+def test_config2_4096(gla, oracle):
+    """BASELINE config 2: A = X'X + n I, n = 4096, Float64: residual + parity with the oracle."""
+    n = 4096
+    rng = np.random.default_rng(123)
+    X = rng.standard_normal((n, n))
+    S = np.asfortranarray(X.T @ X + n * np.eye(n))
+    got = gla.cholRecursive_(S.copy(order="F"))
+    L = np.tril(got)
+    assert np.linalg.norm(L @ L.T - S) / np.linalg.norm(S) <= 10 * n * 2.2e-16
+    ref = oracle.chol_recursive(S, 1, mt=True)
+    assert np.max(np.abs(L - np.tril(ref))) <= 1e-10 * np.max(np.abs(ref))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex128])
+@pytest.mark.parametrize("n,k", [(5, 2), (5, 1), (130, 70), (300, 33)])
+def test_rank_update_lower(gla, oracle, dtype, n, k):
+    """test/juliaBLAS.jl:10-17: C + alpha*B*B' on the lower triangle, generic method == oracle."""
+    rng = np.random.default_rng(n + k)
+    Cm = _spd(rng, n, dtype)
+    B = rng.standard_normal((n, k))
+    if dtype == np.complex128:
+        B = B + 1j * rng.standard_normal((n, k))
+    B = np.asfortranarray(B.astype(dtype))
+    for alpha in (0.5, -1.0):
+        ref = oracle.rank_update_lower(Cm, B, alpha)
+        got = gla.rankUpdate_(Cm.copy(order="F"), B, alpha)
+        assert np.max(np.abs(np.tril(got) - np.tril(ref))) <= TOL[dtype] * 10 * np.max(np.abs(ref))
+        assert np.array_equal(np.triu(got, 1), np.triu(Cm, 1))
+        full = Cm + alpha * (B @ B.conj().T)
+        assert np.max(np.abs(np.tril(got) - np.tril(full))) <= TOL[dtype] * 10 * np.max(np.abs(full))
