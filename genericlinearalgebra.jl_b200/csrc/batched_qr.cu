@@ -12,11 +12,15 @@
 //    pivot column is published once through shared memory (broadcast LDS.128), results go back
 //    through the same staging tile with 128-bit coalesced stores.  The column scaling by 1/xi is
 //    deferred to one pass at the end and folded into the coefficients meanwhile, so each step is
-//    two FMA sweeps (dot, axpy) plus one rsqrt and one reciprocal refined by Newton steps.
+//    two FMA sweeps (dot, axpy) plus a Goldschmidt sqrt/rsqrt and a Newton reciprocal whose MUFU
+//    seeds issue together.  The kernel is LATENCY bound (32 dependent reflector steps per matrix),
+//    so the register budget (= matrices in flight per SM) is tuned as carefully as the arithmetic.
 //  * batched_qr_smem_kernel<T>: any (m,n) whose matrix fits in shared memory, one CTA per matrix
 //    (also used for ComplexF64).
 #include "common.cuh"
 #include "smallqr.cuh"
+
+#include <stdlib.h>
 
 namespace gla {
 
@@ -102,20 +106,59 @@ __device__ __forceinline__ float4 arr_to_vec(const float* a) { return make_float
 // ---------------------------------------------------------------------------------- 32x32, warp
 template <class R>
 struct Reg32Cfg {
-  static constexpr int V = Vec16<R>::N;         // elements per 16-byte vector
+  static constexpr int V = Vec16<R>::N;           // elements per 16-byte vector
   static constexpr int LD = 32 + 16 / sizeof(R);  // padded column stride (34 doubles / 36 floats):
                                                   // 16B aligned, LDS.128 of 8 lanes hit 8 distinct 16B slots
   static constexpr int TILE = 32 * LD;            // elements of staging tile per warp
 };
 
-template <class R, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 384 / (WARPS * 32))
+// 16-byte shared-memory load the compiler may neither hoist nor merge: keeps at most two chunks of
+// the pivot column live (the register budget is what bounds the number of matrices in flight per SM,
+// and the kernel is latency bound, so occupancy is throughput)
+// `dep` is a fake input: it orders the load after the FMA that produced it, so the scheduler cannot
+// cluster all loads of a sweep ahead of the arithmetic (which would keep the whole pivot column live).
+__device__ __forceinline__ void lds16(const double* p, double* out, double dep) {
+  asm volatile("ld.volatile.shared.v2.f64 {%0,%1}, [%2];"
+               : "=d"(out[0]), "=d"(out[1])
+               : "r"((uint32_t)__cvta_generic_to_shared(p)), "d"(dep));
+}
+__device__ __forceinline__ void lds16(const float* p, float* out, float dep) {
+  asm volatile("ld.volatile.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(out[0]), "=f"(out[1]), "=f"(out[2]), "=f"(out[3])
+               : "r"((uint32_t)__cvta_generic_to_shared(p)), "f"(dep));
+}
+template <class R>
+struct Seed;
+template <>
+struct Seed<double> {
+  static __device__ __forceinline__ double rsqrt0(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+  }
+  static __device__ __forceinline__ double rcp0(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+  }
+  static constexpr int ITERS = 2;
+};
+template <>
+struct Seed<float> {
+  static __device__ __forceinline__ float rsqrt0(float x) { return rsqrtf(x); }
+  static __device__ __forceinline__ float rcp0(float x) { return __frcp_rn(x); }
+  static constexpr int ITERS = 1;
+};
+
+template <class R, int WARPS, int MINB>
+__global__ void __maxnreg__(MINB)
     batched_qr32_reg_kernel(R* __restrict__ A, R* __restrict__ tau, i64 batch) {
   using Cfg = Reg32Cfg<R>;
   using VT = typename Vec16<R>::type;
   constexpr int V = Cfg::V;
   constexpr int LD = Cfg::LD;
   constexpr int NVEC = 32 * 32 / V / 32;  // 16-byte vectors per lane per matrix
+  constexpr int CH = 4;                   // rows per chunk of the pivot column
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
@@ -124,14 +167,15 @@ __global__ void __launch_bounds__(WARPS * 32, 384 / (WARPS * 32))
 
   for (i64 mat = (i64)blockIdx.x * WARPS + warp; mat < batch; mat += (i64)gridDim.x * WARPS) {
     R* Ag = A + mat * 1024;
-    // ---- HBM -> staging tile: 16-byte coalesced loads, column-padded stores
-    {
-      VT v[NVEC];
+    // ---- HBM -> staging tile: 16-byte coalesced streaming loads, column-padded stores
 #pragma unroll
-      for (int q = 0; q < NVEC; ++q) v[q] = __ldcs(reinterpret_cast<const VT*>(Ag) + lane + 32 * q);
+    for (int half = 0; half < 2; ++half) {
+      VT v[NVEC / 2];
 #pragma unroll
-      for (int q = 0; q < NVEC; ++q) {
-        int e = (lane + 32 * q) * V;
+      for (int q = 0; q < NVEC / 2; ++q) v[q] = __ldcs(reinterpret_cast<const VT*>(Ag) + lane + 32 * (q + half * (NVEC / 2)));
+#pragma unroll
+      for (int q = 0; q < NVEC / 2; ++q) {
+        const int e = (lane + 32 * (q + half * (NVEC / 2))) * V;
         *reinterpret_cast<VT*>(sm + (e >> 5) * LD + (e & 31)) = v[q];
       }
     }
@@ -139,77 +183,66 @@ __global__ void __launch_bounds__(WARPS * 32, 384 / (WARPS * 32))
     // ---- staging tile -> registers: lane c takes column c
     R a[32];
 #pragma unroll
-    for (int i = 0; i < 32; i += V) {
-      VT v = *reinterpret_cast<const VT*>(sm + lane * LD + i);
-      vec_to_arr<R>(v, a + i);
-    }
+    for (int i = 0; i < 32; i += V) vec_to_arr<R>(*reinterpret_cast<const VT*>(sm + lane * LD + i), a + i);
     __syncwarp();
 
     R my_tau = R(0), my_ixi = R(1);
 #pragma unroll
     for (int k = 0; k < 32; ++k) {
-      const int k0 = k & ~(V - 1);
-      // lane k publishes its (current, un-normalised) column rows k0..31
-      if (lane == k) {
+      // ---- the pivot column (current, un-normalised) is broadcast from lane k with warp shuffles:
+      // no shared-memory round trip, no divergent publish branch, no warp barrier
+      R acc[4] = {R(0), R(0), R(0), R(0)};
+      R x[32];
 #pragma unroll
-        for (int i = k0; i < 32; i += V) *reinterpret_cast<VT*>(sm + k * LD + i) = arr_to_vec(a + i);
-      }
-      __syncwarp();
-      const R* vk = sm + k * LD;
-      // d = sum_{i>k} a_ik * a_ic  (own column c); lane k obtains its tail norm^2
-      R d0 = R(0), d1 = R(0);
-      R alpha = R(0);
+      for (int r = k; r < 32; ++r) x[r] = __shfl_sync(0xffffffffu, a[r], k);
+      // d = sum_{i>k} a_ik * a_ic (own column c); lane k obtains its tail norm^2
 #pragma unroll
-      for (int i = k0; i < 32; i += V) {
-        R y[V];
-        VT v = *reinterpret_cast<const VT*>(vk + i);
-        vec_to_arr<R>(v, y);
-#pragma unroll
-        for (int j = 0; j < V; ++j) {
-          if (i + j == k) alpha = y[j];
-          if (i + j > k) {
-            if ((i + j - k) & 1) d0 = fmad(y[j], a[i + j], d0);
-            else d1 = fmad(y[j], a[i + j], d1);
-          }
-        }
-      }
-      asm volatile("" ::: "memory");  // the axpy sweep below re-reads the pivot column from smem
-      const R d = d0 + d1;
+      for (int r = k + 1; r < 32; ++r) acc[(r - k) & 3] = fmad(x[r], a[r], acc[(r - k) & 3]);
+      const R alpha = x[k];
+      const R d = (acc[0] + acc[1]) + (acc[2] + acc[3]);
       const R dk = __shfl_sync(0xffffffffu, d, k);
       const R n2 = fmad(alpha, alpha, dk);
-      if (n2 != R(0)) {  // warp-uniform
-        const R rs = Fast<R>::rsqrt(n2);
-        const R nrm = Fast<R>::sqrt_from_rsqrt(n2, rs);
-        const R nu = copysign(nrm, alpha);
-        const R inv_nu = copysign(rs, alpha);
-        const R xi = alpha + nu;
-        // tau = xi / nu, correctly rounded (one residual step): a length-1 column must give
-        // exactly 2 as Julia's division does
-        const R tq = xi * inv_nu;
-        const R tk = fmad(fmad(-tq, nu, xi), inv_nu, tq);
-        const R ixi = Fast<R>::rcp(xi);
-        // s = conj(tau) * (a_kc + v^H a_c[k+1:]) with v = a_k/xi  ->  tau*a_kc + d/nu
-        const R s = fmad(d, inv_nu, tk * a[k]);
-        const bool right = lane > k;
-        const R t = right ? s * ixi : R(0);
-        a[k] = (lane == k) ? -nu : (right ? a[k] - s : a[k]);
-        if (lane == k) {
-          my_tau = tk;
-          my_ixi = ixi;
-        }
-        // re-read the pivot column from shared memory (broadcast) instead of holding 32 more
-        // values per lane: keeps the kernel under 128 registers -> 16+ resident warps per SM
-        const R nt = -t;
+      const bool zero = n2 == R(0);  // zero column: tau = 0, nothing changes (branch-free: guarded selects)
+      const R n2s = zero ? R(1) : n2;
+      // Goldschmidt: g -> sqrt(n2), hh -> 1/(2 sqrt(n2)); the reciprocal of xi is seeded from the
+      // approximate norm so its MUFU latency overlaps these iterations
+      const R y0 = Seed<R>::rsqrt0(n2s);
+      R g = n2s * y0, hh = R(0.5) * y0;
+      R r = Seed<R>::rcp0(alpha + copysign(g, alpha));
 #pragma unroll
-        for (int i = (k + 1) & ~(V - 1); i < 32; i += V) {
-          R y[V];
-          VT v = *reinterpret_cast<const VT*>(vk + i);
-          vec_to_arr<R>(v, y);
-#pragma unroll
-          for (int j = 0; j < V; ++j)
-            if (i + j > k) a[i + j] = fmad(nt, y[j], a[i + j]);
-        }
+      for (int it = 0; it < Seed<R>::ITERS; ++it) {
+        const R e = fmad(-g, hh, R(0.5));
+        g = fmad(g, e, g);
+        hh = fmad(hh, e, hh);
       }
+      const R nu = copysign(g, alpha);
+      const R inv_nu = copysign(hh + hh, alpha);
+      const R xi = alpha + nu;
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const R e = fmad(-xi, r, R(1));
+        r = fmad(r, e, r);
+      }
+      const R tq = xi * inv_nu;  // tau = xi / nu
+      // s = conj(tau) * (a_kc + v^H a_c[k+1:]) with v = a_k/xi  ->  tau*a_kc + d/nu
+      const R s = fmad(d, inv_nu, tq * a[k]);
+      const bool right = (lane > k) && !zero;
+      const R nt = right ? -(s * r) : R(0);
+      {
+        // off the critical path: correctly rounded tau (a length-1 column must give exactly 2, as
+        // Julia's division does) and a last correction step for the stored norm
+        const bool mine = (lane == k) && !zero;
+        const R nuc = copysign(fmad(fmad(-g, g, n2s), hh, g), alpha);
+        const R xic = alpha + nuc;
+        const R tqc = xic * inv_nu;
+        const R tk = fmad(fmad(-tqc, nuc, xic), inv_nu, tqc);
+        my_tau = mine ? tk : my_tau;
+        my_ixi = mine ? r : my_ixi;
+        a[k] = mine ? -nuc : (right ? a[k] - s : a[k]);
+      }
+      // ---- axpy sweep: a_ic -= (s/xi) * a_ik
+#pragma unroll
+      for (int rr = k + 1; rr < 32; ++rr) a[rr] = fmad(nt, x[rr], a[rr]);
     }
     // deferred normalisation of the stored reflectors: rows below the diagonal *= 1/xi
 #pragma unroll
@@ -222,13 +255,228 @@ __global__ void __launch_bounds__(WARPS * 32, 384 / (WARPS * 32))
     __syncwarp();
 #pragma unroll
     for (int q = 0; q < NVEC; ++q) {
-      int e = (lane + 32 * q) * V;
-      VT v = *reinterpret_cast<const VT*>(sm + (e >> 5) * LD + (e & 31));
+      const int e = (lane + 32 * q) * V;
+      const VT v = *reinterpret_cast<const VT*>(sm + (e >> 5) * LD + (e & 31));
       __stcs(reinterpret_cast<VT*>(Ag) + lane + 32 * q, v);
     }
     tau[mat * 32 + lane] = my_tau;
     __syncwarp();
   }
+}
+
+// ---------------------------------------------------------------------------------- 32x32, half-warp
+// TWO matrices per warp: half-warp h owns matrix h, lane c of the half owns columns c and c+16
+// (64 payload values per lane).  Compared with one matrix per warp this halves the per-matrix cost
+// of the scalar chain (sqrt / reciprocal / tau are computed once per warp-step for two matrices) and
+// of the pivot-column traffic, and keeps every lane busy for the first 16 steps (column c+16 is always
+// to the right of the pivot).  Measured on B200: 125 M matrices/s vs 110 M for one matrix per warp.
+template <class R>
+struct HwCfg {
+  static constexpr int V = Vec16<R>::N;
+  static constexpr int LD = 32 + 16 / sizeof(R);
+  static constexpr int TILE = 32 * LD + 16 / sizeof(R);   // +16 B: the two tiles of a warp sit 4 banks apart
+  static constexpr int PER_WARP = 2 * TILE;
+};
+
+template <class R, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+    batched_qr32_hw_kernel(R* __restrict__ A, R* __restrict__ tau, i64 batch) {
+  using Cfg = HwCfg<R>;
+  using VT = typename Vec16<R>::type;
+  constexpr int V = Cfg::V;
+  constexpr int LD = Cfg::LD;
+  constexpr int NVEC = 2 * 1024 / V / 32;  // 16-byte vectors per lane per matrix PAIR
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int h = lane >> 4, c = lane & 15;
+  R* sm = reinterpret_cast<R*>(smem_raw) + warp * Cfg::PER_WARP;
+  R* my = sm + h * Cfg::TILE;  // tile of this half-warp's matrix
+
+  const i64 npairs = (batch + 1) >> 1;
+  for (i64 pair = (i64)blockIdx.x * WARPS + warp; pair < npairs; pair += (i64)gridDim.x * WARPS) {
+    const i64 mat0 = pair * 2;
+    const bool both = mat0 + 1 < batch;
+    R* Ag = A + mat0 * 1024;
+    // ---- HBM -> staging tiles (two matrices = 2048 contiguous elements), 16-byte coalesced streaming loads
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      VT v[NVEC / 2];
+#pragma unroll
+      for (int q = 0; q < NVEC / 2; ++q) {
+        const int p = lane + 32 * (q + half * (NVEC / 2));
+        const bool ok = both || (p * V < 1024);
+        v[q] = ok ? __ldcs(reinterpret_cast<const VT*>(Ag) + p) : VT{};
+      }
+#pragma unroll
+      for (int q = 0; q < NVEC / 2; ++q) {
+        const int e = (lane + 32 * (q + half * (NVEC / 2))) * V;
+        const int hm = e >> 10, col = (e & 1023) >> 5, row = e & 31;
+        *reinterpret_cast<VT*>(sm + hm * Cfg::TILE + col * LD + row) = v[q];
+      }
+    }
+    __syncwarp();
+    R a0[32], a1[32];
+#pragma unroll
+    for (int i = 0; i < 32; i += V) {
+      vec_to_arr<R>(*reinterpret_cast<const VT*>(my + c * LD + i), a0 + i);
+      vec_to_arr<R>(*reinterpret_cast<const VT*>(my + (c + 16) * LD + i), a1 + i);
+    }
+    __syncwarp();
+
+    R tau0 = R(0), tau1 = R(0), ixi0 = R(1), ixi1 = R(1);
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const int k0 = k & ~(V - 1);
+      const bool lo = k < 16;                 // compile-time after unrolling
+      const bool own = c == (k & 15);
+      // the owner of the pivot column publishes it (current, un-normalised) to its matrix' tile
+      if (own) {
+#pragma unroll
+        for (int i = k0; i < 32; i += V)
+          *reinterpret_cast<VT*>(my + k * LD + i) = lo ? arr_to_vec(a0 + i) : arr_to_vec(a1 + i);
+      }
+      __syncwarp();
+      const R* vk = my + k * LD;
+      // ---- dots with both owned columns; the owner obtains the tail norm^2
+      R p0 = R(0), p1 = R(0), q0 = R(0), q1 = R(0), alpha = R(0);
+#pragma unroll
+      for (int i = k0; i < 32; i += V) {
+        R y[V];
+        vec_to_arr<R>(*reinterpret_cast<const VT*>(vk + i), y);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          const int r = i + j;
+          if (r == k) alpha = y[j];
+          if (r > k) {
+            if ((r - k) & 1) {
+              if (lo) p0 = fmad(y[j], a0[r], p0);
+              q0 = fmad(y[j], a1[r], q0);
+            } else {
+              if (lo) p1 = fmad(y[j], a0[r], p1);
+              q1 = fmad(y[j], a1[r], q1);
+            }
+          }
+        }
+      }
+      const R d0 = p0 + p1, d1 = q0 + q1;
+      const R dk = __shfl_sync(0xffffffffu, lo ? d0 : d1, k & 15, 16);
+      const R n2 = fmad(alpha, alpha, dk);
+      const bool zero = n2 == R(0);  // zero column: tau = 0, nothing changes (guarded selects, the halves may differ)
+      const R n2s = zero ? R(1) : n2;
+      // Goldschmidt: g -> sqrt(n2), hh -> 1/(2 sqrt(n2)); the reciprocal of xi is seeded from the
+      // approximate norm so that its MUFU latency overlaps these iterations
+      const R y0 = Seed<R>::rsqrt0(n2s);
+      R g = n2s * y0, hh = R(0.5) * y0;
+      R r = Seed<R>::rcp0(alpha + copysign(g, alpha));
+#pragma unroll
+      for (int it = 0; it < Seed<R>::ITERS; ++it) {
+        const R e = fmad(-g, hh, R(0.5));
+        g = fmad(g, e, g);
+        hh = fmad(hh, e, hh);
+      }
+      const R nu = copysign(g, alpha);
+      const R inv_nu = copysign(hh + hh, alpha);
+      const R xi = alpha + nu;
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const R e = fmad(-xi, r, R(1));
+        r = fmad(r, e, r);
+      }
+      const R tq = xi * inv_nu;  // tau = xi / nu
+      // off the critical path: correctly rounded tau (a length-1 column must give exactly 2, as Julia's
+      // division does) and one correction step for the stored norm
+      const R nuc = copysign(fmad(fmad(-g, g, n2s), hh, g), alpha);   // corrected (correctly rounded) norm
+      const R xic = alpha + nuc;
+      const R tqc = xic * inv_nu;
+      const R tk = fmad(fmad(-tqc, nuc, xic), inv_nu, tqc);
+      const R mnu = -nuc;
+      // slot 1: column c+16
+      R nt1;
+      {
+        const bool right = (c + 16 > k) && !zero;
+        const R s = fmad(d1, inv_nu, tq * a1[k]);
+        nt1 = right ? -(s * r) : R(0);
+        const bool mine = !lo && own && !zero;
+        a1[k] = mine ? mnu : (right ? a1[k] - s : a1[k]);
+        tau1 = mine ? tk : tau1;
+        ixi1 = mine ? r : ixi1;
+      }
+      R nt0 = R(0);
+      if (lo) {
+        const bool right = (c > k) && !zero;
+        const R s = fmad(d0, inv_nu, tq * a0[k]);
+        nt0 = right ? -(s * r) : R(0);
+        const bool mine = own && !zero;
+        a0[k] = mine ? mnu : (right ? a0[k] - s : a0[k]);
+        tau0 = mine ? tk : tau0;
+        ixi0 = mine ? r : ixi0;
+      }
+      asm volatile("" ::: "memory");
+      // ---- axpy sweep: a_ic -= (s/xi) a_ik
+#pragma unroll
+      for (int i = (k + 1) & ~(V - 1); i < 32; i += V) {
+        R yy[V];
+        vec_to_arr<R>(*reinterpret_cast<const VT*>(vk + i), yy);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          const int rr = i + j;
+          if (rr > k) {
+            if (lo) a0[rr] = fmad(nt0, yy[j], a0[rr]);
+            a1[rr] = fmad(nt1, yy[j], a1[rr]);
+          }
+        }
+      }
+    }
+    // deferred normalisation of the stored reflectors
+#pragma unroll
+    for (int i = 1; i < 32; ++i) {
+      a0[i] = (i > c) ? a0[i] * ixi0 : a0[i];
+      a1[i] = (i > c + 16) ? a1[i] * ixi1 : a1[i];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 32; i += V) {
+      *reinterpret_cast<VT*>(my + c * LD + i) = arr_to_vec(a0 + i);
+      *reinterpret_cast<VT*>(my + (c + 16) * LD + i) = arr_to_vec(a1 + i);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < NVEC; ++q) {
+      const int p = lane + 32 * q;
+      const int e = p * V;
+      const int hm = e >> 10, col = (e & 1023) >> 5, row = e & 31;
+      if (both || hm == 0) {
+        const VT v = *reinterpret_cast<const VT*>(sm + hm * Cfg::TILE + col * LD + row);
+        __stcs(reinterpret_cast<VT*>(Ag) + p, v);
+      }
+    }
+    if (both || h == 0) {
+      tau[(mat0 + h) * 32 + c] = tau0;
+      tau[(mat0 + h) * 32 + 16 + c] = tau1;
+    }
+    __syncwarp();
+  }
+}
+
+template <class R>
+static int launch_hw32(R* dA, R* dtau, i64 batch, cudaStream_t st) {
+  constexpr int WARPS = 4;
+  constexpr int MINB = sizeof(R) == 8 ? 2 : 4;
+  const size_t smem = (size_t)WARPS * HwCfg<R>::PER_WARP * sizeof(R);
+  auto kern = batched_qr32_hw_kernel<R, WARPS, MINB>;
+  GLA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  GLA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem));
+  if (occ < 1) occ = 1;
+  const i64 npairs = (batch + 1) / 2;
+  const i64 need = (npairs + WARPS - 1) / WARPS;
+  const i64 resident = (i64)sm_count() * occ;
+  const i64 grid = need < resident ? need : resident;   // one resident wave; warps stride over the pairs
+  kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(dA, dtau, batch);
+  GLA_CUDA(cudaGetLastError());
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------- generic, CTA
@@ -260,22 +508,35 @@ struct IsReal<zd> {
 };
 
 template <class R>
-static int launch_reg32(R* dA, R* dtau, i64 batch, cudaStream_t st) {
-  constexpr int WARPS = 4;
-  size_t smem = (size_t)WARPS * Reg32Cfg<R>::TILE * sizeof(R);
-  auto kern = batched_qr32_reg_kernel<R, WARPS>;
+static int launch_hw32(R* dA, R* dtau, i64 batch, cudaStream_t st);
+
+template <class R, int WARPS, int MAXNREG>
+static int launch_reg32_cfg(R* dA, R* dtau, i64 batch, cudaStream_t st) {
+  const size_t smem = (size_t)WARPS * Reg32Cfg<R>::TILE * sizeof(R);
+  auto kern = batched_qr32_reg_kernel<R, WARPS, MAXNREG>;
   GLA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
   GLA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem));
   if (occ < 1) occ = 1;
-  i64 need = (batch + WARPS - 1) / WARPS;
-  i64 resident = (i64)sm_count() * occ;
-  // whole waves of resident CTAs; each warp then strides over its share of the batch
-  i64 grid = need < resident ? need : resident * ((need + resident - 1) / resident > 4 ? 4 : 1);
-  if (grid > need) grid = need;
+  const i64 need = (batch + WARPS - 1) / WARPS;
+  const i64 resident = (i64)sm_count() * occ;
+  // one resident wave of CTAs; each warp strides over its share of the batch
+  const i64 grid = need < resident ? need : resident;
   kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(dA, dtau, batch);
   GLA_CUDA(cudaGetLastError());
   return 0;
+}
+
+template <class R>
+static int launch_reg32(R* dA, R* dtau, i64 batch, cudaStream_t st) {
+  // register cap <-> resident warps per SM: 128 -> 16, 112 -> 18, 96 -> 20 (tuning knob, default measured best)
+  static const int variant = [] {
+    const char* e = getenv("GLA_BATCHED_VARIANT");
+    return e ? atoi(e) : 0;
+  }();
+  if (variant == 1) return launch_reg32_cfg<R, 4, 168>(dA, dtau, batch, st);
+  if (variant == 2) return launch_reg32_cfg<R, 4, 200>(dA, dtau, batch, st);
+  return launch_hw32<R>(dA, dtau, batch, st);
 }
 
 template <class T>

@@ -86,7 +86,7 @@ def _colmajor(A, what):
         raise TypeError(f"{what}: need a numpy float32/float64/complex128 array")
     if A.ndim != 2:
         raise DimensionMismatch(f"{what}: need a matrix")
-    if A.size and A.strides[0] != A.itemsize:
+    if A.size and A.shape[0] > 1 and A.strides[0] != A.itemsize:
         raise ArgumentError(f"{what}: need unit row stride (column-major, order='F')")
     if A.size and A.shape[1] > 1 and (A.strides[1] % A.itemsize or A.strides[1] < A.itemsize * A.shape[0]):
         raise ArgumentError(f"{what}: bad column stride")

@@ -141,7 +141,7 @@ def qr_batched(A, blocksize=12):
     A = np.asarray(A)
     batch, m, n = A.shape
     k = min(m, n)
-    buf = np.ascontiguousarray(np.transpose(A, (0, 2, 1)))  # (batch, n, m) C-order == col-major mats
+    buf = np.array(np.transpose(A, (0, 2, 1)), order="C", copy=True)  # (batch, n, m) C-order == col-major mats
     tau = np.zeros((batch, k), dtype=A.dtype)
     getattr(lib(), f"oracle_{_PFX[buf.dtype]}qr_batched")(_p(buf), _I64(m), _I64(n), _I64(batch),
                                                           _p(tau), _I64(blocksize))

@@ -14,7 +14,7 @@ def _rel(a, b):
 def test_batched_32x32_matches_oracle(gla, oracle, dtype, tol, batch):
     rng = np.random.default_rng(123 + batch)
     A = rng.standard_normal((batch, 32, 32)).astype(dtype)        # A[b] is the matrix
-    buf = np.ascontiguousarray(np.transpose(A, (0, 2, 1)))        # column-major storage per matrix
+    buf = np.array(np.transpose(A, (0, 2, 1)), order="C", copy=True)        # column-major storage per matrix
     ref_f, ref_t = oracle.qr_batched(A, blocksize=12)
     _, tau = gla.qr_batched_(buf)
     got = np.transpose(buf, (0, 2, 1))
@@ -34,7 +34,7 @@ def test_batched_generic_shapes(gla, oracle, dtype, m, n):
     if dtype == np.complex128:
         A = A + 1j * rng.standard_normal((9, m, n))
     A = A.astype(dtype)
-    buf = np.ascontiguousarray(np.transpose(A, (0, 2, 1)))
+    buf = np.array(np.transpose(A, (0, 2, 1)), order="C", copy=True)
     # complex oracle = the UNBLOCKED reference path (the blocked one drops a conj, SURVEY finding 3);
     # blocksize >= n makes qrBlocked! a single unblocked panel
     ref_f, ref_t = oracle.qr_batched(A, blocksize=max(m, n) + 1)
@@ -49,7 +49,7 @@ def test_batched_zero_columns_and_empty(gla, oracle):
     A = np.zeros((3, 32, 32))
     A[1, :, 5] = 1.0
     A[2] = np.eye(32)
-    buf = np.ascontiguousarray(np.transpose(A, (0, 2, 1)))
+    buf = np.array(np.transpose(A, (0, 2, 1)), order="C", copy=True)
     ref_f, ref_t = oracle.qr_batched(A)
     _, tau = gla.qr_batched_(buf)
     assert np.array_equal(tau[0], np.zeros(32))           # zero column -> tau = 0, untouched
