@@ -4,7 +4,8 @@
 // stdlib reflector!/reflectorApply! call sites :96/:102)  ->  T build (src/qr.jl:64-83, with the conj
 // the reference omits at :72)  ->  trailing update A2 <- (I - V T^H V^H) A2 (src/householder.jl:119-157).
 //
-// GPU structure per panel of NB = 64 columns:
+// GPU structure: panels of NB = 64 columns, grouped four at a time into outer blocks of NBO = 256 whose
+// reflectors hit the far trailing matrix in one K = 256 pass (wy_fixup_kernel).  Per panel:
 //   qr_panel_kernel   cooperative, P CTAs each holding a row slab of the panel in shared memory;
 //                     ONE grid-wide reduction per column: every CTA publishes the partial dots
 //                     d_c = sum_{i>j} conj(a_ij) a_ic of the un-normalised pivot column with every
@@ -39,7 +40,8 @@ struct PanelArgs {
   T* tau;      // tau + k0
   T* Vc;       // mk x kk clean reflectors (ld = ldvc)
   i64 ldvc;
-  T* VcT;      // kk x mk (ld = NB)
+  T* VcT;      // kk x mk (ld = ldvct)
+  i64 ldvct;
   T* partial;  // [2][P][NB]
   T* rowj;     // [2][NB]
   unsigned* counter;
@@ -195,21 +197,21 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) qr_panel_kernel(PanelArgs<T>
     const int col = e % kk, i = e / kk;
     const int gi = r0 + i;
     T v = gi < col ? Sc<T>::zero() : (gi == col ? Sc<T>::one() : S[i + (i64)col * ld]);
-    a.VcT[(i64)gi * NB + col] = v;
+    a.VcT[(i64)gi * a.ldvct + col] = v;
   }
 }
 
 // ------------------------------------------------------------------------------- clean V from factors
-// Vc (mk x kk, ldvc) and VcT (kk x mk, ld NB) from the factored panel F (unit lower trapezoid)
+// Vc (mk x kk, ldvc) and VcT (kk x mk, ldvct) from the factored panel F (unit lower trapezoid)
 template <class T>
 __global__ void extract_v_kernel(const T* __restrict__ F, i64 ldf, int mk, int kk, T* __restrict__ Vc, i64 ldvc,
-                                 T* __restrict__ VcT) {
+                                 T* __restrict__ VcT, i64 ldvct) {
   const i64 total = (i64)mk * kk;
   for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
     const int col = (int)(e / mk), i = (int)(e - (i64)col * mk);
     T v = i < col ? Sc<T>::zero() : (i == col ? Sc<T>::one() : F[(i64)col * ldf + i]);
     Vc[(i64)col * ldvc + i] = v;
-    VcT[(i64)i * NB + col] = v;
+    VcT[(i64)i * ldvct + col] = v;
   }
 }
 
@@ -296,46 +298,128 @@ __global__ void __launch_bounds__(256) apply_t_kernel(const T* __restrict__ Wp, 
   }
 }
 
+// ------------------------------------------------------------------------------- outer-block fix-up
+// Two-level blocking: NBO/NB consecutive panels form one OUTER block whose reflectors are applied to the
+// far trailing matrix in a single pass with K = NBO (K = NB would make that pass HBM-bound: 16 B of C
+// traffic per 2*NB flops).  With V = [V_0 .. V_{nj-1}], W = V^H A2 and G = V^H V, the product
+// Q_{nj-1}^H ... Q_0^H A2 = A2 - V Z follows from the block recurrence
+//     Y_j = W_j - sum_{i<j} G_ji Z_i ,   Z_j = T_j^H Y_j ,
+// which needs only the per-panel T_j (never the NBO x NBO T).  One CTA handles 32 columns of W.
+template <class T>
+__global__ void __launch_bounds__(256)
+    wy_fixup_kernel(const T* __restrict__ Wp, i64 wstride, int nsplit, int kbig, i64 nA, const T* __restrict__ G,
+                    i64 ldg, const T* __restrict__ Tm, int ldw, T* __restrict__ Z) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  typedef T RowW[32 + 1];
+  typedef T RowM[NB + 1];
+  RowW* sW = reinterpret_cast<RowW*>(smem_raw);          // sW[l][jj], l < kbig
+  RowM* sM = reinterpret_cast<RowM*>(sW + kbig);         // 64 x 64 operand block
+  const int tid = threadIdx.x;
+  const int jj = tid & 31, rq = tid >> 5;                 // column within the 32, row phase (8 phases)
+  const i64 col = (i64)blockIdx.x * 32 + jj;
+  for (int l = rq; l < kbig; l += 8) {
+    T w = Sc<T>::zero();
+    if (col < nA) {
+      w = Wp[col * ldw + l];
+      for (int z = 1; z < nsplit; ++z) w = w + Wp[(i64)z * wstride + col * ldw + l];
+    }
+    sW[l][jj] = w;
+  }
+  const int nj = (kbig + NB - 1) / NB;
+  for (int j = 0; j < nj; ++j) {
+    const int rows_j = (kbig - j * NB) < NB ? (kbig - j * NB) : NB;
+    for (int i = 0; i < j; ++i) {
+      __syncthreads();
+      for (int e = tid; e < rows_j * NB; e += 256) {       // sM[r][l] = G(jNB + r, iNB + l)
+        const int l = e / rows_j, r = e - l * rows_j;
+        sM[r][l] = G[(i64)(i * NB + l) * ldg + j * NB + r];
+      }
+      __syncthreads();
+      for (int r = rq; r < rows_j; r += 8) {
+        T acc = Sc<T>::zero();
+#pragma unroll 8
+        for (int l = 0; l < NB; ++l) acc = fmad(sM[r][l], sW[i * NB + l][jj], acc);
+        sW[j * NB + r][jj] = sW[j * NB + r][jj] - acc;     // only this thread touches (jNB+r, jj)
+      }
+    }
+    __syncthreads();
+    const T* Tj = Tm + (i64)j * NB * NB;
+    for (int e = tid; e < rows_j * rows_j; e += 256) {     // sM[r][l] = conj(T_j(l, r)), l <= r
+      const int r = e / rows_j, l = e - r * rows_j;
+      sM[r][l] = l <= r ? cj(Tj[(i64)r * NB + l]) : Sc<T>::zero();
+    }
+    __syncthreads();
+    T out[NB / 8];
+#pragma unroll
+    for (int u = 0; u < NB / 8; ++u) {
+      const int r = rq + 8 * u;
+      T acc = Sc<T>::zero();
+      if (r < rows_j)
+        for (int l = 0; l <= r; ++l) acc = fmad(sM[r][l], sW[j * NB + l][jj], acc);
+      out[u] = acc;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < NB / 8; ++u) {
+      const int r = rq + 8 * u;
+      if (r < rows_j) sW[j * NB + r][jj] = out[u];
+    }
+  }
+  __syncthreads();
+  if (col < nA)
+    for (int l = rq; l < kbig; l += 8) Z[col * ldw + l] = sW[l][jj];
+}
+
 // ------------------------------------------------------------------------------- workspace
+constexpr int NBO = 256;  // outer block: K of the far trailing contractions
+
 template <class T>
 struct QrWork {
-  T* Vc = nullptr;
-  i64 ldvc = 0;
-  T* VcT = nullptr;
-  T* Gp = nullptr;   // split-K partials of G
-  T* Tm = nullptr;   // NB x NB
-  T* Wp = nullptr;   // split-K partials of W
-  T* W2 = nullptr;   // NB x nA
+  T* V = nullptr;     // m x NBO clean reflectors of the current outer block (unit diagonal, zeros above)
+  i64 ldv = 0;
+  T* VT = nullptr;    // NBO x m transpose (ld NBO)
+  T* Tm = nullptr;    // NBO/NB per-panel T factors, NB x NB each
+  T* G = nullptr;     // NBO x NBO Gram V^H V (ld NBO)
+  T* Gp = nullptr;    // split-K partials of a Gram
+  T* Wp = nullptr;    // split-K partials of W = V^H A2
+  T* Z = nullptr;     // NBO x nA
   T* partial = nullptr;
   T* rowj = nullptr;
   unsigned* counter = nullptr;
   void* block = nullptr;
   cudaStream_t st = nullptr;
   i64 wp_elems = 0;
+  static constexpr int GP_SPLITS = 32;
 
-  int alloc(i64 m, i64 nA_max, int max_wsplit, cudaStream_t stream) {
+  int alloc(i64 m, i64 nA_max, cudaStream_t stream) {
     st = stream;
-    ldvc = round_up(m, 2);
+    ldv = round_up(m, 2);
+    if (nA_max < 1) nA_max = 1;
     auto al = [](i64 bytes) { return round_up(bytes, 256); };
-    const i64 s_vc = al(ldvc * NB * sizeof(T));
-    const i64 s_vct = al((i64)NB * m * sizeof(T));
-    const i64 s_gp = al((i64)64 * NB * NB * sizeof(T));
-    const i64 s_tm = al((i64)NB * NB * sizeof(T));
-    wp_elems = (i64)max_wsplit * NB * (nA_max > 0 ? nA_max : 1);
+    const i64 s_v = al(ldv * NBO * sizeof(T));
+    const i64 s_vt = al((i64)NBO * m * sizeof(T));
+    const i64 s_tm = al((i64)NBO * NB * sizeof(T));
+    const i64 s_g = al((i64)NBO * NBO * sizeof(T));
+    const i64 s_gp = al((i64)GP_SPLITS * NBO * NBO * sizeof(T));
+    // W partials: at most ~2*SMs tiles worth of split-K slices; sized as 6 full W matrices, never less than
+    // what a 64-slice split of a narrow (<= 4*NBO columns) W needs
+    i64 wcols = 6 * nA_max;
+    if (wcols < 64 * 4 * NBO && nA_max <= 4 * NBO) wcols = 64 * nA_max;
+    wp_elems = (i64)NBO * wcols;
     const i64 s_wp = al(wp_elems * sizeof(T));
-    const i64 s_w2 = al((i64)NB * (nA_max > 0 ? nA_max : 1) * sizeof(T));
+    const i64 s_z = al((i64)NBO * nA_max * sizeof(T));
     const i64 s_part = al((i64)2 * 256 * NB * sizeof(T));
     const i64 s_rowj = al((i64)2 * NB * sizeof(T));
-    const i64 s_cnt = 256;
-    const i64 total = s_vc + s_vct + s_gp + s_tm + s_wp + s_w2 + s_part + s_rowj + s_cnt;
+    const i64 total = s_v + s_vt + s_tm + s_g + s_gp + s_wp + s_z + s_part + s_rowj + 256;
     GLA_CUDA(cudaMallocAsync(&block, total, st));
     char* p = static_cast<char*>(block);
-    Vc = reinterpret_cast<T*>(p); p += s_vc;
-    VcT = reinterpret_cast<T*>(p); p += s_vct;
-    Gp = reinterpret_cast<T*>(p); p += s_gp;
+    V = reinterpret_cast<T*>(p); p += s_v;
+    VT = reinterpret_cast<T*>(p); p += s_vt;
     Tm = reinterpret_cast<T*>(p); p += s_tm;
+    G = reinterpret_cast<T*>(p); p += s_g;
+    Gp = reinterpret_cast<T*>(p); p += s_gp;
     Wp = reinterpret_cast<T*>(p); p += s_wp;
-    W2 = reinterpret_cast<T*>(p); p += s_w2;
+    Z = reinterpret_cast<T*>(p); p += s_z;
     partial = reinterpret_cast<T*>(p); p += s_part;
     rowj = reinterpret_cast<T*>(p); p += s_rowj;
     counter = reinterpret_cast<unsigned*>(p);
@@ -345,20 +429,35 @@ struct QrWork {
     if (block) cudaFreeAsync(block, st);
     block = nullptr;
   }
+  // views of inner panel j (columns j0 = j*NB of the outer block, rows from j0)
+  T* Vj(int j) const { return V + (i64)j * NB + (i64)j * NB * ldv; }
+  T* VTj(int j) const { return VT + (i64)j * NB * NBO + (i64)j * NB; }
+  T* Tj(int j) const { return Tm + (i64)j * NB * NB; }
 };
+
+// rows above panel j's diagonal block inside the outer block are zero in V / VT
+template <class T>
+__global__ void zero_top_kernel(T* __restrict__ V, i64 ldv, T* __restrict__ VT, int j0, int kk) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < j0 * kk; e += gridDim.x * blockDim.x) {
+    const int col = e / j0, i = e - col * j0;
+    V[(i64)(j0 + col) * ldv + i] = Sc<T>::zero();
+    VT[(i64)i * NBO + j0 + col] = Sc<T>::zero();
+  }
+}
 
 // ------------------------------------------------------------------------------- panel launch
 template <class T>
-static int launch_panel(T* A, i64 lda, i64 mk, int nb, T* tau, QrWork<T>& w, cudaStream_t st) {
+static int launch_panel(T* A, i64 lda, i64 mk, int nb, T* tau, QrWork<T>& w, int j, cudaStream_t st) {
   PanelArgs<T> a;
   a.A = A;
   a.lda = lda;
   a.mk = (int)mk;
   a.nb = nb;
   a.tau = tau;
-  a.Vc = w.Vc;
-  a.ldvc = w.ldvc;
-  a.VcT = w.VcT;
+  a.Vc = w.Vj(j);
+  a.ldvc = w.ldv;
+  a.VcT = w.VTj(j);
+  a.ldvct = NBO;
   a.partial = w.partial;
   a.rowj = w.rowj;
   a.counter = w.counter;
@@ -390,36 +489,50 @@ static int launch_panel(T* A, i64 lda, i64 mk, int nb, T* tau, QrWork<T>& w, cud
     kern<<<1, PANEL_THREADS, smem, st>>>(a);
     GLA_CUDA(cudaGetLastError());
   }
+  if (j > 0) {
+    const int kk = (int)(mk < nb ? mk : nb);
+    zero_top_kernel<T><<<ceil_div((i64)j * NB * kk, 256), 256, 0, st>>>(w.V, w.ldv, w.VT, j * NB, kk);
+    GLA_CUDA(cudaGetLastError());
+  }
   return 0;
 }
 
-// T (kk x kk) of the clean reflector block in w.Vc with tau
+// Gram of a clean reflector block: out (kk x kk, ldo) = Vc^H Vc, split-K partials summed in fixed order
 template <class T>
-static int build_T(QrWork<T>& w, i64 mk, int kk, const T* tau, cudaStream_t st) {
+static int gram(QrWork<T>& w, const T* Vc, i64 ldvc, i64 mk, int kk, T* out, i64 ldo, cudaStream_t st) {
   GemmTN<T> g;
-  g.At = w.Vc; g.ldat = w.ldvc;
-  g.B = w.Vc; g.ldb = w.ldvc;
+  g.At = Vc; g.ldat = ldvc;
+  g.B = Vc; g.ldb = ldvc;
   g.C = w.Gp; g.ldc = kk;
   g.M = kk; g.N = kk; g.K = mk;
   g.conj_a = 1;
-  g.nsplit = choose_nsplit(kk, kk, mk, 64, 128);
+  g.nsplit = choose_nsplit(kk, kk, mk, kk <= 64 ? 64 : 128, kk <= 64 ? 128 : 64);
+  if (g.nsplit > QrWork<T>::GP_SPLITS) g.nsplit = QrWork<T>::GP_SPLITS;
   g.split_stride = (i64)kk * kk + (((i64)kk * kk) & 1);
   GLA_TRY(gemm_tn<T>(g, st));
+  return sum_splits<T>(out, ldo, w.Gp, kk, g.split_stride, g.nsplit, kk, kk, st);
+}
+
+// T_j (kk x kk, ld NB) of the clean reflector block (Vc, ldvc) with tau; uses w.G as scratch for the Gram
+template <class T>
+static int build_T(QrWork<T>& w, const T* Vc, i64 ldvc, i64 mk, int kk, const T* tau, T* Tout, cudaStream_t st) {
+  GLA_TRY(gram<T>(w, Vc, ldvc, mk, kk, w.G, kk, st));
   const int smem = (2 * NB * (NB + 1) + NB) * (int)sizeof(T);
   GLA_CUDA(cudaFuncSetAttribute(larft_finish_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  larft_finish_kernel<T><<<1, 256, smem, st>>>(w.Gp, g.split_stride, g.nsplit, kk, tau, w.Tm, NB);
+  larft_finish_kernel<T><<<1, 256, smem, st>>>(w.G, 0, 1, kk, tau, Tout, NB);
   GLA_CUDA(cudaGetLastError());
   return 0;
 }
 
-static int wsplit_for(i64 kk, i64 nA, i64 mk) { return choose_nsplit(kk, nA, mk, 64, 128); }
+static int wsplit_for(i64 kk, i64 nA, i64 mk) { return choose_nsplit(kk, nA, mk, kk <= 64 ? 64 : 128, kk <= 64 ? 128 : 64); }
 
-// A2 (mk x nA, lda) <- (I - Vc op(T) Vc^H) A2 with Vc/VcT/T in w
+// A2 (mk x nA, lda) <- (I - Vc op(T) Vc^H) A2 for ONE panel (kk <= NB reflectors)
 template <class T>
-static int apply_block(QrWork<T>& w, i64 mk, int kk, T* A2, i64 lda, i64 nA, int adjoint, cudaStream_t st) {
+static int apply_panel(QrWork<T>& w, const T* Vc, i64 ldvc, const T* VcT, i64 ldvct, const T* Tj, i64 mk, int kk,
+                       T* A2, i64 lda, i64 nA, int adjoint, cudaStream_t st) {
   if (nA <= 0) return 0;
   GemmTN<T> g1;
-  g1.At = w.Vc; g1.ldat = w.ldvc;
+  g1.At = Vc; g1.ldat = ldvc;
   g1.B = A2; g1.ldb = lda;
   g1.C = w.Wp; g1.ldc = NB;
   g1.M = kk; g1.N = nA; g1.K = mk;
@@ -434,18 +547,51 @@ static int apply_block(QrWork<T>& w, i64 mk, int kk, T* A2, i64 lda, i64 nA, int
   GLA_TRY(gemm_tn<T>(g1, st));
   const int smem_t = (NB * (NB + 1) + NB * 33) * (int)sizeof(T);
   GLA_CUDA(cudaFuncSetAttribute(apply_t_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_t));
-  apply_t_kernel<T><<<(unsigned)ceil_div(nA, 32), 256, smem_t, st>>>(w.Wp, g1.split_stride, g1.nsplit, kk, nA, w.Tm, NB,
-                                                                adjoint, w.W2);
+  apply_t_kernel<T><<<(unsigned)ceil_div(nA, 32), 256, smem_t, st>>>(w.Wp, g1.split_stride, g1.nsplit, kk, nA, Tj, NB,
+                                                                      adjoint, w.Z);
   GLA_CUDA(cudaGetLastError());
   GemmTN<T> g2;
-  g2.At = w.VcT; g2.ldat = NB;
-  g2.B = w.W2; g2.ldb = NB;
+  g2.At = VcT; g2.ldat = ldvct;
+  g2.B = w.Z; g2.ldb = NB;
   g2.C = A2; g2.ldc = lda;
   g2.M = mk; g2.N = nA; g2.K = kk;
   g2.alpha = -1;
   g2.beta_one = 1;
-  GLA_TRY(gemm_tn<T>(g2, st));
-  return 0;
+  return gemm_tn<T>(g2, st);
+}
+
+// A2 (mo x nA) <- Q_{nj-1}^H ... Q_0^H A2 for the whole outer block (kbig reflectors in w.V / w.VT / w.Tm)
+template <class T>
+static int apply_outer(QrWork<T>& w, i64 mo, int kbig, T* A2, i64 lda, i64 nA, cudaStream_t st) {
+  if (nA <= 0) return 0;
+  GLA_TRY(gram<T>(w, w.V, w.ldv, mo, kbig, w.G, NBO, st));
+  GemmTN<T> g1;
+  g1.At = w.V; g1.ldat = w.ldv;
+  g1.B = A2; g1.ldb = lda;
+  g1.C = w.Wp; g1.ldc = NBO;
+  g1.M = kbig; g1.N = nA; g1.K = mo;
+  g1.conj_a = 1;
+  g1.nsplit = wsplit_for(kbig, nA, mo);
+  g1.split_stride = (i64)NBO * nA;
+  if ((i64)g1.nsplit * NBO * nA > w.wp_elems) g1.nsplit = (int)(w.wp_elems / ((i64)NBO * nA));
+  if (g1.nsplit < 1) {
+    set_error(GLA_ERR_INTERNAL, "W workspace too small", __FILE__, __LINE__);
+    return GLA_ERR_INTERNAL;
+  }
+  GLA_TRY(gemm_tn<T>(g1, st));
+  const int smem = (kbig * 33 + NB * (NB + 1)) * (int)sizeof(T);
+  GLA_CUDA(cudaFuncSetAttribute(wy_fixup_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  wy_fixup_kernel<T><<<(unsigned)ceil_div(nA, 32), 256, smem, st>>>(w.Wp, g1.split_stride, g1.nsplit, kbig, nA, w.G, NBO,
+                                                                     w.Tm, NBO, w.Z);
+  GLA_CUDA(cudaGetLastError());
+  GemmTN<T> g2;
+  g2.At = w.VT; g2.ldat = NBO;
+  g2.B = w.Z; g2.ldb = NBO;
+  g2.C = A2; g2.ldc = lda;
+  g2.M = mo; g2.N = nA; g2.K = kbig;
+  g2.alpha = -1;
+  g2.beta_one = 1;
+  return gemm_tn<T>(g2, st);
 }
 
 // ------------------------------------------------------------------------------- drivers
@@ -456,30 +602,46 @@ int geqr_blocked_dev(T* dA, i64 m, i64 n, i64 lda, T* dtau, i64 /*blocksize_hint
   if (lda < (m > 1 ? m : 1)) return -4;
   if (m == 0 || n == 0) return 0;
   QrWork<T> w;
-  // largest split-K factor any panel will ask for
-  int max_ws = 1;
-  for (i64 k0 = 0; k0 < (m < n ? m : n); k0 += NB) {
-    const i64 nA = n - k0 - NB;
-    if (nA <= 0) break;
-    const int s = wsplit_for(NB, nA, m - k0);
-    // workspace is sized for nA_max columns; a later, narrower panel may use a larger split
-    const i64 scaled = ((i64)s * nA + (n - NB) - 1) / ((n - NB) > 0 ? (n - NB) : 1);
-    if (scaled > max_ws) max_ws = (int)scaled;
-  }
-  GLA_TRY(w.alloc(m, n - NB, max_ws + 1, st));
+  GLA_TRY(w.alloc(m, n, st));
   int rc = 0;
-  for (i64 k0 = 0;; k0 += NB) {
-    const i64 mk = m - k0, nk = n - k0;
-    const int nb = (int)(nk < NB ? nk : NB);
-    const int kk = (int)(mk < nb ? mk : nb);
-    T* Ak = dA + k0 + k0 * lda;
-    if ((rc = launch_panel<T>(Ak, lda, mk, nb, dtau + k0, w, st))) break;
-    const i64 nA = nk - nb;
-    if (nA > 0) {
-      if ((rc = build_T<T>(w, mk, kk, dtau + k0, st))) break;
-      if ((rc = apply_block<T>(w, mk, kk, Ak + (i64)nb * lda, lda, nA, 1, st))) break;
+  bool done = false;
+  for (i64 o0 = 0; !done; o0 += NBO) {
+    const i64 mo = m - o0, no = n - o0;
+    const int nbo = (int)(no < NBO ? no : NBO);  // columns of this outer block
+    int kbig = 0;
+    for (int j = 0; j * NB < nbo; ++j) {
+      const i64 k0 = o0 + (i64)j * NB;
+      const i64 mk = m - k0;
+      if (mk <= 0) {  // no rows left (wide matrix): the previous panel was the last one
+        done = true;
+        break;
+      }
+      const int nb = (int)(n - k0 < NB ? n - k0 : NB);
+      const int kk = (int)(mk < nb ? mk : nb);
+      T* Ak = dA + k0 + k0 * lda;
+      if ((rc = launch_panel<T>(Ak, lda, mk, nb, dtau + k0, w, j, st))) break;
+      kbig += kk;
+      const i64 nin = (o0 + nbo) - (k0 + nb);  // remaining columns INSIDE the outer block
+      const i64 nfar = n - (o0 + nbo);
+      if (nin > 0 || nfar > 0) {
+        if ((rc = build_T<T>(w, w.Vj(j), w.ldv, mk, kk, dtau + k0, w.Tj(j), st))) break;
+      }
+      if (nin > 0) {
+        if ((rc = apply_panel<T>(w, w.Vj(j), w.ldv, w.VTj(j), NBO, w.Tj(j), mk, kk, Ak + (i64)nb * lda, lda, nin, 1, st)))
+          break;
+      }
+      if (!(mk > nb && n - k0 > nb)) {  // reference recursion stops: src/qr.jl:136
+        done = true;
+        // columns beyond this panel (wide case) still get this outer block's reflectors below
+        break;
+      }
     }
-    if (!(mk > nb && nk > nb)) break;
+    if (rc) break;
+    const i64 nfar = n - (o0 + nbo);
+    if (nfar > 0 && kbig > 0) {
+      if ((rc = apply_outer<T>(w, mo, kbig, dA + o0 + (o0 + nbo) * lda, lda, nfar, st))) break;
+    }
+    if (o0 + nbo >= n || o0 + nbo >= m) done = true;
   }
   w.release();
   return rc;
@@ -493,12 +655,7 @@ int ormqr_blocked_dev(const T* dF, i64 mF, i64 nF, i64 ldf, const T* dtau, T* dA
   const i64 k = mF < nF ? mF : nF;
   if (k == 0 || nA == 0) return 0;
   QrWork<T> w;
-  int max_ws = 1;
-  for (i64 k0 = 0; k0 < k; k0 += NB) {
-    const int s = wsplit_for(NB, nA, mF - k0);
-    if (s > max_ws) max_ws = s;
-  }
-  GLA_TRY(w.alloc(mF, nA, max_ws, st));
+  GLA_TRY(w.alloc(mF, nA, st));
   int rc = 0;
   const i64 npan = (k + NB - 1) / NB;
   for (i64 ip = 0; ip < npan; ++ip) {
@@ -506,11 +663,11 @@ int ormqr_blocked_dev(const T* dF, i64 mF, i64 nF, i64 ldf, const T* dtau, T* dA
     const i64 k0 = (adjoint ? ip : npan - 1 - ip) * NB;
     const i64 mk = mF - k0;
     const int kk = (int)((k - k0) < NB ? (k - k0) : NB);
-    extract_v_kernel<T><<<(unsigned)ceil_div(mk * kk, 256) > 2048 ? 2048 : (unsigned)ceil_div(mk * kk, 256), 256, 0, st>>>(
-        dF + k0 + k0 * ldf, ldf, (int)mk, kk, w.Vc, w.ldvc, w.VcT);
+    const unsigned grid = (unsigned)(ceil_div(mk * kk, 256) > 2048 ? 2048 : ceil_div(mk * kk, 256));
+    extract_v_kernel<T><<<grid, 256, 0, st>>>(dF + k0 + k0 * ldf, ldf, (int)mk, kk, w.V, w.ldv, w.VT, NBO);
     if ((rc = check_cuda(cudaGetLastError(), __FILE__, __LINE__))) break;
-    if ((rc = build_T<T>(w, mk, kk, dtau + k0, st))) break;
-    if ((rc = apply_block<T>(w, mk, kk, dA + k0, lda, nA, adjoint, st))) break;
+    if ((rc = build_T<T>(w, w.V, w.ldv, mk, kk, dtau + k0, w.Tm, st))) break;
+    if ((rc = apply_panel<T>(w, w.V, w.ldv, w.VT, NBO, w.Tm, mk, kk, dA + k0, lda, nA, adjoint, st))) break;
   }
   w.release();
   return rc;
