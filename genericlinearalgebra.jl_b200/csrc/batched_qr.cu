@@ -460,6 +460,213 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
   }
 }
 
+// ---------------------------------------------------------------------------------- 32x32, left-looking halves
+// Same lane mapping as the half-warp kernel (half-warp h owns matrix h of the pair) but the matrix is
+// processed LEFT-LOOKING in two column halves, so a lane holds ONE column (32 values) at a time:
+//   phase 1  lane c owns column c:      16 reflector steps on the 32 x 16 left half; the final columns
+//            (R above the diagonal, -nu on it, normalised v below) go back to the staging tile
+//   phase 2  lane c owns column 16+c:   the 16 reflectors are applied from the tile (v_k broadcast with
+//            LDS.128, tau_k by shuffle) -- pure FMA streams, no scalar chain, every lane useful
+//   phase 3  16 reflector steps on the trailing 16 x 16 block of the right half
+// Half the register payload of the half-warp kernel (no spills, 3 CTAs/SM) and the pivot column stays in
+// registers between the dot and the axpy sweep of a step.
+template <class R, int K0>
+__device__ __forceinline__ void ll_factor_half(R (&a)[32], R* __restrict__ my, const int c, R& tau_own, R& ixi_own) {
+  using VT = typename Vec16<R>::type;
+  constexpr int V = Vec16<R>::N;
+  constexpr int LD = HwCfg<R>::LD;
+#pragma unroll
+  for (int kk = 0; kk < 16; ++kk) {
+    const int k = K0 + kk;
+    const bool own = c == kk;
+    if (k == 31) {  // length-1 column: still reflected, x1 <- -x1, tau = 2 exactly (tau = 0 for a zero entry)
+      const bool z = a[31] == R(0);
+      tau_own = own ? (z ? R(0) : R(2)) : tau_own;
+      a[31] = (own && !z) ? -a[31] : a[31];
+      continue;
+    }
+    const int k0 = k & ~(V - 1);
+    // the owner publishes the current (un-normalised) pivot column to its own tile column
+    if (own) {
+#pragma unroll
+      for (int i = k0; i < 32; i += V) *reinterpret_cast<VT*>(my + k * LD + i) = arr_to_vec(a + i);
+    }
+    __syncwarp();
+    const R* vk = my + k * LD;
+    R y[32];
+#pragma unroll
+    for (int i = k0; i < 32; i += V) vec_to_arr<R>(*reinterpret_cast<const VT*>(vk + i), y + i);
+    const R alpha = y[k];
+    R acc[4] = {R(0), R(0), R(0), R(0)};
+#pragma unroll
+    for (int r = k + 1; r < 32; ++r) acc[(r - k) & 3] = fmad(y[r], a[r], acc[(r - k) & 3]);
+    const R d = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    const R dk = __shfl_sync(0xffffffffu, d, kk, 16);  // the owner's dot is the tail norm^2
+    const R n2 = fmad(alpha, alpha, dk);
+    const bool zero = n2 == R(0);  // zero column: tau = 0, nothing changes (guarded selects, the halves may differ)
+    const R n2s = zero ? R(1) : n2;
+    // Goldschmidt: g -> sqrt(n2), hh -> 1/(2 sqrt(n2)); the reciprocal of xi is seeded from the approximate
+    // norm so that its MUFU latency overlaps these iterations
+    const R y0 = Seed<R>::rsqrt0(n2s);
+    R g = n2s * y0, hh = R(0.5) * y0;
+    R r = Seed<R>::rcp0(alpha + copysign(g, alpha));
+#pragma unroll
+    for (int it = 0; it < Seed<R>::ITERS; ++it) {
+      const R e = fmad(-g, hh, R(0.5));
+      g = fmad(g, e, g);
+      hh = fmad(hh, e, hh);
+    }
+    const R nu = copysign(g, alpha);
+    const R inv_nu = copysign(hh + hh, alpha);
+    const R xi = alpha + nu;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const R e = fmad(-xi, r, R(1));
+      r = fmad(r, e, r);
+    }
+    const R tq = xi * inv_nu;  // tau = xi / nu
+    // s = conj(tau) (a_kc + v^H a_c[k+1:]) with v = a_k / xi  ->  tau a_kc + d / nu
+    const R s = fmad(d, inv_nu, tq * a[k]);
+    const bool right = (c > kk) && !zero;
+    const bool mine = own && !zero;
+    const R nt = right ? -(s * r) : R(0);
+    a[k] = mine ? -nu : (right ? a[k] - s : a[k]);
+    tau_own = mine ? tq : tau_own;
+    ixi_own = mine ? r : ixi_own;
+#pragma unroll
+    for (int rr = k + 1; rr < 32; ++rr) a[rr] = fmad(nt, y[rr], a[rr]);
+  }
+  // deferred normalisation of the stored reflector (rows below the diagonal of the own column)
+#pragma unroll
+  for (int i = K0 + 1; i < 32; ++i) a[i] = (i > K0 + c) ? a[i] * ixi_own : a[i];
+}
+
+template <class R, int WARPS, int MINB, int MODE = 0, bool PF = false>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+    batched_qr32_ll_kernel(R* __restrict__ A, R* __restrict__ tau, i64 batch) {
+  using Cfg = HwCfg<R>;
+  using VT = typename Vec16<R>::type;
+  constexpr int V = Cfg::V;
+  constexpr int LD = Cfg::LD;
+  constexpr int NVEC = 2 * 1024 / V / 32;  // 16-byte vectors per lane per matrix PAIR
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int h = lane >> 4, c = lane & 15;
+  R* sm = reinterpret_cast<R*>(smem_raw) + warp * Cfg::PER_WARP;
+  R* my = sm + h * Cfg::TILE;  // tile of this half-warp's matrix
+
+  const i64 npairs = (batch + 1) >> 1;
+  for (i64 pair = (i64)blockIdx.x * WARPS + warp; pair < npairs; pair += (i64)gridDim.x * WARPS) {
+    const i64 mat0 = pair * 2;
+    const bool both = mat0 + 1 < batch;
+    R* Ag = A + mat0 * 1024;
+    if (PF) {  // pull the pair this warp handles next into L2 while this one is being factorised
+      const i64 nxt = pair + (i64)gridDim.x * WARPS;
+      if (nxt * 2 + 1 < batch) {
+        const char* pn = reinterpret_cast<const char*>(A + nxt * 2048);
+#pragma unroll
+        for (int q = 0; q < (int)(2048 * sizeof(R) / 128 / 32); ++q)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pn + (size_t)(lane + 32 * q) * 128));
+      }
+    }
+    // ---- HBM -> staging tiles (two matrices = 2048 contiguous elements), 16-byte coalesced streaming loads
+#pragma unroll
+    for (int part = 0; part < 2; ++part) {
+      VT v[NVEC / 2];
+#pragma unroll
+      for (int q = 0; q < NVEC / 2; ++q) {
+        const int p = lane + 32 * (q + part * (NVEC / 2));
+        const bool ok = both || (p * V < 1024);
+        v[q] = ok ? __ldcs(reinterpret_cast<const VT*>(Ag) + p) : VT{};
+      }
+#pragma unroll
+      for (int q = 0; q < NVEC / 2; ++q) {
+        const int e = (lane + 32 * (q + part * (NVEC / 2))) * V;
+        const int hm = e >> 10, col = (e & 1023) >> 5, row = e & 31;
+        *reinterpret_cast<VT*>(sm + hm * Cfg::TILE + col * LD + row) = v[q];
+      }
+    }
+    __syncwarp();
+    R a[32];
+    R tau_l = R(0), tau_r = R(0), ixi = R(1);
+    // ---- phase 1: left half
+#pragma unroll
+    for (int i = 0; i < 32; i += V) vec_to_arr<R>(*reinterpret_cast<const VT*>(my + c * LD + i), a + i);
+    if (MODE != 1) ll_factor_half<R, 0>(a, my, c, tau_l, ixi);
+#pragma unroll
+    for (int i = 0; i < 32; i += V) *reinterpret_cast<VT*>(my + c * LD + i) = arr_to_vec(a + i);
+    __syncwarp();
+    // ---- phase 2: the 16 reflectors applied to the right half
+#pragma unroll
+    for (int i = 0; i < 32; i += V) vec_to_arr<R>(*reinterpret_cast<const VT*>(my + (c + 16) * LD + i), a + i);
+#pragma unroll
+    for (int k = 0; k < (MODE == 1 ? 0 : 16); ++k) {
+      const R tk = __shfl_sync(0xffffffffu, tau_l, k, 16);
+      const R* vk = my + k * LD;
+      R acc[4] = {a[k], R(0), R(0), R(0)};
+      R y[32];
+#pragma unroll
+      for (int i = (k + 1) & ~(V - 1); i < 32; i += V) vec_to_arr<R>(*reinterpret_cast<const VT*>(vk + i), y + i);
+#pragma unroll
+      for (int r = k + 1; r < 32; ++r) acc[(r - k) & 3] = fmad(y[r], a[r], acc[(r - k) & 3]);
+      const R ns = -(tk * ((acc[0] + acc[1]) + (acc[2] + acc[3])));
+      a[k] += ns;
+#pragma unroll
+      for (int r = k + 1; r < 32; ++r) a[r] = fmad(ns, y[r], a[r]);
+    }
+    // ---- phase 3: trailing 16 x 16 block of the right half
+    ixi = R(1);
+    if (MODE != 1) ll_factor_half<R, 16>(a, my, c, tau_r, ixi);
+#pragma unroll
+    for (int i = 0; i < 32; i += V) *reinterpret_cast<VT*>(my + (c + 16) * LD + i) = arr_to_vec(a + i);
+    __syncwarp();
+    // ---- staging tiles -> HBM (16-byte coalesced, streaming)
+#pragma unroll
+    for (int q = 0; q < NVEC; ++q) {
+      const int p = lane + 32 * q;
+      const int e = p * V;
+      const int hm = e >> 10, col = (e & 1023) >> 5, row = e & 31;
+      if (both || hm == 0) {
+        const VT v = *reinterpret_cast<const VT*>(sm + hm * Cfg::TILE + col * LD + row);
+        __stcs(reinterpret_cast<VT*>(Ag) + p, v);
+      }
+    }
+    if (both || h == 0) {
+      tau[(mat0 + h) * 32 + c] = tau_l;
+      tau[(mat0 + h) * 32 + 16 + c] = tau_r;
+    }
+    __syncwarp();
+  }
+}
+
+template <class R>
+static int launch_ll32(R* dA, R* dtau, i64 batch, cudaStream_t st) {
+  constexpr int WARPS = 4;
+  constexpr int MINB = sizeof(R) == 8 ? 3 : 4;
+  const size_t smem = (size_t)WARPS * HwCfg<R>::PER_WARP * sizeof(R);
+  static const int mode = [] {
+    const char* e = getenv("GLA_BATCHED_MODE");
+    return e ? atoi(e) : 0;
+  }();
+  // mode 1 = copy only (memory path ceiling of this structure, for profiling); default = L2 prefetch of the next pair
+  auto kern = mode == 1 ? batched_qr32_ll_kernel<R, WARPS, MINB, 1, false>
+              : mode == 2 ? batched_qr32_ll_kernel<R, WARPS, MINB, 0, false>
+                          : batched_qr32_ll_kernel<R, WARPS, MINB, 0, true>;
+  GLA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  GLA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem));
+  if (occ < 1) occ = 1;
+  const i64 npairs = (batch + 1) / 2;
+  const i64 need = (npairs + WARPS - 1) / WARPS;
+  const i64 resident = (i64)sm_count() * occ;
+  const i64 grid = need < resident ? need : resident;   // one resident wave; warps stride over the pairs
+  kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(dA, dtau, batch);
+  GLA_CUDA(cudaGetLastError());
+  return 0;
+}
+
 template <class R>
 static int launch_hw32(R* dA, R* dtau, i64 batch, cudaStream_t st) {
   constexpr int WARPS = 4;
@@ -536,7 +743,8 @@ static int launch_reg32(R* dA, R* dtau, i64 batch, cudaStream_t st) {
   }();
   if (variant == 1) return launch_reg32_cfg<R, 4, 168>(dA, dtau, batch, st);
   if (variant == 2) return launch_reg32_cfg<R, 4, 200>(dA, dtau, batch, st);
-  return launch_hw32<R>(dA, dtau, batch, st);
+  if (variant == 3) return launch_hw32<R>(dA, dtau, batch, st);
+  return launch_ll32<R>(dA, dtau, batch, st);
 }
 
 template <class T>
