@@ -35,6 +35,14 @@ int sm_count() {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
     cached[dev] = n;
     have[dev] = true;
+    // keep freed workspace in the stream-ordered pool instead of returning it to the driver at every
+    // synchronisation (the default release threshold of 0 makes each call pay a fresh cudaMalloc)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long thr = ~0ull;
+      (void)cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    (void)cudaGetLastError();
   }
   return cached[dev];
 }

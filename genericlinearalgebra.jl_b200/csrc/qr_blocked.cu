@@ -28,9 +28,100 @@
 namespace gla {
 
 constexpr int NB = 64;             // panel width
+constexpr int SB = 16;             // sub-panel width inside the panel kernel
 constexpr int PANEL_THREADS = 256;
-constexpr int TPC = PANEL_THREADS / NB;  // threads per panel column
+constexpr int TPS = PANEL_THREADS / SB;  // threads per sub-panel column (one half-warp)
 constexpr int PANEL_MAX_CTAS = 64;
+constexpr int PANEL_PMAX = 160;          // upper bound on CTAs of one panel launch (exchange buffer sizing)
+constexpr int GW_MAX = SB * NB;          // entries of one sub-panel's [G | W] block
+
+// ---- flag-in-data exchange between the CTAs of a panel launch ("LL" protocol): every exchanged real number
+// travels as one aligned 16-byte {payload, tag} store, readers spin on the same 16 bytes until the tag of the
+// step they wait for shows up.  One L2 round trip per exchange, no separate barrier, no fences; the tag is
+// unique per (launch epoch, step), buffers are reused at distance >= 2 steps (see the WAR argument in DESIGN.md).
+__device__ __forceinline__ void ll_store(ulonglong2* p, unsigned long long bits, unsigned long long tag) {
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(bits), "l"(tag) : "memory");
+}
+__device__ __forceinline__ unsigned long long ll_load(const ulonglong2* p, unsigned long long tag) {
+  unsigned long long v, t;
+  do {
+    asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(v), "=l"(t) : "l"(p) : "memory");
+  } while (t != tag);
+  return v;
+}
+__device__ __forceinline__ unsigned long long to_bits(double v) { return (unsigned long long)__double_as_longlong(v); }
+__device__ __forceinline__ unsigned long long to_bits(float v) { return (unsigned long long)__float_as_uint(v); }
+template <class R>
+__device__ __forceinline__ R from_bits(unsigned long long b);
+template <>
+__device__ __forceinline__ double from_bits<double>(unsigned long long b) { return __longlong_as_double((long long)b); }
+template <>
+__device__ __forceinline__ float from_bits<float>(unsigned long long b) { return __uint_as_float((unsigned)b); }
+
+template <class T>
+struct LLX {  // one T = NR tagged entries
+  static constexpr int NR = Sc<T>::is_complex ? 2 : 1;
+  using R = typename Sc<T>::real;
+  static __device__ __forceinline__ void put(ulonglong2* base, i64 idx, T v, unsigned long long tag) {
+    if constexpr (Sc<T>::is_complex) {
+      ll_store(base + 2 * idx, to_bits(v.x), tag);
+      ll_store(base + 2 * idx + 1, to_bits(v.y), tag);
+    } else {
+      ll_store(base + idx, to_bits(v), tag);
+    }
+  }
+  // sum over pp = q, q+STEP, q+2*STEP, ... < P (ascending) of the T stored at base + pp*stride*NR
+  template <int STEP>
+  static __device__ __forceinline__ T gather(const ulonglong2* base, int q, int P, i64 stride, unsigned long long tag) {
+    constexpr int MAXE = (PANEL_PMAX + STEP - 1) / STEP;  // entries per lane
+    T sum = Sc<T>::zero();
+    for (int b = 0; b < MAXE; b += 4) {   // batches of 4 T (4 or 8 loads in flight)
+      if (q + b * STEP >= P) break;
+      unsigned long long v[4 * NR], t[4 * NR];
+      bool ok;
+      do {
+        ok = true;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int pp = q + (b + u) * STEP;
+          if (pp < P) {
+#pragma unroll
+            for (int c = 0; c < NR; ++c) {
+              const ulonglong2* ptr = base + (i64)pp * stride * NR + c;
+              asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(v[u * NR + c]), "=l"(t[u * NR + c]) : "l"(ptr) : "memory");
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int pp = q + (b + u) * STEP;
+          if (pp < P) {
+#pragma unroll
+            for (int c = 0; c < NR; ++c) ok = ok && (t[u * NR + c] == tag);
+          }
+        }
+      } while (!ok);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int pp = q + (b + u) * STEP;
+        if (pp < P) {
+          if constexpr (Sc<T>::is_complex) sum = sum + make_zd(from_bits<double>(v[u * 2]), from_bits<double>(v[u * 2 + 1]));
+          else sum = sum + from_bits<R>(v[u]);
+        }
+      }
+    }
+    return sum;
+  }
+  static __device__ __forceinline__ T get(const ulonglong2* base, i64 idx, unsigned long long tag) {
+    if constexpr (Sc<T>::is_complex) {
+      const double x = from_bits<double>(ll_load(base + 2 * idx, tag));
+      const double y = from_bits<double>(ll_load(base + 2 * idx + 1, tag));
+      return make_zd(x, y);
+    } else {
+      return from_bits<R>(ll_load(base + idx, tag));
+    }
+  }
+};
 
 template <class T>
 struct PanelArgs {
@@ -42,55 +133,69 @@ struct PanelArgs {
   i64 ldvc;
   T* VcT;      // kk x mk (ld = ldvct)
   i64 ldvct;
-  T* partial;  // [2][P][NB]
-  T* rowj;     // [2][NB]
-  unsigned* counter;
+  ulonglong2* xd;  // [2][PANEL_PMAX][SB] T   per-column partial dots
+  ulonglong2* xr;  // [2][SB] T               pivot-row entries
+  ulonglong2* xw;  // [PANEL_PMAX][GW_MAX] T  partial [G | W] of a sub-panel
+  ulonglong2* xz;  // [2][GW_MAX] T           reduced [G | W]
+  unsigned long long epoch;
   int rows_per;  // rows per CTA
   int resident;  // slab lives in shared memory
   int lds;       // slab leading dimension when resident
 };
 
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+// half-warp (16 lanes) butterfly sum; the mask names only the caller's half, so the two halves of a warp may
+// run different trip counts around it
+__device__ __forceinline__ float hw_shfl(float v, int o, unsigned m) { return __shfl_xor_sync(m, v, o); }
+__device__ __forceinline__ double hw_shfl(double v, int o, unsigned m) { return __shfl_xor_sync(m, v, o); }
+__device__ __forceinline__ zd hw_shfl(zd v, int o, unsigned m) {
+  return make_zd(__shfl_xor_sync(m, v.x, o), __shfl_xor_sync(m, v.y, o));
+}
+__device__ __forceinline__ float hw_shfl_idx(float v, int src, unsigned m) { return __shfl_sync(m, v, src, TPS); }
+__device__ __forceinline__ double hw_shfl_idx(double v, int src, unsigned m) { return __shfl_sync(m, v, src, TPS); }
+__device__ __forceinline__ zd hw_shfl_idx(zd v, int src, unsigned m) {
+  return make_zd(__shfl_sync(m, v.x, src, TPS), __shfl_sync(m, v.y, src, TPS));
+}
+// broadcast from lane `src` of the caller's half-warp
+template <class T>
+__device__ __forceinline__ T hw_bcast(T v, int src) {
+  return hw_shfl_idx(v, src, 0xffffu << (threadIdx.x & 16));
+}
+template <class T>
+__device__ __forceinline__ T hw_sum(T v) {
+  const unsigned m = 0xffffu << (threadIdx.x & 16);
+#pragma unroll
+  for (int o = 1; o < TPS; o <<= 1) v = v + hw_shfl(v, o, m);
   return v;
 }
 
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target, int nctas) {
-  __syncthreads();
-  if (nctas > 1 && threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(counter, 1u);
-    while (ld_acquire_u32(counter) < target) {
-    }
-    __threadfence();
-  }
-  __syncthreads();
-}
-
-template <class T>
-__device__ __forceinline__ T ldcg(const T* p) {
-  return __ldcg(p);
-}
-template <>
-__device__ __forceinline__ zd ldcg<zd>(const zd* p) {
-  double2 v = __ldcg(reinterpret_cast<const double2*>(p));
-  return make_zd(v.x, v.y);
-}
-
+// K1: panel factorisation.  P CTAs, CTA p owns the row slab [p*rows_per, ...) of the panel (in shared memory).
+// The NB columns are processed in sub-panels of SB columns:
+//   column step j (right-looking INSIDE the sub-panel only): local partial dots of the un-normalised pivot
+//     column with the remaining sub-panel columns -> LL exchange (every CTA sums the partials in the same fixed
+//     order, so all CTAs hold bitwise identical scalars) -> nu, tau, 1/xi -> rank-1 update of the sub-panel;
+//   block step (once per sub-panel): [G | W] = Vs^H [Vs | A_rest] partials -> reduce-scatter + all-gather over
+//     the LL buffers -> T_s = (I + diag(tau) striu(G))^-1 diag(tau) -> A_rest -= Vs (T_s^H W).
+// Afterwards the panel is written back together with the clean reflector block Vc (unit diagonal, zeros
+// above) and its transpose VcT, the K-contiguous operands of the trailing contractions.
 template <class T>
 __global__ void __launch_bounds__(PANEL_THREADS, 1) qr_panel_kernel(PanelArgs<T> a) {
   using R = typename Sc<T>::real;
+  using X = LLX<T>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ T sh_d[NB];
-  __shared__ T sh_row[NB];
+  __shared__ T sh_d[SB];
+  __shared__ T sh_row[SB];
+  __shared__ T sh_tau[SB];
+  __shared__ T sh_gw[GW_MAX];            // reduced [G | W], entry (l, x) at x*SB + l
+  __shared__ T sh_z[SB * (NB - SB)];     // Z = T_s^H W, entry (l, x) at x*SB + l
+  __shared__ T sh_t[SB][SB + 1];         // T_s
   const int P = gridDim.x, p = blockIdx.x;
   const int r0 = p * a.rows_per;
   const int r1 = (r0 + a.rows_per < a.mk) ? r0 + a.rows_per : a.mk;
   const int rows = r1 > r0 ? r1 - r0 : 0;
   const int tid = threadIdx.x;
-  const int c = tid / TPC, q = tid % TPC;  // column, row phase
+  const int cl = tid / TPS, q = tid % TPS;  // sub-panel column, row phase
   const int kk = a.mk < a.nb ? a.mk : a.nb;
+  const unsigned long long tagbase = a.epoch << 12;
 
   // slab S(i_local, col)
   T* S;
@@ -109,74 +214,185 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) qr_panel_kernel(PanelArgs<T>
   T prev_ixi = Sc<T>::one();
   R prev_nu = R(0);
   bool prev_nonzero = false;
-  unsigned bar_target = 0;
-
-  for (int j = 0; j <= kk; ++j) {
-    // ---- deferred finish of pivot column j-1: rows below the diagonal *= 1/xi, diagonal <- -nu
-    if (j > 0 && prev_nonzero) {
-      T* col = S + (i64)(j - 1) * ld;
-      int lo = j - r0;  // first local row with global index >= j
-      if (lo < 0) lo = 0;
-      for (int i = lo + tid; i < rows; i += PANEL_THREADS) col[i] = col[i] * prev_ixi;
-      if (tid == 0 && j - 1 >= r0 && j - 1 < r1) col[j - 1 - r0] = Sc<T>::from_real(-prev_nu);
-    }
-    if (j == kk) break;
-    const int buf = j & 1;
-    const T* piv = S + (i64)j * ld;
-    int lo = j + 1 - r0;  // first local row strictly below the diagonal
+  // deferred finish of a factored pivot column: rows below the diagonal *= 1/xi, diagonal <- -nu
+  auto finish = [&](int jc) {
+    if (!prev_nonzero) return;
+    T* col = S + (i64)jc * ld;
+    int lo = jc + 1 - r0;
     if (lo < 0) lo = 0;
-    const bool active = c >= j && c < a.nb;
-    // ---- partial dots with the un-normalised pivot column
-    T d = Sc<T>::zero();
-    if (active) {
-      const T* cc = S + (i64)c * ld;
-      T d1 = Sc<T>::zero();
-      int i = lo + q;
-      for (; i + TPC < rows; i += 2 * TPC) {
-        d = fmad(cj(piv[i]), cc[i], d);
-        d1 = fmad(cj(piv[i + TPC]), cc[i + TPC], d1);
-      }
-      if (i < rows) d = fmad(cj(piv[i]), cc[i], d);
-      d = d + d1;
-    }
-#pragma unroll
-    for (int o = 1; o < TPC; o <<= 1) d = d + shfl_xor_t<T>(d, o);
-    if (P > 1) {
-      if (active && q == 0) a.partial[((i64)buf * P + p) * NB + c] = d;
-      if (active && q == 1 && j >= r0 && j < r1) a.rowj[buf * NB + c] = S[(j - r0) + (i64)c * ld];
-      bar_target += P;
-      grid_barrier(a.counter, bar_target, P);
-      // ---- fixed-order reduction of the partials (identical in every CTA)
-      T sum = Sc<T>::zero();
+    for (int i = lo + tid; i < rows; i += PANEL_THREADS) col[i] = col[i] * prev_ixi;
+    if (tid == 0 && jc >= r0 && jc < r1) col[jc - r0] = Sc<T>::from_real(-prev_nu);
+  };
+
+  const int nsub = (kk + SB - 1) / SB;
+  for (int sp = 0; sp < nsub; ++sp) {
+    const int sb0 = sp * SB;
+    const int sbe = sb0 + SB < kk ? sb0 + SB : kk;
+    const int c = sb0 + cl;
+    for (int j = sb0; j < sbe; ++j) {
+      if (j > sb0) finish(j - 1);
+      const int jl = j - sb0;
+      const int par = j & 1;
+      const unsigned long long tag = tagbase + 1 + j;
+      const T* piv = S + (i64)j * ld;
+      int lo = j + 1 - r0;  // first local row strictly below the diagonal
+      if (lo < 0) lo = 0;
+      const bool active = cl >= jl && c < sbe;
+      // ---- partial dots with the un-normalised pivot column
+      T d = Sc<T>::zero();
       if (active) {
-        for (int pp = q; pp < P; pp += TPC) sum = sum + ldcg<T>(a.partial + ((i64)buf * P + pp) * NB + c);
+        const T* cc = S + (i64)c * ld;
+        T d1 = Sc<T>::zero();
+        int i = lo + q;
+        for (; i + TPS < rows; i += 2 * TPS) {
+          d = fmad(cj(piv[i]), cc[i], d);
+          d1 = fmad(cj(piv[i + TPS]), cc[i + TPS], d1);
+        }
+        if (i < rows) d = fmad(cj(piv[i]), cc[i], d);
+        d = d + d1;
       }
+      d = hw_sum<T>(d);
+      if (P > 1) {
+        if (active && q == 0) X::put(a.xd, ((i64)par * PANEL_PMAX + p) * SB + cl, d, tag);
+        if (active && q == 1 && j >= r0 && j < r1) X::put(a.xr, par * SB + cl, S[(j - r0) + (i64)c * ld], tag);
+        // fixed-order reduction of the partials (identical in every CTA); lane TPS-1 of the column fetches the
+        // pivot-row entry meanwhile, so both exchanges cost one round trip together
+        T sum = Sc<T>::zero();
+        if (active) sum = X::template gather<TPS>(a.xd + ((i64)par * PANEL_PMAX * SB + cl) * X::NR, q, P, (i64)SB, tag);
+        T rowv = Sc<T>::zero();
+        if (active && q == TPS - 1) rowv = X::get(a.xr, par * SB + cl, tag);
+        sum = hw_sum<T>(sum);
+        rowv = hw_bcast<T>(rowv, TPS - 1);
+        if (active && q == 0) {
+          sh_d[cl] = sum;
+          sh_row[cl] = rowv;
+        }
+      } else if (active && q == 0) {
+        sh_d[cl] = d;
+        sh_row[cl] = S[j + (i64)c * ld];
+      }
+      __syncthreads();
+      const T alpha = sh_row[jl];
+      const R n2 = abs2(alpha) + re(sh_d[jl]);
+      const ReflScalars<T> rs = reflector_scalars<T>(alpha, n2);
+      prev_nonzero = rs.nonzero;
+      prev_ixi = rs.ixi;
+      prev_nu = rs.nu;
+      if (tid == 0) {
+        sh_tau[jl] = rs.tau;
+        if (p == 0) a.tau[j] = rs.tau;
+      }
+      if (rs.nonzero && active && cl > jl) {
+        const T s = cj(rs.tau) * (sh_row[cl] + cj(rs.ixi) * sh_d[cl]);
+        const T t = s * rs.ixi;
+        T* cc = S + (i64)c * ld;
+        for (int i = lo + q; i < rows; i += TPS) cc[i] = cc[i] - piv[i] * t;
+        if (q == 0 && j >= r0 && j < r1) cc[j - r0] = cc[j - r0] - s;
+      }
+      __syncthreads();
+    }
+    finish(sbe - 1);
+    prev_nonzero = false;
+    __syncthreads();
+
+    // ---- block step: apply the sub-panel's reflectors to the remaining panel columns [sbe, nb)
+    const int ws = sbe - sb0;
+    const int nrest = a.nb - sbe;
+    if (nrest <= 0) continue;
+    const int nx = ws + nrest;  // columns of [G | W]
+    // Vs(i_local, l): unit lower trapezoid of the sub-panel
+    auto vs = [&](int i, int l) -> T {
+      const int gi = r0 + i, col = sb0 + l;
+      return gi > col ? S[i + (i64)col * ld] : (gi == col ? Sc<T>::one() : Sc<T>::zero());
+    };
+    // local partials: thread -> column x = tid / 4, reflectors l = 4*(tid%4) .. +3
+    {
+      const int lg = (tid & 3) * 4;
+      for (int x = tid >> 2; x < nx; x += PANEL_THREADS / 4) {
+        T acc[4] = {Sc<T>::zero(), Sc<T>::zero(), Sc<T>::zero(), Sc<T>::zero()};
+        if (x < ws) {
+          for (int i = 0; i < rows; ++i) {
+            const T b = vs(i, x);
 #pragma unroll
-      for (int o = 1; o < TPC; o <<= 1) sum = sum + shfl_xor_t<T>(sum, o);
-      if (active && q == 0) {
-        sh_d[c] = sum;
-        sh_row[c] = ldcg<T>(a.rowj + buf * NB + c);
+            for (int u = 0; u < 4; ++u) acc[u] = fmad(cj(vs(i, lg + u)), b, acc[u]);
+          }
+        } else {
+          const T* bc = S + (i64)(sbe + x - ws) * ld;
+          for (int i = 0; i < rows; ++i) {
+            const T b = bc[i];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[u] = fmad(cj(vs(i, lg + u)), b, acc[u]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (lg + u < ws) {
+            if (P > 1) X::put(a.xw, (i64)p * GW_MAX + x * SB + lg + u, acc[u], tagbase + 200 + sp);
+            else sh_gw[x * SB + lg + u] = acc[u];
+          }
+        }
       }
-    } else {
-      if (active && q == 0) {
-        sh_d[c] = d;
-        sh_row[c] = S[j + (i64)c * ld];
+    }
+    if (P > 1) {
+      // reduce-scatter: CTA p sums entries e = p, p+P, ... over all CTAs (fixed order), publishes them
+      const int zpar = sp & 1;
+      for (int e0 = p + cl * P; e0 < nx * SB; e0 += SB * P) {   // entry handled by this half-warp
+        const int l = e0 % SB;
+        T sum = Sc<T>::zero();
+        if (l < ws) sum = X::template gather<TPS>(a.xw + (i64)e0 * X::NR, q, P, (i64)GW_MAX, tagbase + 200 + sp);
+        sum = hw_sum<T>(sum);
+        if (q == 0) X::put(a.xz, (i64)zpar * GW_MAX + e0, sum, tagbase + 300 + sp);
       }
+      // all-gather
+      for (int e = tid; e < nx * SB; e += PANEL_THREADS) sh_gw[e] = X::get(a.xz, (i64)zpar * GW_MAX + e, tagbase + 300 + sp);
     }
     __syncthreads();
-    const T alpha = sh_row[j];
-    const R n2 = abs2(alpha) + re(sh_d[j]);
-    const ReflScalars<T> rs = reflector_scalars<T>(alpha, n2);
-    prev_nonzero = rs.nonzero;
-    prev_ixi = rs.ixi;
-    prev_nu = rs.nu;
-    if (p == 0 && tid == 0) a.tau[j] = rs.tau;
-    if (rs.nonzero && active && c > j) {
-      const T s = cj(rs.tau) * (sh_row[c] + cj(rs.ixi) * sh_d[c]);
-      const T t = s * rs.ixi;
-      T* cc = S + (i64)c * ld;
-      for (int i = lo + q; i < rows; i += TPC) cc[i] = cc[i] - piv[i] * t;
-      if (q == 0 && j >= r0 && j < r1) cc[j - r0] = cc[j - r0] - s;
+    // T_s = (I + diag(tau) striu(G))^-1 diag(tau), one half-warp, row i per lane
+    if (tid < SB) {
+      const int i = tid;
+      T xrow[SB];
+#pragma unroll
+      for (int l = 0; l < SB; ++l) xrow[l] = (l == i) ? Sc<T>::one() : Sc<T>::zero();
+#pragma unroll
+      for (int jj = 1; jj < SB; ++jj) {
+        T acc = Sc<T>::zero();
+#pragma unroll
+        for (int l = 0; l < SB; ++l)
+          if (l < jj && l >= i && jj < ws) acc = fmad(xrow[l], sh_tau[l] * sh_gw[jj * SB + l], acc);
+        if (i < jj && jj < ws) xrow[jj] = -acc;
+      }
+#pragma unroll
+      for (int l = 0; l < SB; ++l) sh_t[i][l] = (i <= l && l < ws && i < ws) ? xrow[l] * sh_tau[l] : Sc<T>::zero();
+    }
+    __syncthreads();
+    // Z = T_s^H W
+    for (int e = tid; e < nrest * SB; e += PANEL_THREADS) {
+      const int x = e / SB, l = e % SB;
+      T acc = Sc<T>::zero();
+      if (l < ws)
+        for (int l2 = 0; l2 <= l; ++l2) acc = fmad(cj(sh_t[l2][l]), sh_gw[(ws + x) * SB + l2], acc);
+      sh_z[x * SB + l] = acc;
+    }
+    __syncthreads();
+    // A_rest -= Vs Z on the local rows
+    {
+      int xs_n = PANEL_THREADS / (rows > 0 ? rows : 1);
+      if (xs_n < 1) xs_n = 1;
+      if (xs_n > nrest) xs_n = nrest;
+      for (int w = tid; w < rows * xs_n; w += PANEL_THREADS) {
+        const int i = w % rows, xs = w / rows;
+        const int xb = (int)((i64)nrest * xs / xs_n), xe = (int)((i64)nrest * (xs + 1) / xs_n);
+        T v[SB];
+#pragma unroll
+        for (int l = 0; l < SB; ++l) v[l] = l < ws ? vs(i, l) : Sc<T>::zero();
+        for (int x = xb; x < xe; ++x) {
+          T* pa = S + i + (i64)(sbe + x) * ld;
+          T acc = *pa;
+#pragma unroll
+          for (int l = 0; l < SB; ++l) acc = acc - v[l] * sh_z[x * SB + l];
+          *pa = acc;
+        }
+      }
     }
     __syncthreads();
   }
@@ -373,66 +589,98 @@ __global__ void __launch_bounds__(256)
 // ------------------------------------------------------------------------------- workspace
 constexpr int NBO = 256;  // outer block: K of the far trailing contractions
 
+// Workspace of one factorisation.  The outer-block state (V, VT, per-panel T, Gram) is DOUBLE BUFFERED by outer
+// block parity and every scratch array exists once per execution path, because the driver overlaps two paths:
+//   path 0 (panel chain, high-priority stream): panels, per-panel T, updates inside the outer block
+//   path 1 (far update, caller's stream):       Gram of the outer block, W = V^H A2, fix-up, A2 -= V Z
 template <class T>
 struct QrWork {
-  T* V = nullptr;     // m x NBO clean reflectors of the current outer block (unit diagonal, zeros above)
+  T* V[2] = {nullptr, nullptr};    // m x NBO clean reflectors of an outer block (unit diagonal, zeros above)
   i64 ldv = 0;
-  T* VT = nullptr;    // NBO x m transpose (ld NBO)
-  T* Tm = nullptr;    // NBO/NB per-panel T factors, NB x NB each
-  T* G = nullptr;     // NBO x NBO Gram V^H V (ld NBO)
-  T* Gp = nullptr;    // split-K partials of a Gram
-  T* Wp = nullptr;    // split-K partials of W = V^H A2
-  T* Z = nullptr;     // NBO x nA
-  T* partial = nullptr;
-  T* rowj = nullptr;
-  unsigned* counter = nullptr;
+  T* VT[2] = {nullptr, nullptr};   // NBO x m transpose (ld NBO)
+  T* Tm[2] = {nullptr, nullptr};   // NBO/NB per-panel T factors, NB x NB each
+  T* G[2] = {nullptr, nullptr};    // NBO x NBO Gram V^H V (ld NBO)
+  T* Gs = nullptr;                 // NB x NB Gram scratch of build_T (path 0)
+  T* Gp[2] = {nullptr, nullptr};   // split-K partials of a Gram, per path
+  T* Wp[2] = {nullptr, nullptr};   // split-K partials of W = V^H A2, per path
+  T* Z[2] = {nullptr, nullptr};    // NBO x nA, per path
+  i64 wp_elems[2] = {0, 0};
+  ulonglong2* xd = nullptr;        // LL exchange buffers of the panel kernel
+  ulonglong2* xr = nullptr;
+  ulonglong2* xw = nullptr;
+  ulonglong2* xz = nullptr;
+  unsigned long long epoch = 0;
   void* block = nullptr;
   cudaStream_t st = nullptr;
-  i64 wp_elems = 0;
+  int cur = 0;                     // outer buffer the panel chain is filling
   static constexpr int GP_SPLITS = 32;
 
-  int alloc(i64 m, i64 nA_max, cudaStream_t stream) {
+  // nA0 / nA1: widest trailing block handled on path 0 / path 1 (0 = path unused); nbuf outer buffers
+  int alloc(i64 m, i64 nA0, i64 nA1, int nbuf, cudaStream_t stream) {
     st = stream;
     ldv = round_up(m, 2);
-    if (nA_max < 1) nA_max = 1;
     auto al = [](i64 bytes) { return round_up(bytes, 256); };
     const i64 s_v = al(ldv * NBO * sizeof(T));
     const i64 s_vt = al((i64)NBO * m * sizeof(T));
     const i64 s_tm = al((i64)NBO * NB * sizeof(T));
     const i64 s_g = al((i64)NBO * NBO * sizeof(T));
+    const i64 s_gs = al((i64)NB * NB * sizeof(T));
     const i64 s_gp = al((i64)GP_SPLITS * NBO * NBO * sizeof(T));
-    // W partials: at most ~2*SMs tiles worth of split-K slices; sized as 6 full W matrices, never less than
-    // what a 64-slice split of a narrow (<= 4*NBO columns) W needs
-    i64 wcols = 6 * nA_max;
-    if (wcols < 64 * 4 * NBO && nA_max <= 4 * NBO) wcols = 64 * nA_max;
-    wp_elems = (i64)NBO * wcols;
-    const i64 s_wp = al(wp_elems * sizeof(T));
-    const i64 s_z = al((i64)NBO * nA_max * sizeof(T));
-    const i64 s_part = al((i64)2 * 256 * NB * sizeof(T));
-    const i64 s_rowj = al((i64)2 * NB * sizeof(T));
-    const i64 total = s_v + s_vt + s_tm + s_g + s_gp + s_wp + s_z + s_part + s_rowj + 256;
+    i64 s_wp[2], s_z[2];
+    const i64 nAs[2] = {nA0, nA1};
+    for (int q = 0; q < 2; ++q) {
+      i64 nA = nAs[q] < 1 ? 1 : nAs[q];
+      // W partials: at most ~2*SMs tiles worth of split-K slices; 6 full W matrices, never less than what a
+      // 64-slice split of a narrow (<= 4*NBO columns) W needs
+      i64 wcols = 6 * nA;
+      if (wcols < 64 * 4 * NBO && nA <= 4 * NBO) wcols = 64 * nA;
+      wp_elems[q] = nAs[q] > 0 ? (i64)NBO * wcols : 0;
+      s_wp[q] = al((wp_elems[q] > 0 ? wp_elems[q] : 1) * sizeof(T));
+      s_z[q] = al((i64)NBO * nA * sizeof(T));
+    }
+    constexpr i64 NR = Sc<T>::is_complex ? 2 : 1;
+    const i64 s_xd = al((i64)2 * PANEL_PMAX * SB * NR * 16);
+    const i64 s_xr = al((i64)2 * SB * NR * 16);
+    const i64 s_xw = al((i64)PANEL_PMAX * GW_MAX * NR * 16);
+    const i64 s_xz = al((i64)2 * GW_MAX * NR * 16);
+    const i64 total = nbuf * (s_v + s_vt + s_tm + s_g) + s_gs + 2 * s_gp + s_wp[0] + s_wp[1] + s_z[0] + s_z[1] +
+                      s_xd + s_xr + s_xw + s_xz + 256;
     GLA_CUDA(cudaMallocAsync(&block, total, st));
     char* p = static_cast<char*>(block);
-    V = reinterpret_cast<T*>(p); p += s_v;
-    VT = reinterpret_cast<T*>(p); p += s_vt;
-    Tm = reinterpret_cast<T*>(p); p += s_tm;
-    G = reinterpret_cast<T*>(p); p += s_g;
-    Gp = reinterpret_cast<T*>(p); p += s_gp;
-    Wp = reinterpret_cast<T*>(p); p += s_wp;
-    Z = reinterpret_cast<T*>(p); p += s_z;
-    partial = reinterpret_cast<T*>(p); p += s_part;
-    rowj = reinterpret_cast<T*>(p); p += s_rowj;
-    counter = reinterpret_cast<unsigned*>(p);
+    for (int b = 0; b < 2; ++b) {
+      const int src = b < nbuf ? b : 0;
+      if (b < nbuf) {
+        V[b] = reinterpret_cast<T*>(p); p += s_v;
+        VT[b] = reinterpret_cast<T*>(p); p += s_vt;
+        Tm[b] = reinterpret_cast<T*>(p); p += s_tm;
+        G[b] = reinterpret_cast<T*>(p); p += s_g;
+      } else {
+        V[b] = V[src]; VT[b] = VT[src]; Tm[b] = Tm[src]; G[b] = G[src];
+      }
+    }
+    Gs = reinterpret_cast<T*>(p); p += s_gs;
+    for (int q = 0; q < 2; ++q) {
+      Gp[q] = reinterpret_cast<T*>(p); p += s_gp;
+      Wp[q] = reinterpret_cast<T*>(p); p += s_wp[q];
+      Z[q] = reinterpret_cast<T*>(p); p += s_z[q];
+    }
+    xd = reinterpret_cast<ulonglong2*>(p); p += s_xd;
+    xr = reinterpret_cast<ulonglong2*>(p); p += s_xr;
+    xw = reinterpret_cast<ulonglong2*>(p); p += s_xw;
+    xz = reinterpret_cast<ulonglong2*>(p); p += s_xz;
+    // tags of a fresh workspace: zero never matches (epochs start at 1)
+    GLA_CUDA(cudaMemsetAsync(xd, 0, s_xd + s_xr + s_xw + s_xz, st));
+    epoch = 0;
     return 0;
   }
   void release() {
     if (block) cudaFreeAsync(block, st);
     block = nullptr;
   }
-  // views of inner panel j (columns j0 = j*NB of the outer block, rows from j0)
-  T* Vj(int j) const { return V + (i64)j * NB + (i64)j * NB * ldv; }
-  T* VTj(int j) const { return VT + (i64)j * NB * NBO + (i64)j * NB; }
-  T* Tj(int j) const { return Tm + (i64)j * NB * NB; }
+  // views of inner panel j (columns j0 = j*NB of the outer block, rows from j0) in the chain's buffer
+  T* Vj(int j) const { return V[cur] + (i64)j * NB + (i64)j * NB * ldv; }
+  T* VTj(int j) const { return VT[cur] + (i64)j * NB * NBO + (i64)j * NB; }
+  T* Tj(int j) const { return Tm[cur] + (i64)j * NB * NB; }
 };
 
 // rows above panel j's diagonal block inside the outer block are zero in V / VT
@@ -458,10 +706,12 @@ static int launch_panel(T* A, i64 lda, i64 mk, int nb, T* tau, QrWork<T>& w, int
   a.ldvc = w.ldv;
   a.VcT = w.VTj(j);
   a.ldvct = NBO;
-  a.partial = w.partial;
-  a.rowj = w.rowj;
-  a.counter = w.counter;
-  const i64 smem_cap = 200 * 1024;
+  a.xd = w.xd;
+  a.xr = w.xr;
+  a.xw = w.xw;
+  a.xz = w.xz;
+  a.epoch = ++w.epoch;
+  const i64 smem_cap = 176 * 1024;
   const i64 max_rows = (smem_cap / ((i64)nb * sizeof(T)) - 4) / 16 * 16;  // rows that fit one CTA
   const int sms = sm_count();
   i64 rows_per = round_up((mk + PANEL_MAX_CTAS - 1) / PANEL_MAX_CTAS, 16);
@@ -481,7 +731,6 @@ static int launch_panel(T* A, i64 lda, i64 mk, int nb, T* tau, QrWork<T>& w, int
   size_t smem = resident ? (size_t)a.lds * nb * sizeof(T) : 0;
   auto kern = qr_panel_kernel<T>;
   GLA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_cap + 8 * 1024)));
-  GLA_CUDA(cudaMemsetAsync(w.counter, 0, sizeof(unsigned), st));
   void* args[] = {&a};
   if (P > 1) {
     GLA_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(P), dim3(PANEL_THREADS), args, smem, st));
@@ -491,7 +740,7 @@ static int launch_panel(T* A, i64 lda, i64 mk, int nb, T* tau, QrWork<T>& w, int
   }
   if (j > 0) {
     const int kk = (int)(mk < nb ? mk : nb);
-    zero_top_kernel<T><<<ceil_div((i64)j * NB * kk, 256), 256, 0, st>>>(w.V, w.ldv, w.VT, j * NB, kk);
+    zero_top_kernel<T><<<ceil_div((i64)j * NB * kk, 256), 256, 0, st>>>(w.V[w.cur], w.ldv, w.VT[w.cur], j * NB, kk);
     GLA_CUDA(cudaGetLastError());
   }
   return 0;
@@ -499,34 +748,34 @@ static int launch_panel(T* A, i64 lda, i64 mk, int nb, T* tau, QrWork<T>& w, int
 
 // Gram of a clean reflector block: out (kk x kk, ldo) = Vc^H Vc, split-K partials summed in fixed order
 template <class T>
-static int gram(QrWork<T>& w, const T* Vc, i64 ldvc, i64 mk, int kk, T* out, i64 ldo, cudaStream_t st) {
+static int gram(QrWork<T>& w, int path, const T* Vc, i64 ldvc, i64 mk, int kk, T* out, i64 ldo, cudaStream_t st) {
   GemmTN<T> g;
   g.At = Vc; g.ldat = ldvc;
   g.B = Vc; g.ldb = ldvc;
-  g.C = w.Gp; g.ldc = kk;
+  g.C = w.Gp[path]; g.ldc = kk;
   g.M = kk; g.N = kk; g.K = mk;
   g.conj_a = 1;
   g.nsplit = choose_nsplit(kk, kk, mk, kk <= 64 ? 64 : 128, kk <= 64 ? 128 : 64);
   if (g.nsplit > QrWork<T>::GP_SPLITS) g.nsplit = QrWork<T>::GP_SPLITS;
   g.split_stride = (i64)kk * kk + (((i64)kk * kk) & 1);
   GLA_TRY(gemm_tn<T>(g, st));
-  return sum_splits<T>(out, ldo, w.Gp, kk, g.split_stride, g.nsplit, kk, kk, st);
+  return sum_splits<T>(out, ldo, w.Gp[path], kk, g.split_stride, g.nsplit, kk, kk, st);
 }
 
-// T_j (kk x kk, ld NB) of the clean reflector block (Vc, ldvc) with tau; uses w.G as scratch for the Gram
+// T_j (kk x kk, ld NB) of the clean reflector block (Vc, ldvc) with tau (path 0 scratch)
 template <class T>
 static int build_T(QrWork<T>& w, const T* Vc, i64 ldvc, i64 mk, int kk, const T* tau, T* Tout, cudaStream_t st) {
-  GLA_TRY(gram<T>(w, Vc, ldvc, mk, kk, w.G, kk, st));
+  GLA_TRY(gram<T>(w, 0, Vc, ldvc, mk, kk, w.Gs, kk, st));
   const int smem = (2 * NB * (NB + 1) + NB) * (int)sizeof(T);
   GLA_CUDA(cudaFuncSetAttribute(larft_finish_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  larft_finish_kernel<T><<<1, 256, smem, st>>>(w.G, 0, 1, kk, tau, Tout, NB);
+  larft_finish_kernel<T><<<1, 256, smem, st>>>(w.Gs, 0, 1, kk, tau, Tout, NB);
   GLA_CUDA(cudaGetLastError());
   return 0;
 }
 
 static int wsplit_for(i64 kk, i64 nA, i64 mk) { return choose_nsplit(kk, nA, mk, kk <= 64 ? 64 : 128, kk <= 64 ? 128 : 64); }
 
-// A2 (mk x nA, lda) <- (I - Vc op(T) Vc^H) A2 for ONE panel (kk <= NB reflectors)
+// A2 (mk x nA, lda) <- (I - Vc op(T) Vc^H) A2 for ONE panel (kk <= NB reflectors); path 0 scratch
 template <class T>
 static int apply_panel(QrWork<T>& w, const T* Vc, i64 ldvc, const T* VcT, i64 ldvct, const T* Tj, i64 mk, int kk,
                        T* A2, i64 lda, i64 nA, int adjoint, cudaStream_t st) {
@@ -534,12 +783,12 @@ static int apply_panel(QrWork<T>& w, const T* Vc, i64 ldvc, const T* VcT, i64 ld
   GemmTN<T> g1;
   g1.At = Vc; g1.ldat = ldvc;
   g1.B = A2; g1.ldb = lda;
-  g1.C = w.Wp; g1.ldc = NB;
+  g1.C = w.Wp[0]; g1.ldc = NB;
   g1.M = kk; g1.N = nA; g1.K = mk;
   g1.conj_a = 1;
   g1.nsplit = wsplit_for(kk, nA, mk);
   g1.split_stride = (i64)NB * nA;
-  if ((i64)g1.nsplit * NB * nA > w.wp_elems) g1.nsplit = (int)(w.wp_elems / ((i64)NB * nA));
+  if ((i64)g1.nsplit * NB * nA > w.wp_elems[0]) g1.nsplit = (int)(w.wp_elems[0] / ((i64)NB * nA));
   if (g1.nsplit < 1) {
     set_error(GLA_ERR_INTERNAL, "W workspace too small", __FILE__, __LINE__);
     return GLA_ERR_INTERNAL;
@@ -547,12 +796,12 @@ static int apply_panel(QrWork<T>& w, const T* Vc, i64 ldvc, const T* VcT, i64 ld
   GLA_TRY(gemm_tn<T>(g1, st));
   const int smem_t = (NB * (NB + 1) + NB * 33) * (int)sizeof(T);
   GLA_CUDA(cudaFuncSetAttribute(apply_t_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_t));
-  apply_t_kernel<T><<<(unsigned)ceil_div(nA, 32), 256, smem_t, st>>>(w.Wp, g1.split_stride, g1.nsplit, kk, nA, Tj, NB,
-                                                                      adjoint, w.Z);
+  apply_t_kernel<T><<<(unsigned)ceil_div(nA, 32), 256, smem_t, st>>>(w.Wp[0], g1.split_stride, g1.nsplit, kk, nA, Tj, NB,
+                                                                      adjoint, w.Z[0]);
   GLA_CUDA(cudaGetLastError());
   GemmTN<T> g2;
   g2.At = VcT; g2.ldat = ldvct;
-  g2.B = w.Z; g2.ldb = NB;
+  g2.B = w.Z[0]; g2.ldb = NB;
   g2.C = A2; g2.ldc = lda;
   g2.M = mk; g2.N = nA; g2.K = kk;
   g2.alpha = -1;
@@ -560,20 +809,20 @@ static int apply_panel(QrWork<T>& w, const T* Vc, i64 ldvc, const T* VcT, i64 ld
   return gemm_tn<T>(g2, st);
 }
 
-// A2 (mo x nA) <- Q_{nj-1}^H ... Q_0^H A2 for the whole outer block (kbig reflectors in w.V / w.VT / w.Tm)
+// A2 (mo x nA) <- Q_{nj-1}^H ... Q_0^H A2 for the whole outer block held in buffer b (kbig reflectors, Gram
+// already in w.G[b]); path 1 scratch
 template <class T>
-static int apply_outer(QrWork<T>& w, i64 mo, int kbig, T* A2, i64 lda, i64 nA, cudaStream_t st) {
+static int apply_outer(QrWork<T>& w, int b, i64 mo, int kbig, T* A2, i64 lda, i64 nA, cudaStream_t st) {
   if (nA <= 0) return 0;
-  GLA_TRY(gram<T>(w, w.V, w.ldv, mo, kbig, w.G, NBO, st));
   GemmTN<T> g1;
-  g1.At = w.V; g1.ldat = w.ldv;
+  g1.At = w.V[b]; g1.ldat = w.ldv;
   g1.B = A2; g1.ldb = lda;
-  g1.C = w.Wp; g1.ldc = NBO;
+  g1.C = w.Wp[1]; g1.ldc = NBO;
   g1.M = kbig; g1.N = nA; g1.K = mo;
   g1.conj_a = 1;
   g1.nsplit = wsplit_for(kbig, nA, mo);
   g1.split_stride = (i64)NBO * nA;
-  if ((i64)g1.nsplit * NBO * nA > w.wp_elems) g1.nsplit = (int)(w.wp_elems / ((i64)NBO * nA));
+  if ((i64)g1.nsplit * NBO * nA > w.wp_elems[1]) g1.nsplit = (int)(w.wp_elems[1] / ((i64)NBO * nA));
   if (g1.nsplit < 1) {
     set_error(GLA_ERR_INTERNAL, "W workspace too small", __FILE__, __LINE__);
     return GLA_ERR_INTERNAL;
@@ -581,12 +830,12 @@ static int apply_outer(QrWork<T>& w, i64 mo, int kbig, T* A2, i64 lda, i64 nA, c
   GLA_TRY(gemm_tn<T>(g1, st));
   const int smem = (kbig * 33 + NB * (NB + 1)) * (int)sizeof(T);
   GLA_CUDA(cudaFuncSetAttribute(wy_fixup_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  wy_fixup_kernel<T><<<(unsigned)ceil_div(nA, 32), 256, smem, st>>>(w.Wp, g1.split_stride, g1.nsplit, kbig, nA, w.G, NBO,
-                                                                     w.Tm, NBO, w.Z);
+  wy_fixup_kernel<T><<<(unsigned)ceil_div(nA, 32), 256, smem, st>>>(w.Wp[1], g1.split_stride, g1.nsplit, kbig, nA, w.G[b],
+                                                                     NBO, w.Tm[b], NBO, w.Z[1]);
   GLA_CUDA(cudaGetLastError());
   GemmTN<T> g2;
-  g2.At = w.VT; g2.ldat = NBO;
-  g2.B = w.Z; g2.ldb = NBO;
+  g2.At = w.VT[b]; g2.ldat = NBO;
+  g2.B = w.Z[1]; g2.ldb = NBO;
   g2.C = A2; g2.ldc = lda;
   g2.M = mo; g2.N = nA; g2.K = kbig;
   g2.alpha = -1;
@@ -595,20 +844,56 @@ static int apply_outer(QrWork<T>& w, i64 mo, int kbig, T* A2, i64 lda, i64 nA, c
 }
 
 // ------------------------------------------------------------------------------- drivers
+namespace {
+struct AuxStream {  // high-priority side stream + the events of the look-ahead schedule
+  cudaStream_t s = nullptr;
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  int create() {
+    int lo = 0, hi = 0;
+    GLA_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    GLA_CUDA(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi));
+    for (auto& e : ev) GLA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return 0;
+  }
+  ~AuxStream() {
+    for (auto& e : ev)
+      if (e) cudaEventDestroy(e);
+    if (s) cudaStreamDestroy(s);
+  }
+};
+}  // namespace
+
+// Look-ahead schedule (one outer block ahead):
+//   chain(o)  on the side stream : panels + per-panel T + updates inside outer block o   (needs far A(o-1))
+//   far A(o)  on the caller's    : outer block o applied to the columns of outer block o+1
+//   far B(o)  on the caller's    : ... and to everything right of it, concurrently with chain(o+1)
 template <class T>
 int geqr_blocked_dev(T* dA, i64 m, i64 n, i64 lda, T* dtau, i64 /*blocksize_hint*/, cudaStream_t st) {
   if (m < 0) return -2;
   if (n < 0) return -3;
   if (lda < (m > 1 ? m : 1)) return -4;
   if (m == 0 || n == 0) return 0;
+  const bool overlap = n > 2 * NBO && m > 2 * NBO;   // small problems: one stream, one buffer
   QrWork<T> w;
-  GLA_TRY(w.alloc(m, n, st));
+  GLA_TRY(w.alloc(m, NBO, n > NBO ? n - NBO : 0, overlap ? 2 : 1, st));
+  AuxStream aux;
+  cudaStream_t sc = st;  // chain stream
   int rc = 0;
+  if (overlap) {
+    rc = aux.create();
+    if (!rc) rc = check_cuda(cudaEventRecord(aux.ev[0], st), __FILE__, __LINE__);      // workspace ready
+    if (!rc) rc = check_cuda(cudaStreamWaitEvent(aux.s, aux.ev[0], 0), __FILE__, __LINE__);
+    sc = aux.s;
+  }
   bool done = false;
-  for (i64 o0 = 0; !done; o0 += NBO) {
+  int ob = 0;
+  for (i64 o0 = 0; !done && !rc; o0 += NBO, ++ob) {
     const i64 mo = m - o0, no = n - o0;
     const int nbo = (int)(no < NBO ? no : NBO);  // columns of this outer block
+    const int b = overlap ? (ob & 1) : 0;
+    w.cur = b;
     int kbig = 0;
+    // ---- chain(o)
     for (int j = 0; j * NB < nbo; ++j) {
       const i64 k0 = o0 + (i64)j * NB;
       const i64 mk = m - k0;
@@ -619,15 +904,15 @@ int geqr_blocked_dev(T* dA, i64 m, i64 n, i64 lda, T* dtau, i64 /*blocksize_hint
       const int nb = (int)(n - k0 < NB ? n - k0 : NB);
       const int kk = (int)(mk < nb ? mk : nb);
       T* Ak = dA + k0 + k0 * lda;
-      if ((rc = launch_panel<T>(Ak, lda, mk, nb, dtau + k0, w, j, st))) break;
+      if ((rc = launch_panel<T>(Ak, lda, mk, nb, dtau + k0, w, j, sc))) break;
       kbig += kk;
       const i64 nin = (o0 + nbo) - (k0 + nb);  // remaining columns INSIDE the outer block
       const i64 nfar = n - (o0 + nbo);
       if (nin > 0 || nfar > 0) {
-        if ((rc = build_T<T>(w, w.Vj(j), w.ldv, mk, kk, dtau + k0, w.Tj(j), st))) break;
+        if ((rc = build_T<T>(w, w.Vj(j), w.ldv, mk, kk, dtau + k0, w.Tj(j), sc))) break;
       }
       if (nin > 0) {
-        if ((rc = apply_panel<T>(w, w.Vj(j), w.ldv, w.VTj(j), NBO, w.Tj(j), mk, kk, Ak + (i64)nb * lda, lda, nin, 1, st)))
+        if ((rc = apply_panel<T>(w, w.Vj(j), w.ldv, w.VTj(j), NBO, w.Tj(j), mk, kk, Ak + (i64)nb * lda, lda, nin, 1, sc)))
           break;
       }
       if (!(mk > nb && n - k0 > nb)) {  // reference recursion stops: src/qr.jl:136
@@ -638,10 +923,30 @@ int geqr_blocked_dev(T* dA, i64 m, i64 n, i64 lda, T* dtau, i64 /*blocksize_hint
     }
     if (rc) break;
     const i64 nfar = n - (o0 + nbo);
-    if (nfar > 0 && kbig > 0) {
-      if ((rc = apply_outer<T>(w, mo, kbig, dA + o0 + (o0 + nbo) * lda, lda, nfar, st))) break;
-    }
     if (o0 + nbo >= n || o0 + nbo >= m) done = true;
+    if (nfar > 0 && kbig > 0) {
+      if (overlap) {
+        if ((rc = check_cuda(cudaEventRecord(aux.ev[1], sc), __FILE__, __LINE__))) break;       // chain(o) done
+        if ((rc = check_cuda(cudaStreamWaitEvent(st, aux.ev[1], 0), __FILE__, __LINE__))) break;
+      }
+      // ---- far update of outer block o: Gram once, then the next outer block's columns first
+      if ((rc = gram<T>(w, 1, w.V[b], w.ldv, mo, kbig, w.G[b], NBO, st))) break;
+      T* A2 = dA + o0 + (o0 + nbo) * lda;
+      const i64 nA = (overlap && !done && nfar > NBO) ? NBO : nfar;
+      if ((rc = apply_outer<T>(w, b, mo, kbig, A2, lda, nA, st))) break;
+      if (overlap && !done) {
+        if ((rc = check_cuda(cudaEventRecord(aux.ev[2], st), __FILE__, __LINE__))) break;       // far A(o) done
+        if ((rc = check_cuda(cudaStreamWaitEvent(sc, aux.ev[2], 0), __FILE__, __LINE__))) break;
+      }
+      if (nfar > nA) {
+        if ((rc = apply_outer<T>(w, b, mo, kbig, A2 + nA * lda, lda, nfar - nA, st))) break;
+      }
+    }
+  }
+  if (overlap) {  // join: everything issued on the side stream is ordered before what follows on `st`
+    cudaError_t e = cudaEventRecord(aux.ev[1], aux.s);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, aux.ev[1], 0);
+    if (!rc) rc = check_cuda(e, __FILE__, __LINE__);
   }
   w.release();
   return rc;
@@ -655,7 +960,7 @@ int ormqr_blocked_dev(const T* dF, i64 mF, i64 nF, i64 ldf, const T* dtau, T* dA
   const i64 k = mF < nF ? mF : nF;
   if (k == 0 || nA == 0) return 0;
   QrWork<T> w;
-  GLA_TRY(w.alloc(mF, nA, st));
+  GLA_TRY(w.alloc(mF, nA, 0, 1, st));
   int rc = 0;
   const i64 npan = (k + NB - 1) / NB;
   for (i64 ip = 0; ip < npan; ++ip) {
@@ -664,10 +969,10 @@ int ormqr_blocked_dev(const T* dF, i64 mF, i64 nF, i64 ldf, const T* dtau, T* dA
     const i64 mk = mF - k0;
     const int kk = (int)((k - k0) < NB ? (k - k0) : NB);
     const unsigned grid = (unsigned)(ceil_div(mk * kk, 256) > 2048 ? 2048 : ceil_div(mk * kk, 256));
-    extract_v_kernel<T><<<grid, 256, 0, st>>>(dF + k0 + k0 * ldf, ldf, (int)mk, kk, w.V, w.ldv, w.VT, NBO);
+    extract_v_kernel<T><<<grid, 256, 0, st>>>(dF + k0 + k0 * ldf, ldf, (int)mk, kk, w.V[0], w.ldv, w.VT[0], NBO);
     if ((rc = check_cuda(cudaGetLastError(), __FILE__, __LINE__))) break;
-    if ((rc = build_T<T>(w, w.V, w.ldv, mk, kk, dtau + k0, w.Tm, st))) break;
-    if ((rc = apply_panel<T>(w, w.V, w.ldv, w.VT, NBO, w.Tm, mk, kk, dA + k0, lda, nA, adjoint, st))) break;
+    if ((rc = build_T<T>(w, w.V[0], w.ldv, mk, kk, dtau + k0, w.Tm[0], st))) break;
+    if ((rc = apply_panel<T>(w, w.V[0], w.ldv, w.VT[0], NBO, w.Tm[0], mk, kk, dA + k0, lda, nA, adjoint, st))) break;
   }
   w.release();
   return rc;
