@@ -376,12 +376,28 @@ bool tma_ok(const GemmTN<double>& g) {
 
 int choose_nsplit(i64 M, i64 N, i64 K, int bm, int bn) {
   const i64 tiles = (i64)ceil_div(M, bm) * ceil_div(N, bn);
-  const int target = 2 * sm_count();
-  i64 ns = tiles >= target ? 1 : (target + tiles - 1) / tiles;
+  const i64 slots = 2 * (i64)sm_count();  // resident CTAs of the DMMA kernel
   const i64 max_by_k = K / 256 > 0 ? K / 256 : 1;
-  if (ns > max_by_k) ns = max_by_k;
-  if (ns > 64) ns = 64;
-  return (int)(ns < 1 ? 1 : ns);
+  if (tiles < slots) {  // under-filled grid: cut K until the machine is full
+    i64 ns = (slots + tiles - 1) / tiles;
+    if (ns > max_by_k) ns = max_by_k;
+    if (ns > 64) ns = 64;
+    return (int)(ns < 1 ? 1 : ns);
+  }
+  // a few waves: pick the split whose last wave is fullest (each extra slice costs one more pass over the
+  // partial outputs, charged as 1.5 % per slice)
+  if (tiles >= 8 * slots) return 1;
+  int best = 1;
+  double best_eff = 0.0;
+  for (int ns = 1; ns <= 8 && ns <= max_by_k; ++ns) {
+    const i64 ctas = tiles * ns;
+    const double eff = (double)ctas / (double)((ctas + slots - 1) / slots * slots) - 0.015 * (ns - 1);
+    if (eff > best_eff + 1e-9) {
+      best_eff = eff;
+      best = ns;
+    }
+  }
+  return best;
 }
 
 template <class T>

@@ -200,11 +200,20 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) qr_panel_kernel(PanelArgs<T>
   // slab S(i_local, col)
   T* S;
   i64 ld;
+  // 2-D thread mapping of the slab copies: rw threads walk the rows of a column, 256/rw columns at a time
+  const int rw = rows > 128 ? 256 : (rows > 64 ? 128 : 64);
+  const int ci0 = tid % rw, ccg = tid / rw, cncg = PANEL_THREADS / rw;
   if (a.resident) {
     S = reinterpret_cast<T*>(smem_raw);
     ld = a.lds;
-    for (int col = 0; col < a.nb; ++col)
-      for (int i = tid; i < rows; i += PANEL_THREADS) S[i + col * ld] = a.A[(i64)col * a.lda + r0 + i];
+    // every element is one cp.async: all loads of the slab are in flight at once
+    for (int col = ccg; col < a.nb; col += cncg)
+      for (int i = ci0; i < rows; i += rw) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(S + i + col * ld);
+        const T* src = a.A + (i64)col * a.lda + r0 + i;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst), "l"(src), "n"((int)sizeof(T)) : "memory");
+      }
+    asm volatile("cp.async.wait_all;" ::: "memory");
   } else {
     S = a.A + r0;
     ld = a.lda;
@@ -318,10 +327,19 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) qr_panel_kernel(PanelArgs<T>
           }
         } else {
           const T* bc = S + (i64)(sbe + x - ws) * ld;
-          for (int i = 0; i < rows; ++i) {
+          int isp = sbe - r0;  // local rows below isp lie strictly below the sub-panel's triangle: plain loads
+          isp = isp < 0 ? 0 : (isp > rows ? rows : isp);
+          for (int i = 0; i < isp; ++i) {
             const T b = bc[i];
 #pragma unroll
             for (int u = 0; u < 4; ++u) acc[u] = fmad(cj(vs(i, lg + u)), b, acc[u]);
+          }
+          const T* v0 = S + (i64)(sb0 + lg) * ld;
+#pragma unroll 4
+          for (int i = isp; i < rows; ++i) {
+            const T b = bc[i];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[u] = fmad(cj(v0[i + (i64)u * ld]), b, acc[u]);
           }
         }
 #pragma unroll
@@ -399,21 +417,23 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) qr_panel_kernel(PanelArgs<T>
   __syncthreads();
 
   // ---- write back: panel (if staged), clean reflectors Vc and VcT
-  if (a.resident) {
-    for (int col = 0; col < a.nb; ++col)
-      for (int i = tid; i < rows; i += PANEL_THREADS) a.A[(i64)col * a.lda + r0 + i] = S[i + col * ld];
-  }
-  for (int col = 0; col < kk; ++col)
-    for (int i = tid; i < rows; i += PANEL_THREADS) {
-      const int gi = r0 + i;
-      T v = gi < col ? Sc<T>::zero() : (gi == col ? Sc<T>::one() : S[i + (i64)col * ld]);
-      a.Vc[(i64)col * a.ldvc + gi] = v;
+  for (int col = ccg; col < a.nb; col += cncg)
+    for (int i = ci0; i < rows; i += rw) {
+      const T x = S[i + (i64)col * ld];
+      if (a.resident) a.A[(i64)col * a.lda + r0 + i] = x;
+      if (col < kk) {
+        const int gi = r0 + i;
+        a.Vc[(i64)col * a.ldvc + gi] = gi < col ? Sc<T>::zero() : (gi == col ? Sc<T>::one() : x);
+      }
     }
-  for (int e = tid; e < rows * kk; e += PANEL_THREADS) {
-    const int col = e % kk, i = e / kk;
-    const int gi = r0 + i;
-    T v = gi < col ? Sc<T>::zero() : (gi == col ? Sc<T>::one() : S[i + (i64)col * ld]);
-    a.VcT[(i64)gi * a.ldvct + col] = v;
+  {
+    const int col = tid % NB;  // VcT is contiguous along the reflector index
+    if (col < kk)
+      for (int i = tid / NB; i < rows; i += PANEL_THREADS / NB) {
+        const int gi = r0 + i;
+        const T v = gi < col ? Sc<T>::zero() : (gi == col ? Sc<T>::one() : S[i + (i64)col * ld]);
+        a.VcT[(i64)gi * a.ldvct + col] = v;
+      }
   }
 }
 
@@ -632,7 +652,7 @@ struct QrWork {
       i64 nA = nAs[q] < 1 ? 1 : nAs[q];
       // W partials: at most ~2*SMs tiles worth of split-K slices; 6 full W matrices, never less than what a
       // 64-slice split of a narrow (<= 4*NBO columns) W needs
-      i64 wcols = 6 * nA;
+      i64 wcols = 8 * nA;
       if (wcols < 64 * 4 * NBO && nA <= 4 * NBO) wcols = 64 * nA;
       wp_elems[q] = nAs[q] > 0 ? (i64)NBO * wcols : 0;
       s_wp[q] = al((wp_elems[q] > 0 ? wp_elems[q] : 1) * sizeof(T));

@@ -1,2 +1,2 @@
-timeout 300 python -m pytest tests/test_qr_blocked_gpu.py tests/test_cholesky_gpu.py -x -q 2>&1 | tail -3
-timeout 200 python tools/time_qr.py 1024 2048 4096 8192 16384
+timeout 300 python -m pytest tests/test_qr_blocked_gpu.py -x -q 2>&1 | tail -3
+timeout 200 python tools/time_qr.py 1024 4096 8192 16384
