@@ -258,7 +258,7 @@ def main():
         "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "traffic": 17.39e9 * batch / BATCH_PER_GPU,
-                     "kernel": "batched_qr32_reg_kernel<double>", "peak_source": peak_src,
+                     "kernel": "batched_qr32_ll_kernel<double>", "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": BYTES_PER_MATRIX * batch,
                      "fp64_tflops": FLOPS_PER_MATRIX * batch / (kernel_ms * 1e-3) / 1e12},
         "clocks": clocks,
@@ -333,31 +333,52 @@ def other_configs(g, torch, dist, dev, rank, world, stream):
         out["chol_f64_n4096"] = {"ms": best, "tflops": n ** 3 / 3.0 / (best * 1e-3) / 1e12, "info": int(info.item())}
         del X, S, dS
         torch.cuda.empty_cache()
-    # config 4: TSQR 8,388,608 x 64, row-sharded, R factors exchanged with NCCL all-gather
+    # config 4: TSQR 8,388,608 x 64, row-sharded; the 64x64 R factors are exchanged by ONE ncclAllGather issued
+    # inside the library (gla_dtsqr_allreduce_dev on a library-owned communicator) and reduced on every rank
     m_total, n = 1 << 23, 64
-    rows = m_total // world
+    _, rows = g.shard_range(m_total, rank, world)
     A = torch.randn((n, rows), device=dev, dtype=torch.float64)       # column-major rows x n
     Rloc = torch.zeros((n, n), device=dev, dtype=torch.float64)
     Rall = torch.zeros((world, n, n), device=dev, dtype=torch.float64)
     R = torch.zeros((n, n), device=dev, dtype=torch.float64)
+    comm = None
+    if world > 1:
+        def bcast(raw):
+            t = torch.zeros(128, dtype=torch.uint8, device=dev)
+            if raw is not None:
+                t.copy_(torch.tensor(list(raw), dtype=torch.uint8))
+            dist.broadcast(t, 0)
+            return bytes(t.cpu().tolist())
+        comm = g.TsqrComm(rank, world, bcast)
 
     def tsqr():
-        g.tsqr_local_dev(A.data_ptr(), rows, n, rows, Rloc.data_ptr(), n, stream)
+        g.tsqr_local_dev(A.data_ptr(), rows, n, rows, (Rloc if world > 1 else R).data_ptr(), n, stream)
         if world > 1:
-            dist.all_gather_into_tensor(Rall, Rloc)
-            g.tsqr_combine_dev(Rall.data_ptr(), world, n, R.data_ptr(), n, stream)
-    tsqr()
+            comm.allreduce_R(Rloc.data_ptr(), n, Rall.data_ptr(), R.data_ptr(), n, stream)
+    for _ in range(2):
+        tsqr()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    ms, _ = _time(torch, tsqr, reps=3)
+    ms, _ = _time(torch, tsqr, reps=5)
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = t.item()
+    # Gram identity of the local shard (sign independent): R_loc^T R_loc = A^T A
+    Rl = torch.triu((Rloc if world > 1 else R).t())
+    G = A @ A.t()
+    gram = ((Rl.t() @ Rl - G).abs().amax() / G.abs().amax()).item()
+    tf = 2.0 * m_total * n * n / (ms * 1e-3) / 1e12
     out["tsqr_f64_8388608x64"] = {"ms": ms, "rows_per_s": m_total / (ms * 1e-3), "gb_per_s": m_total * n * 8 / (ms * 1e-3) / 1e9,
-                                  "tflops": 2.0 * m_total * n * n / (ms * 1e-3) / 1e12, "scaling": "strong",
-                                  "collective": "ncclAllGather of 64x64 R factors" if world > 1 else "none"}
+                                  "tflops": tf, "scaling": "strong", "gram_check_local": gram,
+                                  "roofline": {"bound": "fp64 (AI 16 flop/B)", "achieved": tf, "peak": FP64_TENSOR_PEAK_TFLOPS * world,
+                                               "unit": "TFLOP/s", "frac": tf / (FP64_TENSOR_PEAK_TFLOPS * world),
+                                               "hbm_frac": m_total * n * 8 / (ms * 1e-3) / 1e9 / (_peaks()[0] * world)},
+                                  "collective": "ncclAllGather of 64x64 R factors inside gla_dtsqr_allreduce_dev" if world > 1 else "none"}
+    if comm is not None:
+        torch.cuda.synchronize()
+        comm.destroy()
     return out
 
 

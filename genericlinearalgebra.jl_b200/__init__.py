@@ -8,3 +8,5 @@ The directory name contains a dot, so it is loaded by path: see `load()` in /__g
 """
 from .glacuda import *  # noqa: F401,F403
 from . import glacuda  # noqa: F401
+from . import sharding  # noqa: F401
+from .sharding import shard_range, tsqr_R_sharded  # noqa: F401

@@ -351,6 +351,19 @@ int gla_zreflector_apply_right(void* A, int64_t m, int64_t n, int64_t lda, const
 int gla_dtsqr_local_dev(const double* dA, int64_t m, int64_t n, int64_t lda, double* dR, int64_t ldr, void* stream) { return tsqr_local_dev(dA, m, n, lda, dR, ldr, STREAM(stream)); }
 int gla_dtsqr_combine_dev(const double* dRs, int64_t count, int64_t n, double* dR, int64_t ldr, void* stream) { return tsqr_combine_dev(dRs, count, n, dR, ldr, STREAM(stream)); }
 int gla_dtsqr(const double* A, int64_t m, int64_t n, int64_t lda, double* R, int64_t ldr) { return tsqr_host(A, m, n, lda, R, ldr); }
+int gla_nccl_unique_id(void* id128) { return id128 ? nccl_unique_id(id128) : -1; }
+int gla_nccl_comm_init(void** comm, int nranks, const void* id128, int rank) {
+  if (!comm) return -1;
+  if (nranks < 1) return -2;
+  if (!id128) return -3;
+  if (rank < 0 || rank >= nranks) return -4;
+  return nccl_comm_init(comm, nranks, id128, rank);
+}
+int gla_nccl_comm_destroy(void* comm) { return comm ? nccl_comm_destroy(comm) : -1; }
+int gla_dtsqr_allreduce_dev(void* comm, int nranks, const double* dRloc, int64_t n, double* dstack, double* dR, int64_t ldr,
+                            void* stream) {
+  return tsqr_allreduce_dev(comm, nranks, dRloc, n, dstack, dR, ldr, STREAM(stream));
+}
 
 // ---- recursive Cholesky
 int gla_spotrf_recursive_L(float* A, int64_t n, int64_t lda, int64_t cutoff) { return potrf_host<float>(A, n, lda, cutoff); }

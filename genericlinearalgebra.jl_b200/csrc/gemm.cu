@@ -16,6 +16,7 @@
 
 #include <cuda.h>
 #include <mutex>
+#include <stdlib.h>
 
 namespace gla {
 
@@ -221,6 +222,169 @@ __global__ void __launch_bounds__(DmmaCfg<BM, BN, STAGES>::THREADS, 2)
           if (w1) p[1] = add ? p[1] + v1 : v1;
         }
       }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------- ComplexF64 on the DMMA pipe
+// C(i,j) = sum_k op(At(k,i)) B(k,j) for interleaved complex operands, computed as TWO real contractions over the
+// 2K interleaved doubles of each operand row (the tile a TMA box delivers IS that real row):
+//     conj:  Re C = sum_k' a[k'] b[k'],            Im C = sum_k' a[k'] b~[k'],   b~ = (b_im, -b_re) per pair
+//     plain: Re C = sum_k' a[k'] (b_re, -b_im),    Im C = sum_k' a[k'] (b_im,  b_re)
+// i.e. the B fragment of the "imaginary" product is the lane's PARTNER element inside the 16-byte complex number
+// (address ^ 8) with a sign flip on odd lanes -- an XOR on the sign bit, no FP64 instruction.  4 real DMMA flops
+// per complex FMA, the minimum without the 3M trick.  Warp tile 32 x 16 complex (Re and Im accumulators = the
+// same 64 registers as the real kernel's 32 x 32 tile), CTA tile BM x BN complex, same TMA / mbarrier ring.
+template <int BM, int BN, int STAGES>
+struct ZdmmaCfg {
+  static constexpr int WM = BM / 32, WN = BN / 16, NCW = WM * WN;
+  static constexpr int THREADS = NCW * 32;
+  static constexpr int STAGE_BYTES = (BM + BN) * 128;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 1024;
+};
+
+__device__ __forceinline__ double xor_sign(double v, unsigned m) {
+  return __hiloint2double(__double2hiint(v) ^ (int)m, __double2loint(v));
+}
+
+template <int BM, int BN, int STAGES>
+__global__ void __launch_bounds__(ZdmmaCfg<BM, BN, STAGES>::THREADS, 2)
+    gemm_tn_zdmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         zd* __restrict__ C, i64 ldc, int M, int N, int K2, int klen2, i64 split_stride, double alpha,
+                         int beta_one, int conj_a, int lower_only) {
+  using Cfg = ZdmmaCfg<BM, BN, STAGES>;
+  constexpr int WM = Cfg::WM, NCW = Cfg::NCW;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* sA = base;
+  unsigned char* sB = base + STAGES * BM * 128;
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  if (lower_only == 1 && n0 >= m0 + BM) return;
+  if (lower_only == 2 && m0 >= n0 + BN) return;
+  const int kbeg = blockIdx.z * klen2;                       // in doubles
+  const int kend = (kbeg + klen2 < K2) ? kbeg + klen2 : K2;
+  const int nk = (kend - kbeg + 15) >> 4;
+  const bool producer = threadIdx.x == 0;
+
+  if (producer) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], NCW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int it = 0; it < STAGES && it < nk; ++it) {
+      mbar_expect_tx(&full[it], Cfg::STAGE_BYTES);
+      tma_load_2d(sA + it * BM * 128, &tmA, kbeg + it * 16, m0, &full[it]);
+      tma_load_2d(sB + it * BN * 128, &tmB, kbeg + it * 16, n0, &full[it]);
+    }
+  }
+
+  const int wm = warp % WM, wn = warp / WM;
+  const int g = lane >> 2, t = lane & 3;
+  zd* Cz = C + (i64)blockIdx.z * split_stride;
+  // thread owns rows i0, i0+1 (per P) x columns 4t .. 4t+3 of the warp's 32 x 16 tile; column 4t + 2c + e lives in
+  // accumulator [.][e][c] (same interleave as the real kernel)
+  double are[4][2][2], aim[4][2][2];
+  const bool preload = beta_one && (alpha == 1.0 || alpha == -1.0);
+#pragma unroll
+  for (int P = 0; P < 2; ++P) {
+    const int i0 = m0 + wm * 32 + 16 * P + 2 * g;
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const int c = cc >> 1, e = cc & 1;
+      const int j = n0 + wn * 16 + 4 * t + cc;
+      zd v0 = make_zd(0., 0.), v1 = make_zd(0., 0.);
+      if (preload && j < N && i0 < M) {
+        const zd* p = Cz + (i64)j * ldc + i0;
+        v0 = p[0];
+        if (i0 + 1 < M) v1 = p[1];
+        v0 = scale_real(v0, alpha);
+        v1 = scale_real(v1, alpha);
+      }
+      are[2 * P][e][c] = v0.x;
+      aim[2 * P][e][c] = v0.y;
+      are[2 * P + 1][e][c] = v1.x;
+      aim[2 * P + 1][e][c] = v1.y;
+    }
+  }
+  __syncthreads();
+
+  int rowoff[4], key[4];
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const int r = 16 * (b >> 1) + 2 * g + (b & 1);
+    rowoff[b] = r * 128;
+    key[b] = r & 7;
+  }
+  const int tlo = (t & 1) << 3, thi = t >> 1;
+  const unsigned SIGN = 0x80000000u;
+  const unsigned mre = (t & 1) ? (conj_a ? 0u : SIGN) : 0u;   // flips the own element feeding Re C
+  const unsigned mim = (t & 1) ? (conj_a ? SIGN : 0u) : 0u;   // flips the partner element feeding Im C
+
+  for (int it = 0; it < nk; ++it) {
+    const int s = it % STAGES;
+    if (producer && it >= 1 && it - 1 + STAGES < nk) {
+      const int ps = (it - 1) % STAGES;
+      mbar_wait(&empty[ps], ((it - 1) / STAGES) & 1);
+      mbar_expect_tx(&full[ps], Cfg::STAGE_BYTES);
+      tma_load_2d(sA + ps * BM * 128, &tmA, kbeg + (it - 1 + STAGES) * 16, m0, &full[ps]);
+      tma_load_2d(sB + ps * BN * 128, &tmB, kbeg + (it - 1 + STAGES) * 16, n0, &full[ps]);
+    }
+    __syncwarp();
+    mbar_wait(&full[s], (it / STAGES) & 1);
+    const unsigned char* pa = sA + s * BM * 128 + wm * 32 * 128;
+    const unsigned char* pb = sB + s * BN * 128 + wn * 16 * 128;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double a[4], bre[2], bim[2];
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        const int off = rowoff[x] + ((((2 * j + thi) ^ key[x]) << 4) | tlo);
+        a[x] = *reinterpret_cast<const double*>(pa + off);
+      }
+#pragma unroll
+      for (int y = 0; y < 2; ++y) {
+        const int off = rowoff[y] + ((((2 * j + thi) ^ key[y]) << 4) | tlo);
+        bre[y] = xor_sign(*reinterpret_cast<const double*>(pb + off), mre);
+        bim[y] = xor_sign(*reinterpret_cast<const double*>(pb + (off ^ 8)), mim);
+      }
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 2; ++y) {
+          dmma884(are[x][y], a[x], bre[y]);
+          dmma884(aim[x][y], a[x], bim[y]);
+        }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
+
+  // ---- epilogue: two consecutive complex rows = 32 contiguous bytes per column
+#pragma unroll
+  for (int P = 0; P < 2; ++P) {
+    const int i0 = m0 + wm * 32 + 16 * P + 2 * g;
+    if (i0 >= M) continue;
+    const bool two = i0 + 1 < M;
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const int c = cc >> 1, e = cc & 1;
+      const int j = n0 + wn * 16 + 4 * t + cc;
+      if (j >= N) continue;
+      zd v0 = make_zd(alpha * are[2 * P][e][c], alpha * aim[2 * P][e][c]);
+      zd v1 = make_zd(alpha * are[2 * P + 1][e][c], alpha * aim[2 * P + 1][e][c]);
+      zd* p = Cz + (i64)j * ldc + i0;
+      const bool w0 = !lower_only || (lower_only == 1 ? i0 >= j : i0 <= j);
+      const bool w1 = two && (!lower_only || (lower_only == 1 ? i0 + 1 >= j : i0 + 1 <= j));
+      const bool add = beta_one && !preload;
+      if (w0) p[0] = add ? p[0] + v0 : v0;
+      if (w1) p[1] = add ? p[1] + v1 : v1;
     }
   }
 }
@@ -432,10 +596,33 @@ int gemm_tn<float>(const GemmTN<float>& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return 0;
   return launch_fma<float>(g, slice_len(g.K > 0 ? g.K : 1, g.nsplit), st);
 }
+template <int BM, int BN, int STAGES>
+static int launch_zdmma(const GemmTN<zd>& g, int klen, cudaStream_t st) {
+  using Cfg = ZdmmaCfg<BM, BN, STAGES>;
+  CUtensorMap tmA, tmB;   // complex K x R operand viewed as real 2K x R, ld doubled
+  GLA_TRY(make_map(&tmA, reinterpret_cast<const double*>(g.At), 2 * g.K, g.M, 2 * g.ldat, BM));
+  GLA_TRY(make_map(&tmB, reinterpret_cast<const double*>(g.B), 2 * g.K, g.N, 2 * g.ldb, BN));
+  auto kern = gemm_tn_zdmma_kernel<BM, BN, STAGES>;
+  GLA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+  dim3 grid((unsigned)ceil_div(g.M, BM), (unsigned)ceil_div(g.N, BN), (unsigned)g.nsplit);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmA, tmB, g.C, g.ldc, (int)g.M, (int)g.N, (int)(2 * g.K), 2 * klen,
+                                              g.split_stride, g.alpha, g.nsplit > 1 ? 0 : g.beta_one, g.conj_a,
+                                              g.lower_only);
+  GLA_CUDA(cudaGetLastError());
+  return 0;
+}
+
 template <>
 int gemm_tn<zd>(const GemmTN<zd>& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return 0;
-  return launch_fma<zd>(g, slice_len(g.K > 0 ? g.K : 1, g.nsplit), st);
+  const int klen = slice_len(g.K > 0 ? g.K : 1, g.nsplit);
+  static const bool use_fma = getenv("GLA_ZGEMM_FMA") != nullptr;   // A/B switch for profiling
+  if (!use_fma && g.K > 0 && g.M < (1ll << 31) && g.N < (1ll << 31) && g.K < (1ll << 30) && g.ldat < (1ll << 35) &&
+      g.ldb < (1ll << 35)) {
+    if (g.M <= 64) return launch_zdmma<64, 64, 4>(g, klen, st);
+    return launch_zdmma<128, 32, 4>(g, klen, st);
+  }
+  return launch_fma<zd>(g, klen, st);
 }
 
 template <class T>

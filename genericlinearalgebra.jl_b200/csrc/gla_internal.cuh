@@ -27,6 +27,12 @@ int reflector_apply_right_dev(T* dA, i64 m, i64 n, i64 lda, const T* dx, T tau, 
 // K5: TSQR (tsqr.cu)
 int tsqr_local_dev(const double* dA, i64 m, i64 n, i64 lda, double* dR, i64 ldr, cudaStream_t st);
 int tsqr_combine_dev(const double* dRs, i64 count, i64 n, double* dR, i64 ldr, cudaStream_t st);
+// NCCL (libnccl.so.2, dlopen'ed): communicator helpers and the R-factor exchange + reduction
+int nccl_unique_id(void* id128);
+int nccl_comm_init(void** comm, int nranks, const void* id128, int rank);
+int nccl_comm_destroy(void* comm);
+int tsqr_allreduce_dev(void* comm, int nranks, const double* dRloc, i64 n, double* dstack, double* dR, i64 ldr,
+                       cudaStream_t st);
 
 // K6: Cholesky (chol.cu)
 template <class T>

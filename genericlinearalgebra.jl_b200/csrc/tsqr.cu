@@ -1,94 +1,296 @@
-// tsqr.cu -- K5: tall-skinny QR, R factor only, as a communication-avoiding tree.
+// tsqr.cu -- K5: tall-skinny QR, R factor only, as a communication-avoiding reduction.
 //
 // Semantics: the R that qrBlocked! (reference src/qr.jl:113-146) leaves in the upper triangle of a
-// tall m x n matrix, n <= 64, up to the row signs discussed in DESIGN.md ("TSQR sign"): each tree
-// node is a Householder QR with the reference's reflector! convention (smallqr.cuh), so every
-// node's diagonal is -copysign(norm, pivot); the signs of the final R are those of the LAST node,
-// which need not equal the signs sequential Householder on the whole matrix would give.
+// tall m x n matrix, n <= 64, up to the row signs discussed in DESIGN.md ("TSQR sign"): every
+// reduction node is a Householder QR with the reference's reflector! convention (stdlib reflector!,
+// call site src/qr.jl:96: nu = copysign(norm, pivot), diagonal <- -nu, tau = (pivot+nu)/nu; left
+// reflectorApply!, call site src/qr.jl:102), so each node's diagonal is -copysign(norm, pivot); the
+// signs of the final R are those of the LAST node, which need not equal the signs sequential
+// Householder on the whole matrix would give.
 //
-// Level 0: one CTA per chunk of ROWS0 rows (chunk staged in shared memory, Householder QR in place,
-//          n x n R written out).  Level l>0: one CTA per group of FAN stacked R factors.
-// Multi-GPU: each rank runs level 0.. on its row block (gla_dtsqr_local_dev), the ranks exchange
-// their n x n R factors (NCCL all-gather, 32 KiB each) and every rank reduces the stack
-// (gla_dtsqr_combine_dev).
+// tsqr_stream_kernel: TWO PERSISTENT CTAs PER SM, each streams over its contiguous row range in chunks of
+// 32*NWARPS rows and folds every chunk into a running n x n R held in shared memory:
+//     [ R ]          [ R' ]
+//     [ C ]  = Q  *  [ 0  ]        (R upper triangular, C the dense chunk)
+// Column step k only touches row k of R and the dense rows, so the flop count is the minimal 2 m n^2.
+//   * warp w keeps rows 32w..32w+31 of the chunk IN REGISTERS, lane c owning columns c and c+32
+//     (64 values x 2); the pivot column is published once per step through shared memory and read
+//     back with broadcast LDS.128;
+//   * one __syncthreads per step: every warp writes its 64 partial dots, all warps sum the NWARPS
+//     partials in the same fixed order (bitwise identical scalars in every warp, deterministic);
+//   * the next chunk is prefetched with cp.async into the (then free) staging tile while the current
+//     one is being reduced; out-of-range rows / columns are zero-filled (zero rows do not change R);
+//   * sqrt / reciprocal from MUFU seeds + FMA refinement (fastmath.cuh).
+// The per-CTA R factors are stacked into a tall matrix and reduced by the same kernel until one is left.
+// Multi-GPU: each rank reduces its row block (gla_dtsqr_local_dev), the ranks exchange their n x n R
+// factors with ONE ncclAllGather (32 KiB each, NVLink) and every rank reduces the stack
+// (gla_dtsqr_combine_dev); gla_dtsqr_allreduce_dev does exchange + reduction on a caller-owned communicator.
+#include "fastmath.cuh"
 #include "gla_internal.cuh"
-#include "smallqr.cuh"
+
+#include <dlfcn.h>
+#include <mutex>
 
 namespace gla {
 
 constexpr int TSQR_MAXN = 64;
+constexpr int GLA_ERR_NCCL_CODE = 2000;  // GLA_ERR_NCCL in include/gla_cuda.h
+constexpr int TS_LD = 34;  // staging column stride (doubles): 16 B aligned, LDS.128 of 8 lanes hit 8 distinct 16 B slots
 
-// chunk c = `nblk` consecutive blocks starting at block c*nblk; block b: rows_blk x n at src + b*bstride, ld
-__global__ void __launch_bounds__(SMALLQR_THREADS)
-    tsqr_node_kernel(const double* __restrict__ src, i64 ld, i64 bstride, i64 total_blocks, int rows_blk, i64 last_rows,
-                     int nblk, int n, double* __restrict__ Rout) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* sA = reinterpret_cast<double*>(smem_raw);
-  const i64 c = blockIdx.x;
-  const i64 b0 = c * nblk;
-  i64 b1 = b0 + nblk;
-  if (b1 > total_blocks) b1 = total_blocks;
-  // rows of this chunk (only the globally last block may be short)
-  i64 rows = (b1 - b0) * rows_blk;
-  if (b1 == total_blocks) rows -= rows_blk - last_rows;
-  const int lds = (int)(((i64)nblk * rows_blk) | 1);  // odd stride: conflict-free column walks
-  const int R = (int)rows;
-  for (i64 b = b0; b < b1; ++b) {
-    const double* blk = src + b * bstride;
-    const int rb = (b == total_blocks - 1) ? (int)last_rows : rows_blk;
-    const int roff = (int)((b - b0) * rows_blk);
-    for (int e = threadIdx.x; e < rb * n; e += blockDim.x) {
-      const int j = e / rb, i = e - j * rb;
-      sA[roff + i + j * lds] = blk[i + (i64)j * ld];
+// element (row, col) of the source: p + (row / blk_rows) * bstride + (row % blk_rows) + col * ld
+struct TsqrSrc {
+  const double* p;
+  i64 ld, blk_rows, bstride;
+};
+
+template <int NWARPS>
+struct TsCfg {
+  static constexpr int ROWS = 32 * NWARPS;
+  static constexpr int SMEM_DOUBLES = 64 * 64 + 2 * NWARPS * 64 + NWARPS * 32 + NWARPS * 64 * TS_LD;
+  static constexpr size_t SMEM = (size_t)SMEM_DOUBLES * sizeof(double);
+};
+
+__device__ __forceinline__ void cp_async8(double* dst, const double* src, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  const int sz = valid ? 8 : 0;  // src-size 0: the 8 destination bytes are zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+
+// one column step.  H = 0: pivot in the lane's first column (k = kl), H = 1: in the second (k = 32 + kl)
+template <int NWARPS, bool TWO, int H>
+__device__ __forceinline__ void ts_step(double (&a0)[32], double (&a1)[32], const int kl, const int lane, const int warp,
+                                        double* __restrict__ sR, double* __restrict__ part, double* __restrict__ pubw) {
+  const int k = 32 * H + kl;
+  if (lane == kl) {
+#pragma unroll
+    for (int r = 0; r < 32; r += 2)
+      *reinterpret_cast<double2*>(pubw + r) = H == 0 ? make_double2(a0[r], a0[r + 1]) : make_double2(a1[r], a1[r + 1]);
+  }
+  __syncwarp();
+  // row k of R: read BEFORE the step's barrier, warp 0 rewrites it after the barrier
+  const double top0 = (H == 0) ? sR[k * 64 + lane] : 0.0;
+  const double top1 = TWO ? sR[k * 64 + 32 + lane] : 0.0;
+  double p0[4] = {0., 0., 0., 0.}, p1[4] = {0., 0., 0., 0.};
+#pragma unroll
+  for (int r = 0; r < 32; r += 4) {
+    const double2 xa = *reinterpret_cast<const double2*>(pubw + r);
+    const double2 xb = *reinterpret_cast<const double2*>(pubw + r + 2);
+    if (H == 0) {
+      p0[0] = fma(xa.x, a0[r], p0[0]);
+      p0[1] = fma(xa.y, a0[r + 1], p0[1]);
+      p0[2] = fma(xb.x, a0[r + 2], p0[2]);
+      p0[3] = fma(xb.y, a0[r + 3], p0[3]);
+    }
+    if (TWO) {
+      p1[0] = fma(xa.x, a1[r], p1[0]);
+      p1[1] = fma(xa.y, a1[r + 1], p1[1]);
+      p1[2] = fma(xb.x, a1[r + 2], p1[2]);
+      p1[3] = fma(xb.y, a1[r + 3], p1[3]);
     }
   }
+  double* pp = part + ((k & 1) * NWARPS + warp) * 64;
+  if (H == 0) pp[lane] = (p0[0] + p0[1]) + (p0[2] + p0[3]);
+  if (TWO) pp[32 + lane] = (p1[0] + p1[1]) + (p1[2] + p1[3]);
   __syncthreads();
-  cta_qr_smem<double>(sA, R, n, lds, nullptr);
-  double* out = Rout + c * (i64)n * n;
-  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+  const double* pr = part + (k & 1) * NWARPS * 64;
+  double d0 = 0., d1 = 0.;
+#pragma unroll
+  for (int w = 0; w < NWARPS; ++w) {
+    if (H == 0) d0 += pr[w * 64 + lane];
+    if (TWO) d1 += pr[w * 64 + 32 + lane];
+  }
+  const double dk = __shfl_sync(0xffffffffu, H == 0 ? d0 : d1, kl);
+  const double alpha = __shfl_sync(0xffffffffu, H == 0 ? top0 : top1, kl);
+  const double n2 = fma(alpha, alpha, dk);
+  if (n2 != 0.0) {  // uniform over the CTA (identical scalars everywhere); zero column: tau = 0, nothing changes
+    double nu, ixi, tau;
+    if (n2 > 1e-280 && n2 < 1e280) {
+      // Goldschmidt: g -> sqrt(n2), hh -> 1/(2 sqrt(n2)); the reciprocal of xi is seeded from the approximate
+      // norm so that its MUFU latency overlaps these iterations (same scalar chain as the batched kernel)
+      double y0, r;
+      asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(n2));
+      double g = n2 * y0, hh = 0.5 * y0;
+      asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(alpha + copysign(g, alpha)));
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const double e = fma(-g, hh, 0.5);
+        g = fma(g, e, g);
+        hh = fma(hh, e, hh);
+      }
+      g = fma(fma(-g, g, n2), hh, g);  // last correction of the norm
+      nu = copysign(g, alpha);
+      const double xi = alpha + nu;
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const double e = fma(-xi, r, 1.0);
+        r = fma(r, e, r);
+      }
+      ixi = r;
+      tau = xi * copysign(hh + hh, alpha);  // xi / nu
+    } else {  // tiny / huge column (e.g. rounding residue of a rank-deficient block): IEEE sqrt and division
+      nu = copysign(sqrt(n2), alpha);
+      const double xi = alpha + nu;
+      ixi = 1.0 / xi;
+      tau = xi / nu;
+    }
+    // s = tau (R_kc + v^H a_c) with v = [1; x/xi]; R_kc -= s; dense part -= (s/xi) x
+    double t0 = 0., t1 = 0., nt0 = top0, nt1 = top1;
+    if (H == 0) {
+      const bool right = lane > kl;
+      const double s = tau * fma(d0, ixi, top0);
+      t0 = right ? -(s * ixi) : 0.;
+      nt0 = right ? top0 - s : (lane == kl ? -nu : top0);
+    }
+    if (TWO) {
+      const bool right = (H == 0) || lane > kl;
+      const double s = tau * fma(d1, ixi, top1);
+      t1 = right ? -(s * ixi) : 0.;
+      nt1 = right ? top1 - s : ((H == 1 && lane == kl) ? -nu : top1);
+    }
+    if (warp == 0) {
+      if (H == 0) sR[k * 64 + lane] = nt0;
+      if (TWO) sR[k * 64 + 32 + lane] = nt1;
+    }
+#pragma unroll
+    for (int r = 0; r < 32; r += 4) {
+      const double2 xa = *reinterpret_cast<const double2*>(pubw + r);
+      const double2 xb = *reinterpret_cast<const double2*>(pubw + r + 2);
+      if (H == 0) {
+        a0[r] = fma(t0, xa.x, a0[r]);
+        a0[r + 1] = fma(t0, xa.y, a0[r + 1]);
+        a0[r + 2] = fma(t0, xb.x, a0[r + 2]);
+        a0[r + 3] = fma(t0, xb.y, a0[r + 3]);
+      }
+      if (TWO) {
+        a1[r] = fma(t1, xa.x, a1[r]);
+        a1[r + 1] = fma(t1, xa.y, a1[r + 1]);
+        a1[r + 2] = fma(t1, xb.x, a1[r + 2]);
+        a1[r + 3] = fma(t1, xb.y, a1[r + 3]);
+      }
+    }
+  }
+  __syncwarp();  // every lane is done with the published column before the next owner overwrites it
+}
+
+// CTA b reduces rows [b*rows_per_cta, min(m, (b+1)*rows_per_cta)) to an n x n R, written (upper, zeros below) to
+// Rout + b*out_row_step with leading dimension ldro.
+template <int NWARPS, bool TWO>
+__global__ void __launch_bounds__(NWARPS * 32, 2)
+    tsqr_stream_kernel(const TsqrSrc src, const i64 m, const int n, const i64 rows_per_cta, double* __restrict__ Rout,
+                       const i64 ldro, const i64 out_row_step) {
+  using Cfg = TsCfg<NWARPS>;
+  extern __shared__ __align__(16) double ts_smem[];
+  double* sR = ts_smem;                       // [64][64]   R(k, c) at k*64 + c
+  double* part = sR + 64 * 64;                // [2][NWARPS][64] partial dots, double-buffered by step parity
+  double* pub = part + 2 * NWARPS * 64;       // [NWARPS][32] published pivot column
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* tile = pub + NWARPS * 32 + warp * 64 * TS_LD;  // [64][TS_LD] staging tile of this warp
+  double* pubw = pub + warp * 32;
+
+  for (int e = threadIdx.x; e < 64 * 64; e += NWARPS * 32) sR[e] = 0.0;
+  const i64 row_begin = (i64)blockIdx.x * rows_per_cta;
+  i64 row_end = row_begin + rows_per_cta;
+  if (row_end > m) row_end = m;
+  const i64 nchunks = (row_end - row_begin + Cfg::ROWS - 1) / Cfg::ROWS;
+  const int ncols = TWO ? 64 : 32;
+
+  auto prefetch = [&](i64 chunk) {
+    const i64 row = row_begin + chunk * Cfg::ROWS + 32 * warp + lane;
+    const bool rok = row < row_end;
+    const i64 rr = rok ? row : row_begin;
+    const double* base = src.p + (rr / src.blk_rows) * src.bstride + (rr % src.blk_rows);
+#pragma unroll 8
+    for (int c = 0; c < ncols; ++c) {
+      const bool ok = rok && c < n;
+      cp_async8(tile + c * TS_LD + lane, ok ? base + (i64)c * src.ld : src.p, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  if (nchunks > 0) prefetch(0);
+  __syncthreads();  // sR zeroed
+  const int k0max = n < 32 ? n : 32;
+  const int k1max = n - 32;
+  for (i64 chunk = 0; chunk < nchunks; ++chunk) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    double a0[32], a1[32];
+#pragma unroll
+    for (int r = 0; r < 32; r += 2) {
+      const double2 v = *reinterpret_cast<const double2*>(tile + lane * TS_LD + r);
+      a0[r] = v.x;
+      a0[r + 1] = v.y;
+      if (TWO) {
+        const double2 u = *reinterpret_cast<const double2*>(tile + (lane + 32) * TS_LD + r);
+        a1[r] = u.x;
+        a1[r + 1] = u.y;
+      } else {
+        a1[r] = a1[r + 1] = 0.0;
+      }
+    }
+    __syncwarp();  // the tile is free: stream the next chunk into it while this one is reduced
+    if (chunk + 1 < nchunks) prefetch(chunk + 1);
+    for (int kl = 0; kl < k0max; ++kl) ts_step<NWARPS, TWO, 0>(a0, a1, kl, lane, warp, sR, part, pubw);
+    if (TWO)
+      for (int kl = 0; kl < k1max; ++kl) ts_step<NWARPS, TWO, 1>(a0, a1, kl, lane, warp, sR, part, pubw);
+  }
+  __syncthreads();
+  double* out = Rout + (i64)blockIdx.x * out_row_step;
+  for (int e = threadIdx.x; e < n * n; e += NWARPS * 32) {
     const int j = e / n, i = e - j * n;
-    out[e] = (i <= j && i < R) ? sA[i + j * lds] : 0.0;
+    out[(i64)j * ldro + i] = i <= j ? sR[i * 64 + j] : 0.0;
   }
 }
 
-static int run_tree(const double* src, i64 ld, i64 bstride, i64 total_blocks, int rows_blk, i64 last_rows, int n,
-                    double* dR, i64 ldr, cudaStream_t st) {
-  // workspace: ping-pong buffers of R stacks
-  const int rows_target = n <= 16 ? 1024 : (n <= 32 ? 512 : 256);
-  int nblk = rows_target / rows_blk;
-  if (nblk < 2) nblk = 2;
-  i64 chunks = (total_blocks + nblk - 1) / nblk;
+constexpr int TS_WARPS = 4;   // 128-row chunks
+constexpr int TS_CTAS_PER_SM = 2;  // two independent CTAs per SM: one's scalar chain / barrier hides behind the other's FMA sweeps
+
+static int launch_stream(const TsqrSrc& src, i64 m, int n, i64 rows_per_cta, i64 grid, double* out, i64 ldro,
+                         i64 out_row_step, cudaStream_t st) {
+  using Cfg = TsCfg<TS_WARPS>;
+  if (n > 32) {
+    auto kern = tsqr_stream_kernel<TS_WARPS, true>;
+    GLA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    kern<<<(unsigned)grid, TS_WARPS * 32, Cfg::SMEM, st>>>(src, m, n, rows_per_cta, out, ldro, out_row_step);
+  } else {
+    auto kern = tsqr_stream_kernel<TS_WARPS, false>;
+    GLA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    kern<<<(unsigned)grid, TS_WARPS * 32, Cfg::SMEM, st>>>(src, m, n, rows_per_cta, out, ldro, out_row_step);
+  }
+  GLA_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// src (m rows) -> dR (n x n, ldr).  Level 0 uses one CTA per SM; the stacked per-CTA R factors (a tall
+// (grid*n) x n matrix) are reduced by the same kernel, one chunk per CTA, until a single CTA remains.
+static int run_reduction(TsqrSrc src, i64 m, int n, double* dR, i64 ldr, cudaStream_t st) {
+  constexpr int ROWS = TsCfg<TS_WARPS>::ROWS;
+  const i64 sms = (i64)sm_count() * TS_CTAS_PER_SM;  // resident CTAs
   double* buf[2] = {nullptr, nullptr};
-  GLA_CUDA(cudaMallocAsync(&buf[0], (size_t)chunks * n * n * sizeof(double), st));
-  i64 chunks1 = (chunks + 3) / 4;
-  int rc = check_cuda(cudaMallocAsync(&buf[1], (size_t)(chunks1 > 0 ? chunks1 : 1) * n * n * sizeof(double), st),
-                      __FILE__, __LINE__);
-  auto kern = tsqr_node_kernel;
-  int cur = 0;
-  if (!rc) rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), __FILE__, __LINE__);
-  if (!rc) {
-    size_t smem = (size_t)(((i64)nblk * rows_blk) | 1) * n * sizeof(double);
-    kern<<<(unsigned)chunks, SMALLQR_THREADS, smem, st>>>(src, ld, bstride, total_blocks, rows_blk, last_rows, nblk, n,
-                                                          buf[0]);
-    rc = check_cuda(cudaGetLastError(), __FILE__, __LINE__);
-  }
-  i64 count = chunks;
-  while (!rc && count > 1) {
-    int fan = rows_target / n;
-    if (fan < 2) fan = 2;
-    const i64 next = (count + fan - 1) / fan;
-    size_t smem = (size_t)(((i64)fan * n) | 1) * n * sizeof(double);
-    kern<<<(unsigned)next, SMALLQR_THREADS, smem, st>>>(buf[cur], n, (i64)n * n, count, n, n, fan, n, buf[cur ^ 1]);
-    rc = check_cuda(cudaGetLastError(), __FILE__, __LINE__);
+  int rc = 0, cur = 0;
+  bool first = true;
+  while (!rc) {
+    i64 grid = (m + ROWS - 1) / ROWS;
+    if (first && grid > sms) grid = sms;                 // persistent: every CTA streams many chunks
+    if (!first && grid > 1) grid = (m + 2 * ROWS - 1) / (2 * ROWS);  // upper levels: 2 chunks (4 R factors) per CTA
+    if (grid < 1) grid = 1;
+    i64 rows_per_cta = round_up((m + grid - 1) / grid, ROWS);
+    grid = (m + rows_per_cta - 1) / rows_per_cta;
+    if (grid <= 1) {
+      rc = launch_stream(src, m, n, rows_per_cta, 1, dR, ldr, 0, st);
+      break;
+    }
+    const i64 tall = grid * n;
+    if (!buf[cur]) rc = check_cuda(cudaMallocAsync(&buf[cur], (size_t)sms * n * n * sizeof(double), st), __FILE__, __LINE__);
+    if (rc) break;
+    rc = launch_stream(src, m, n, rows_per_cta, grid, buf[cur], tall, n, st);
+    src = TsqrSrc{buf[cur], tall, tall, 0};
+    m = tall;
     cur ^= 1;
-    count = next;
+    first = false;
   }
-  if (!rc)
-    rc = check_cuda(cudaMemcpy2DAsync(dR, ldr * sizeof(double), buf[cur], n * sizeof(double), n * sizeof(double), n,
-                                      cudaMemcpyDeviceToDevice, st),
-                    __FILE__, __LINE__);
-  cudaFreeAsync(buf[0], st);
-  if (buf[1]) cudaFreeAsync(buf[1], st);
+  for (double* b : buf)
+    if (b) cudaFreeAsync(b, st);
   return rc;
 }
 
@@ -102,12 +304,7 @@ int tsqr_local_dev(const double* dA, i64 m, i64 n, i64 lda, double* dR, i64 ldr,
     GLA_CUDA(cudaMemset2DAsync(dR, ldr * sizeof(double), 0, n * sizeof(double), n, st));
     return 0;
   }
-  // level-0 blocks of 64 rows so that the chunk size (rows_target) adapts to n
-  const int rows_blk = 64;
-  const i64 total_blocks = (m + rows_blk - 1) / rows_blk;
-  const i64 last_rows = m - (total_blocks - 1) * rows_blk;
-  // the ping-pong sizing in run_tree assumes a fan-in >= 4 at the upper levels
-  return run_tree(dA, lda, rows_blk, total_blocks, rows_blk, last_rows, (int)n, dR, ldr, st);
+  return run_reduction(TsqrSrc{dA, lda, m, 0}, m, (int)n, dR, ldr, st);
 }
 
 int tsqr_combine_dev(const double* dRs, i64 count, i64 n, double* dR, i64 ldr, cudaStream_t st) {
@@ -119,7 +316,84 @@ int tsqr_combine_dev(const double* dRs, i64 count, i64 n, double* dR, i64 ldr, c
     GLA_CUDA(cudaMemset2DAsync(dR, ldr * sizeof(double), 0, n * sizeof(double), n, st));
     return 0;
   }
-  return run_tree(dRs, n, n * n, count, (int)n, n, (int)n, dR, ldr, st);
+  // `count` stacked n x n blocks (each ld n): block b holds rows b*n .. b*n + n - 1 of the tall matrix
+  return run_reduction(TsqrSrc{dRs, n, n, n * n}, count * n, (int)n, dR, ldr, st);
+}
+
+// ------------------------------------------------------------------------------- NCCL exchange
+// libnccl.so.2 is resolved lazily with dlopen so that the library loads on hosts without NCCL (inside a
+// torch process the soname resolves to the copy torch already mapped).
+namespace {
+struct NcclUniqueId128 {  // ncclUniqueId: 128 opaque bytes, passed BY VALUE to ncclCommInitRank
+  char internal[128];
+};
+struct NcclApi {
+  void* h = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclUniqueId128, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+}  // namespace
+namespace {
+NcclApi& nccl() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    api.h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!api.h) api.h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!api.h) return;
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(api.h, "ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(api.h, "ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.h, "ncclCommDestroy"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(api.h, "ncclAllGather"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.h, "ncclGetErrorString"));
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.GetErrorString;
+  });
+  return api;
+}
+int nccl_check(int r, const char* file, int line) {
+  if (r == 0) return 0;
+  set_error(GLA_ERR_NCCL_CODE + r, nccl().GetErrorString ? nccl().GetErrorString(r) : "NCCL error", file, line);
+  return GLA_ERR_NCCL_CODE + r;
+}
+int nccl_ready() {
+  if (nccl().ok) return 0;
+  set_error(GLA_ERR_NCCL_CODE, "libnccl.so.2 not found or incomplete", __FILE__, __LINE__);
+  return GLA_ERR_NCCL_CODE;
+}
+}  // namespace
+
+int nccl_unique_id(void* id128) {
+  GLA_TRY(nccl_ready());
+  return nccl_check(nccl().GetUniqueId(id128), __FILE__, __LINE__);
+}
+int nccl_comm_init(void** comm, int nranks, const void* id128, int rank) {
+  GLA_TRY(nccl_ready());
+  NcclUniqueId128 id;
+  memcpy(&id, id128, sizeof(id));
+  return nccl_check(nccl().CommInitRank(comm, nranks, id, rank), __FILE__, __LINE__);
+}
+int nccl_comm_destroy(void* comm) {
+  GLA_TRY(nccl_ready());
+  return nccl_check(nccl().CommDestroy(comm), __FILE__, __LINE__);
+}
+
+// dRloc (n x n, contiguous, ld n) of this rank -> all-gather over `comm` into dstack (nranks x n x n) -> every
+// rank reduces the stack to the same dR.
+int tsqr_allreduce_dev(void* comm, int nranks, const double* dRloc, i64 n, double* dstack, double* dR, i64 ldr,
+                       cudaStream_t st) {
+  if (!comm) return -1;
+  if (nranks < 1) return -2;
+  if (n < 0 || n > TSQR_MAXN) return -4;
+  if (ldr < (n > 1 ? n : 1)) return -7;
+  if (n == 0) return 0;
+  GLA_TRY(nccl_ready());
+  const int ncclDouble = 8;  // ncclFloat64 (nccl.h: ncclDataType_t)
+  GLA_TRY(nccl_check(nccl().AllGather(dRloc, dstack, (size_t)(n * n), ncclDouble, comm, st), __FILE__, __LINE__));
+  return tsqr_combine_dev(dstack, nranks, n, dR, ldr, st);
 }
 
 }  // namespace gla

@@ -280,6 +280,33 @@ def tsqr_combine_dev(dRs: int, count: int, n: int, dR: int, ldr: int, stream: in
     _check(rc, "tsqr_combine_dev", ArgumentError)
 
 
+class TsqrComm:
+    """NCCL communicator owned by the library for the TSQR R-factor exchange (one process per GPU).
+    `broadcast_bytes(bytes_or_None) -> bytes` is the host framework's broadcast from rank 0 (e.g. over
+    torch.distributed); it carries the 128-byte ncclUniqueId."""
+
+    def __init__(self, rank: int, nranks: int, broadcast_bytes):
+        uid = C.create_string_buffer(128)
+        if rank == 0:
+            _check(lib().gla_nccl_unique_id(uid), "nccl_unique_id", ArgumentError)
+        raw = broadcast_bytes(bytes(uid.raw) if rank == 0 else None)
+        uid = C.create_string_buffer(bytes(raw), 128)
+        self.comm = C.c_void_p()
+        self.nranks = nranks
+        _check(lib().gla_nccl_comm_init(C.byref(self.comm), C.c_int(nranks), uid, C.c_int(rank)), "nccl_comm_init",
+               ArgumentError)
+
+    def allreduce_R(self, dRloc: int, n: int, dstack: int, dR: int, ldr: int, stream: int = 0) -> None:
+        rc = lib().gla_dtsqr_allreduce_dev(self.comm, C.c_int(self.nranks), C.c_void_p(dRloc), _I64(n), C.c_void_p(dstack),
+                                           C.c_void_p(dR), _I64(ldr), C.c_void_p(stream))
+        _check(rc, "tsqr_allreduce_dev", ArgumentError)
+
+    def destroy(self) -> None:
+        if self.comm:
+            lib().gla_nccl_comm_destroy(self.comm)
+            self.comm = C.c_void_p()
+
+
 # ------------------------------------------------------------------------------------ Cholesky
 def cholRecursive_(A, uplo="L", cutoff: int = 1):
     """GenericLinearAlgebra.cholRecursive!(A, Val{:L}, cutoff): lower Cholesky in place; the strict

@@ -111,6 +111,15 @@ GLA_API int gla_zgeqr_batched_dev(void* dA, int64_t m, int64_t n, int64_t batch,
 GLA_API int gla_dtsqr_local_dev(const double* dA, int64_t m, int64_t n, int64_t lda, double* dR, int64_t ldr, void* stream);
 GLA_API int gla_dtsqr_combine_dev(const double* dRstack, int64_t count, int64_t n, double* dR, int64_t ldr, void* stream);
 GLA_API int gla_dtsqr(const double* A, int64_t m, int64_t n, int64_t lda, double* R, int64_t ldr);
+/* multi-GPU exchange step (one process per GPU): NCCL is resolved with dlopen("libnccl.so.2").
+ *   gla_nccl_unique_id   : rank 0 fills 128 bytes (ncclUniqueId) that the host framework broadcasts
+ *   gla_nccl_comm_init   : every rank, after cudaSetDevice; *comm is an ncclComm_t
+ *   gla_dtsqr_allreduce_dev: dRloc (n x n, ld n, this rank's local R) -> ncclAllGather into dstack
+ *                          (nranks x n x n) -> every rank reduces the stack to the same dR (n x n, ldr). */
+GLA_API int gla_nccl_unique_id(void* id128);
+GLA_API int gla_nccl_comm_init(void** comm, int nranks, const void* id128, int rank);
+GLA_API int gla_nccl_comm_destroy(void* comm);
+GLA_API int gla_dtsqr_allreduce_dev(void* comm, int nranks, const double* dRloc, int64_t n, double* dstack, double* dR, int64_t ldr, void* stream);
 
 /* ---- recursive Cholesky, lower ------------------------------------------------------
  * replaces cholRecursive!(A, Val{:L}, cutoff)   src/cholesky.jl:37-55

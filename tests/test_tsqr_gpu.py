@@ -14,7 +14,7 @@ def _normalise(R):
 
 
 @pytest.mark.parametrize("m,n", [(4096, 64), (100000, 64), (5000, 32), (777, 17), (64, 64), (65, 64), (10, 4), (3, 5),
-                                 (300000, 8)])
+                                 (300000, 8), (1000003, 64), (40001, 33), (257, 64), (256, 40), (37888, 64)])
 def test_tsqr_matches_oracle_up_to_row_signs(gla, oracle, m, n):
     rng = np.random.default_rng(m + n)
     A = np.asfortranarray(rng.standard_normal((m, n)))
@@ -50,4 +50,22 @@ def test_tsqr_sharded_combine(gla, oracle):
     Ah = np.asfortranarray(A.cpu().numpy().T)
     ref_f, _ = oracle.qr_blocked(Ah, 12)
     a, b = _normalise(Rh), _normalise(np.triu(ref_f)[:n])
+    assert np.max(np.abs(a - b)) <= 1e-10 * np.max(np.abs(b))
+
+
+@pytest.mark.parametrize("count,n", [(1, 64), (3, 17), (8, 64), (40, 33)])
+def test_tsqr_combine_of_stacked_blocks(gla, oracle, count, n):
+    """gla_dtsqr_combine_dev on `count` stacked n x n upper factors == QR of the stacked matrix."""
+    import torch
+    rng = np.random.default_rng(count * 100 + n)
+    # well-conditioned upper factors (R of random tall blocks); a random triangular matrix would have kappa ~ 2^n
+    Rs = np.stack([np.linalg.qr(rng.standard_normal((4 * n, n)))[1] for _ in range(count)])   # block b, row i, col j
+    dRs = torch.from_numpy(np.ascontiguousarray(np.transpose(Rs, (0, 2, 1)))).cuda()   # each block column-major, ld n
+    R = torch.zeros((n, n), device="cuda", dtype=torch.float64)
+    gla.tsqr_combine_dev(dRs.data_ptr(), count, n, R.data_ptr(), n, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    Rh = R.cpu().numpy().T
+    ref_f, _ = oracle.qr_blocked(np.asfortranarray(Rs.reshape(count * n, n)), 12)
+    a, b = _normalise(Rh), _normalise(np.triu(ref_f)[:n])
+    assert np.array_equal(np.tril(Rh, -1), np.zeros((n, n)))
     assert np.max(np.abs(a - b)) <= 1e-10 * np.max(np.abs(b))
