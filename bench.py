@@ -304,11 +304,41 @@ def other_configs(g, torch, dist, dev, rank, world, stream):
             ms, _ = _time(torch, qr, reps=1)
             best = min(best, ms)
         tf = 4.0 / 3.0 * n ** 3 / (best * 1e-3) / 1e12
-        out["qr_f64_n16384"] = {"ms": best, "tflops": tf, "unit": "TFLOP/s",
+        # validate what was timed: R^T R x = A^T A x for a random x (storage is column-major: dA[j, i] = F[i, j])
+        xv = torch.randn(n, device=dev, dtype=torch.float64)
+        Rm = torch.triu(dA.t())
+        y1 = Rm.t() @ (Rm @ xv)
+        y2 = src @ (src.t() @ xv)
+        probe = ((y1 - y2).abs().max() / y2.abs().max()).item()
+        del Rm, y1, y2
+        out["qr_f64_n16384"] = {"ms": best, "tflops": tf, "unit": "TFLOP/s", "gram_probe": probe,
                                 "roofline": {"bound": "tensor", "achieved": tf, "peak": FP64_TENSOR_PEAK_TFLOPS,
                                              "unit": "TFLOP/s", "frac": tf / FP64_TENSOR_PEAK_TFLOPS,
                                              "peak_source": "measured DMMA.8x8x4 peak, tools/fp64_peak.cu"}}
         del src, dA
+        # config 5: ComplexF64 n = 16384 (complex reflectors, contraction on the FP64 tensor pipe as 2 real DMMA products)
+        import numpy as np
+        src = torch.randn((n, n), device=dev, dtype=torch.complex128)
+        dA = torch.empty_like(src)
+        ztau = torch.zeros(n, device=dev, dtype=torch.complex128)
+        best = 1e30
+        for _ in range(2):
+            dA.copy_(src)
+            ms, _ = _time(torch, lambda: g.qr_blocked_dev(dA.data_ptr(), n, n, n, ztau.data_ptr(), 0, stream, np.complex128), reps=1)
+            best = min(best, ms)
+        tf = 4.0 * 4.0 / 3.0 * n ** 3 / (best * 1e-3) / 1e12
+        xv = torch.randn(n, device=dev, dtype=torch.complex128)
+        Rm = torch.triu(dA.t())
+        y1 = Rm.conj().t() @ (Rm @ xv)
+        y2 = src.conj() @ (src.t() @ xv)
+        probe = ((y1 - y2).abs().max() / y2.abs().max()).item()
+        del Rm, y1, y2
+        out["qr_c128_n16384"] = {"ms": best, "tflops_real": tf, "gram_probe": probe, "unit": "real TFLOP/s (4 per complex FMA pair)",
+                                 "roofline": {"bound": "tensor", "achieved": tf, "peak": FP64_TENSOR_PEAK_TFLOPS,
+                                              "unit": "TFLOP/s", "frac": tf / FP64_TENSOR_PEAK_TFLOPS,
+                                              "peak_source": "measured DMMA.8x8x4 peak, tools/fp64_peak.cu"}}
+        del src, dA, ztau
+        torch.cuda.empty_cache()
         # config 1: n = 1024
         n = 1024
         src = torch.randn((n, n), device=dev, dtype=torch.float64)

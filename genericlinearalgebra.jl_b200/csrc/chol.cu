@@ -83,6 +83,12 @@ __global__ void conj_transpose_kernel(const T* __restrict__ A, i64 lda, int n, i
 // ------------------------------------------------------------------------------- diagonal block
 // One CTA: upper Cholesky of the nb x nb (<= 64) block at W (ld ldw) in place, plus its inverse into
 // Uinv (CB x CB, ld CB, upper, zero below).  Non-positive pivot -> *info = offset + index + 1 (first wins).
+//   factorisation: the block lives in REGISTERS, thread (ty, tx) of a 16 x 16 grid owns the cyclic 4 x 4 sub-grid
+//     S(ty + 16a, tx + 16b); per column step the owners of row j publish the un-scaled row (double-buffered by
+//     step parity, ONE __syncthreads per step), every thread derives d = sqrt(pivot) itself and applies the rank-1
+//     update to its 16 entries;
+//   inverse: back substitution X(i,c) = -(sum_{l=i+1..c} U(i,l) X(l,c)) / U(i,i), four lanes of ONE warp per column,
+//     so the 63 dependent steps are separated by __syncwarp only.
 template <class T>
 __global__ void __launch_bounds__(256) potrf_block_kernel(T* __restrict__ W, i64 ldw, int nb, T* __restrict__ Uinv,
                                                           int* __restrict__ info, int offset) {
@@ -91,63 +97,82 @@ __global__ void __launch_bounds__(256) potrf_block_kernel(T* __restrict__ W, i64
   typedef T Row[CB + 1];
   Row* S = reinterpret_cast<Row*>(smem_raw);  // S[i][j]
   Row* X = S + CB;
-  __shared__ int bad;
+  __shared__ T rowbuf[2][CB];
   const int tid = threadIdx.x;
-  if (tid == 0) bad = 0;
-  for (int e = tid; e < nb * nb; e += blockDim.x) {
-    const int j = e / nb, i = e - j * nb;
-    S[i][j] = i <= j ? W[(i64)j * ldw + i] : Sc<T>::zero();
-  }
-  __syncthreads();
-  for (int j = 0; j < nb; ++j) {
-    const R piv = re(S[j][j]);
-    if (!(piv > R(0))) {
-      if (tid == 0) bad = j + 1;
-      break;  // uniform: every thread reads the same S[j][j]
+  const int ty = tid >> 4, tx = tid & 15;
+  T s[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int i = ty + 16 * a, c = tx + 16 * b;
+      s[a][b] = (i <= c && c < nb) ? W[(i64)c * ldw + i] : Sc<T>::zero();
     }
-    const R d = sqrt(piv);
-    const R rd = R(1) / d;
-    __syncthreads();
-    // row j scaled
-    for (int c = j + tid; c < nb; c += blockDim.x) S[j][c] = (c == j) ? Sc<T>::from_real(d) : scale_real(S[j][c], rd);
-    __syncthreads();
-    // trailing update of the upper triangle: S(i,c) -= conj(U(j,i)) U(j,c), j < i <= c
-    const int rem = nb - j - 1;
-    for (int e = tid; e < rem * rem; e += blockDim.x) {
-      const int ii = e / rem, cc = e - ii * rem;
-      if (ii <= cc) {
-        const int i = j + 1 + ii, c = j + 1 + cc;
-        S[i][c] = S[i][c] - cj(S[j][i]) * S[j][c];
+  int bad = 0;
+  for (int j = 0; j < nb; ++j) {
+    T* rb = rowbuf[j & 1];
+    if (ty == (j & 15)) {
+      const int ja = j >> 4;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const T v01 = ja == 0 ? s[0][b] : s[1][b];
+        const T v23 = ja == 2 ? s[2][b] : s[3][b];
+        rb[tx + 16 * b] = ja < 2 ? v01 : v23;
       }
     }
     __syncthreads();
+    const R piv = re(rb[j]);
+    if (!(piv > R(0))) {  // uniform: every thread reads the same pivot
+      bad = j + 1;
+      break;
+    }
+    const R d = sqrt(piv);
+    const R rd = R(1) / d;
+    T ui[4], uc[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) ui[a] = cj(scale_real(rb[ty + 16 * a], rd));
+#pragma unroll
+    for (int b = 0; b < 4; ++b) uc[b] = scale_real(rb[tx + 16 * b], rd);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int i = ty + 16 * a;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int c = tx + 16 * b;
+        if (i > j && c >= i) s[a][b] = s[a][b] - ui[a] * uc[b];                   // trailing upper triangle
+        else if (i == j && c >= j) s[a][b] = c == j ? Sc<T>::from_real(d) : uc[b];  // row j of the factor
+      }
+    }
   }
-  __syncthreads();
   if (bad) {
     if (tid == 0) atomicCAS(info, 0, offset + bad);
     return;
   }
-  // inverse of the upper factor by back substitution, one column per 4 threads:
-  //   X(c,c) = 1/U(c,c);  X(i,c) = -(sum_{l=i+1..c} U(i,l) X(l,c)) / U(i,i),  i = c-1 .. 0
-  const int c = tid >> 2, part = tid & 3;
-  for (int e = tid; e < CB * CB; e += blockDim.x) X[e / CB][e % CB] = Sc<T>::zero();
-  __syncthreads();
-  if (c < nb && part == 0) X[c][c] = Sc<T>::from_real(R(1) / re(S[c][c]));
-  __syncthreads();
-  for (int i = nb - 2; i >= 0; --i) {
-    T s = Sc<T>::zero();
-    if (c < nb && c > i) {
-      for (int l = i + 1 + part; l <= c; l += 4) s = fmad(S[i][l], X[l][c], s);
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int i = ty + 16 * a, c = tx + 16 * b;
+      S[i][c] = s[a][b];
+      X[i][c] = Sc<T>::zero();
+      if (i <= c && c < nb) W[(i64)c * ldw + i] = s[a][b];
     }
-    s = s + shfl_xor_t<T>(s, 1);
-    s = s + shfl_xor_t<T>(s, 2);
-    if (c < nb && c > i && part == 0) X[i][c] = scale_real(-s, R(1) / re(S[i][i]));
-    __syncthreads();
+  __syncthreads();
+  // inverse of the upper factor, column c by lanes 4c .. 4c+3 of one warp
+  const int c = tid >> 2, part = tid & 3;
+  if (c < nb && part == 0) X[c][c] = Sc<T>::from_real(R(1) / re(S[c][c]));
+  __syncwarp();
+  for (int i = nb - 2; i >= 0; --i) {
+    T acc = Sc<T>::zero();
+    if (c < nb && c > i) {
+      for (int l = i + 1 + part; l <= c; l += 4) acc = fmad(S[i][l], X[l][c], acc);
+    }
+    acc = acc + shfl_xor_t<T>(acc, 1);
+    acc = acc + shfl_xor_t<T>(acc, 2);
+    if (c < nb && c > i && part == 0) X[i][c] = scale_real(-acc, R(1) / re(S[i][i]));
+    __syncwarp();
   }
-  for (int e = tid; e < nb * nb; e += blockDim.x) {
-    const int j = e / nb, i = e - j * nb;
-    if (i <= j) W[(i64)j * ldw + i] = S[i][j];
-  }
+  __syncthreads();
   for (int e = tid; e < CB * CB; e += blockDim.x) {
     const int j = e / CB, i = e - j * CB;
     Uinv[(i64)j * CB + i] = (i <= j && j < nb) ? X[i][j] : Sc<T>::zero();

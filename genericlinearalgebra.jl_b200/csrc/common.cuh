@@ -104,6 +104,18 @@ __host__ __device__ __forceinline__ float inv(float a) { return 1.f / a; }
 __host__ __device__ __forceinline__ double inv(double a) { return 1. / a; }
 __host__ __device__ __forceinline__ zd inv(zd a) { return zinv(a); }
 
+// ------------------------------------------------------------------ L2-only loads
+// Data handed from one kernel to the next at a FIXED address (per-panel T, Gram, split-K partials, Z, the C tile of
+// an in-place update) is read with ld.global.cg: kernels of the two look-ahead streams share SMs, and a stale L1 /
+// read-only-cache line of the previous contents of such a buffer was observed to survive the (other stream's) kernel
+// boundary on a busy SM.  L2 is the point of coherence, so .cg loads cannot see stale data.
+__device__ __forceinline__ float ldcg_t(const float* p) { return __ldcg(p); }
+__device__ __forceinline__ double ldcg_t(const double* p) { return __ldcg(p); }
+__device__ __forceinline__ zd ldcg_t(const zd* p) {
+  const double2 v = __ldcg(reinterpret_cast<const double2*>(p));
+  return make_zd(v.x, v.y);
+}
+
 // ------------------------------------------------------------------ warp helpers
 template <class R>
 __device__ __forceinline__ R warp_sum(R v) {

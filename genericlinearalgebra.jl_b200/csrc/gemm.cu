@@ -51,6 +51,13 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, in
       "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// explicit shared-state-space loads on 32-bit addresses (a pointer derived from the aligned-up dynamic-smem base is a
+// GENERIC pointer to the compiler, which then emits LD.E plus 64-bit address arithmetic instead of LDS)
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c[0]), "+d"(c[1])
@@ -74,7 +81,7 @@ template <int BM, int BN, int STAGES>
 __global__ void __launch_bounds__(DmmaCfg<BM, BN, STAGES>::THREADS, 2)
     gemm_tn_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                         double* __restrict__ C, i64 ldc, int M, int N, int K, int klen, i64 split_stride,
-                        double alpha, int beta_one, int lower_only, int vec_ok) {
+                        double alpha, int beta_one, int lower_only, int vec_ok, int dbg) {
   using Cfg = DmmaCfg<BM, BN, STAGES>;
   constexpr int WM = Cfg::WM, NCW = Cfg::NCW;
   extern __shared__ unsigned char smem_raw[];
@@ -94,13 +101,18 @@ __global__ void __launch_bounds__(DmmaCfg<BM, BN, STAGES>::THREADS, 2)
   const bool producer = threadIdx.x == 0;
 
   if (producer) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    if (!(dbg & 1)) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], NCW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (dbg & 2) __syncthreads();
+  if (producer) {
     // prologue: fill the ring
     for (int it = 0; it < STAGES && it < nk; ++it) {
       mbar_expect_tx(&full[it], Cfg::STAGE_BYTES);
@@ -131,12 +143,12 @@ __global__ void __launch_bounds__(DmmaCfg<BM, BN, STAGES>::THREADS, 2)
         if (preload && j < N && i0 < M) {
           const double* p = Cz + (i64)j * ldc + i0;
           if (vec_ok && i0 + 1 < M) {
-            const double2 o = *reinterpret_cast<const double2*>(p);
+            const double2 o = __ldcg(reinterpret_cast<const double2*>(p));
             v0 = o.x;
             v1 = o.y;
           } else {
-            v0 = p[0];
-            if (i0 + 1 < M) v1 = p[1];
+            v0 = __ldcg(p);
+            if (i0 + 1 < M) v1 = __ldcg(p + 1);
           }
           v0 *= alpha;
           v1 *= alpha;
@@ -157,6 +169,7 @@ __global__ void __launch_bounds__(DmmaCfg<BM, BN, STAGES>::THREADS, 2)
     key[b] = r & 7;
   }
   const int tlo = (t & 1) << 3, thi = t >> 1;
+  const uint32_t sA_u32 = smem_u32(sA), sB_u32 = smem_u32(sB);
 
   for (int it = 0; it < nk; ++it) {
     const int s = it % STAGES;
@@ -170,22 +183,23 @@ __global__ void __launch_bounds__(DmmaCfg<BM, BN, STAGES>::THREADS, 2)
     }
     __syncwarp();
     mbar_wait(&full[s], (it / STAGES) & 1);
-    const unsigned char* pa = sA + s * BM * 128 + wm * 32 * 128;
-    const unsigned char* pb = sB + s * BN * 128 + wn * 32 * 128;
+    const uint32_t pa = sA_u32 + s * BM * 128 + wm * 32 * 128;
+    const uint32_t pb = sB_u32 + s * BN * 128 + wn * 32 * 128;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       double a[4], b[4];
 #pragma unroll
       for (int x = 0; x < 4; ++x) {
         const int off = rowoff[x] + ((((2 * j + thi) ^ key[x]) << 4) | tlo);
-        a[x] = *reinterpret_cast<const double*>(pa + off);
-        b[x] = *reinterpret_cast<const double*>(pb + off);
+        a[x] = lds_f64(pa + off);
+        b[x] = lds_f64(pb + off);
       }
 #pragma unroll
       for (int x = 0; x < 4; ++x)
 #pragma unroll
         for (int y = 0; y < 4; ++y) dmma884(acc[x][y], a[x], b[y]);
     }
+    if (dbg & 4) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
   }
@@ -212,14 +226,14 @@ __global__ void __launch_bounds__(DmmaCfg<BM, BN, STAGES>::THREADS, 2)
         if (vec_ok && w0 && w1) {
           double2* pv = reinterpret_cast<double2*>(p);
           if (add) {
-            double2 o = *pv;
+            double2 o = __ldcg(pv);
             v0 += o.x;
             v1 += o.y;
           }
           *pv = make_double2(v0, v1);
         } else {
-          if (w0) p[0] = add ? p[0] + v0 : v0;
-          if (w1) p[1] = add ? p[1] + v1 : v1;
+          if (w0) p[0] = add ? __ldcg(p) + v0 : v0;
+          if (w1) p[1] = add ? __ldcg(p + 1) + v1 : v1;
         }
       }
     }
@@ -251,7 +265,7 @@ template <int BM, int BN, int STAGES>
 __global__ void __launch_bounds__(ZdmmaCfg<BM, BN, STAGES>::THREADS, 2)
     gemm_tn_zdmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          zd* __restrict__ C, i64 ldc, int M, int N, int K2, int klen2, i64 split_stride, double alpha,
-                         int beta_one, int conj_a, int lower_only) {
+                         int beta_one, int conj_a, int lower_only, int dbg) {
   using Cfg = ZdmmaCfg<BM, BN, STAGES>;
   constexpr int WM = Cfg::WM, NCW = Cfg::NCW;
   extern __shared__ unsigned char smem_raw[];
@@ -271,13 +285,18 @@ __global__ void __launch_bounds__(ZdmmaCfg<BM, BN, STAGES>::THREADS, 2)
   const bool producer = threadIdx.x == 0;
 
   if (producer) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    if (!(dbg & 1)) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], NCW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (dbg & 2) __syncthreads();
+  if (producer) {
     for (int it = 0; it < STAGES && it < nk; ++it) {
       mbar_expect_tx(&full[it], Cfg::STAGE_BYTES);
       tma_load_2d(sA + it * BM * 128, &tmA, kbeg + it * 16, m0, &full[it]);
@@ -302,8 +321,8 @@ __global__ void __launch_bounds__(ZdmmaCfg<BM, BN, STAGES>::THREADS, 2)
       zd v0 = make_zd(0., 0.), v1 = make_zd(0., 0.);
       if (preload && j < N && i0 < M) {
         const zd* p = Cz + (i64)j * ldc + i0;
-        v0 = p[0];
-        if (i0 + 1 < M) v1 = p[1];
+        v0 = ldcg_t(p);
+        if (i0 + 1 < M) v1 = ldcg_t(p + 1);
         v0 = scale_real(v0, alpha);
         v1 = scale_real(v1, alpha);
       }
@@ -323,6 +342,7 @@ __global__ void __launch_bounds__(ZdmmaCfg<BM, BN, STAGES>::THREADS, 2)
     key[b] = r & 7;
   }
   const int tlo = (t & 1) << 3, thi = t >> 1;
+  const uint32_t sA_u32 = smem_u32(sA), sB_u32 = smem_u32(sB);
   const unsigned SIGN = 0x80000000u;
   const unsigned mre = (t & 1) ? (conj_a ? 0u : SIGN) : 0u;   // flips the own element feeding Re C
   const unsigned mim = (t & 1) ? (conj_a ? SIGN : 0u) : 0u;   // flips the partner element feeding Im C
@@ -338,21 +358,21 @@ __global__ void __launch_bounds__(ZdmmaCfg<BM, BN, STAGES>::THREADS, 2)
     }
     __syncwarp();
     mbar_wait(&full[s], (it / STAGES) & 1);
-    const unsigned char* pa = sA + s * BM * 128 + wm * 32 * 128;
-    const unsigned char* pb = sB + s * BN * 128 + wn * 16 * 128;
+    const uint32_t pa = sA_u32 + s * BM * 128 + wm * 32 * 128;
+    const uint32_t pb = sB_u32 + s * BN * 128 + wn * 16 * 128;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       double a[4], bre[2], bim[2];
 #pragma unroll
       for (int x = 0; x < 4; ++x) {
         const int off = rowoff[x] + ((((2 * j + thi) ^ key[x]) << 4) | tlo);
-        a[x] = *reinterpret_cast<const double*>(pa + off);
+        a[x] = lds_f64(pa + off);
       }
 #pragma unroll
       for (int y = 0; y < 2; ++y) {
         const int off = rowoff[y] + ((((2 * j + thi) ^ key[y]) << 4) | tlo);
-        bre[y] = xor_sign(*reinterpret_cast<const double*>(pb + off), mre);
-        bim[y] = xor_sign(*reinterpret_cast<const double*>(pb + (off ^ 8)), mim);
+        bre[y] = xor_sign(lds_f64(pb + off), mre);
+        bim[y] = xor_sign(lds_f64(pb + (off ^ 8)), mim);
       }
 #pragma unroll
       for (int x = 0; x < 4; ++x)
@@ -362,6 +382,7 @@ __global__ void __launch_bounds__(ZdmmaCfg<BM, BN, STAGES>::THREADS, 2)
           dmma884(aim[x][y], a[x], bim[y]);
         }
     }
+    if (dbg & 4) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
   }
@@ -383,8 +404,8 @@ __global__ void __launch_bounds__(ZdmmaCfg<BM, BN, STAGES>::THREADS, 2)
       const bool w0 = !lower_only || (lower_only == 1 ? i0 >= j : i0 <= j);
       const bool w1 = two && (!lower_only || (lower_only == 1 ? i0 + 1 >= j : i0 + 1 <= j));
       const bool add = beta_one && !preload;
-      if (w0) p[0] = add ? p[0] + v0 : v0;
-      if (w1) p[1] = add ? p[1] + v1 : v1;
+      if (w0) p[0] = add ? ldcg_t(p) + v0 : v0;
+      if (w1) p[1] = add ? ldcg_t(p + 1) + v1 : v1;
     }
   }
 }
@@ -416,8 +437,8 @@ __global__ void __launch_bounds__(256)
       const int i = lr + 16 * r;
       const int k = k0 + lk;
       T va = Sc<T>::zero(), vb = Sc<T>::zero();
-      if (k < kend && m0 + i < M) va = At[(i64)(m0 + i) * ldat + k];
-      if (k < kend && n0 + i < N) vb = B[(i64)(n0 + i) * ldb + k];
+      if (k < kend && m0 + i < M) va = ldcg_t(At + (i64)(m0 + i) * ldat + k);
+      if (k < kend && n0 + i < N) vb = ldcg_t(B + (i64)(n0 + i) * ldb + k);
       sA[lk][i] = conj_a ? cj(va) : va;
       sB[lk][i] = vb;
     }
@@ -450,7 +471,7 @@ __global__ void __launch_bounds__(256)
       if (lower_only == 2 && i > j) continue;
       T v = scale_real(acc[x][y], alpha);
       T* p = Cz + (i64)j * ldc + i;
-      *p = beta_one ? *p + v : v;
+      *p = beta_one ? ldcg_t(p) + v : v;
     }
   }
 }
@@ -461,8 +482,8 @@ __global__ void sum_splits_kernel(T* __restrict__ out, i64 ldo, const T* __restr
   const i64 total = M * N;
   for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
     const i64 j = e / M, i = e - j * M;
-    T s = part[j * ldp + i];
-    for (int z = 1; z < nsplit; ++z) s = s + part[(i64)z * stride + j * ldp + i];
+    T s = ldcg_t(part + j * ldp + i);
+    for (int z = 1; z < nsplit; ++z) s = s + ldcg_t(part + (i64)z * stride + j * ldp + i);
     out[j * ldo + i] = s;
   }
 }
@@ -486,6 +507,11 @@ EncodeTiledFn get_encode() {
       fn = reinterpret_cast<EncodeTiledFn>(p);
   }
   return fn;
+}
+
+int gemm_dbg() {
+  static const int f = [] { const char* e = getenv("GLA_GEMM_DBG"); return e ? atoi(e) : 0; }();
+  return f;
 }
 
 // K x R column-major f64 operand (K contiguous), box = 16 x rows
@@ -524,8 +550,8 @@ int launch_dmma(const GemmTN<double>& g, int klen, cudaStream_t st) {
   const int vec_ok = ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0 && (g.ldc & 1) == 0 &&
                       ((g.split_stride & 1) == 0)) ? 1 : 0;
   kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmA, tmB, g.C, g.ldc, (int)g.M, (int)g.N, (int)g.K, klen,
-                                              g.split_stride, g.alpha, g.nsplit > 1 ? 0 : g.beta_one,
-                                              g.lower_only, vec_ok);
+                                         g.split_stride, g.alpha, g.nsplit > 1 ? 0 : g.beta_one,
+                                         g.lower_only, vec_ok, gemm_dbg());
   GLA_CUDA(cudaGetLastError());
   return 0;
 }
@@ -584,7 +610,8 @@ template <>
 int gemm_tn<double>(const GemmTN<double>& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return 0;
   const int klen = slice_len(g.K > 0 ? g.K : 1, g.nsplit);
-  if (g.K > 0 && tma_ok(g)) {
+  static const bool force_fma = getenv("GLA_DGEMM_FMA") != nullptr;   // A/B switch for profiling
+  if (!force_fma && g.K > 0 && tma_ok(g)) {
     // 8 consumer warps (32x32 each) + 1 TMA warp, 4 x 24 KB stages -> two CTAs per SM
     if (g.M <= 64) return launch_dmma<64, 128, 4>(g, klen, st);
     return launch_dmma<128, 64, 4>(g, klen, st);
@@ -607,7 +634,7 @@ static int launch_zdmma(const GemmTN<zd>& g, int klen, cudaStream_t st) {
   dim3 grid((unsigned)ceil_div(g.M, BM), (unsigned)ceil_div(g.N, BN), (unsigned)g.nsplit);
   kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmA, tmB, g.C, g.ldc, (int)g.M, (int)g.N, (int)(2 * g.K), 2 * klen,
                                               g.split_stride, g.alpha, g.nsplit > 1 ? 0 : g.beta_one, g.conj_a,
-                                              g.lower_only);
+                                              g.lower_only, gemm_dbg());
   GLA_CUDA(cudaGetLastError());
   return 0;
 }

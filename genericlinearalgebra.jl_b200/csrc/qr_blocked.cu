@@ -24,6 +24,7 @@
 #include "smallqr.cuh"
 
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 namespace gla {
 
@@ -207,13 +208,17 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) qr_panel_kernel(PanelArgs<T>
     S = reinterpret_cast<T*>(smem_raw);
     ld = a.lds;
     // every element is one cp.async: all loads of the slab are in flight at once
-    for (int col = ccg; col < a.nb; col += cncg)
-      for (int i = ci0; i < rows; i += rw) {
-        const unsigned dst = (unsigned)__cvta_generic_to_shared(S + i + col * ld);
+    // L2-only loads (see ldcg_t): the panel columns were just rewritten by the other stream's far update
+    for (int col = ccg; col < a.nb; col += cncg) {
+      int i = ci0;
+      for (; i + 3 * rw < rows; i += 4 * rw) {   // four independent loads in flight per thread
         const T* src = a.A + (i64)col * a.lda + r0 + i;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst), "l"(src), "n"((int)sizeof(T)) : "memory");
+        const T v0 = ldcg_t(src), v1 = ldcg_t(src + rw), v2 = ldcg_t(src + 2 * rw), v3 = ldcg_t(src + 3 * rw);
+        T* dst = S + i + col * ld;
+        dst[0] = v0; dst[rw] = v1; dst[2 * rw] = v2; dst[3 * rw] = v3;
       }
-    asm volatile("cp.async.wait_all;" ::: "memory");
+      for (; i < rows; i += rw) S[i + col * ld] = ldcg_t(a.A + (i64)col * a.lda + r0 + i);
+    }
   } else {
     S = a.A + r0;
     ld = a.lda;
@@ -463,14 +468,14 @@ __global__ void __launch_bounds__(256) larft_finish_kernel(const T* __restrict__
   Row* X = U + NB;
   T* st = reinterpret_cast<T*>(X + NB);
   const int tid = threadIdx.x;
-  if (tid < kk) st[tid] = tau[tid];
+  if (tid < kk) st[tid] = ldcg_t(tau + tid);
   __syncthreads();
   for (int e = tid; e < kk * kk; e += blockDim.x) {
     const int j = e / kk, i = e - j * kk;
     T g = Sc<T>::zero();
     if (i < j) {
-      g = Gp[(i64)j * kk + i];
-      for (int z = 1; z < nsplit; ++z) g = g + Gp[(i64)z * gstride + (i64)j * kk + i];
+      g = ldcg_t(Gp + (i64)j * kk + i);
+      for (int z = 1; z < nsplit; ++z) g = g + ldcg_t(Gp + (i64)z * gstride + (i64)j * kk + i);
       g = st[i] * g;
     }
     U[i][j] = g;
@@ -509,8 +514,8 @@ __global__ void __launch_bounds__(256) apply_t_kernel(const T* __restrict__ Wp, 
   for (int e = tid; e < kk * kk; e += blockDim.x) {
     const int l = e / kk, i = e - l * kk;  // element (i,l) of op(T)
     T v;
-    if (adjoint) v = (l <= i) ? cj(Tm[(i64)i * ldt + l]) : Sc<T>::zero();  // T^H(i,l) = conj(T(l,i))
-    else v = (i <= l) ? Tm[(i64)l * ldt + i] : Sc<T>::zero();
+    if (adjoint) v = (l <= i) ? cj(ldcg_t(Tm + (i64)i * ldt + l)) : Sc<T>::zero();  // T^H(i,l) = conj(T(l,i))
+    else v = (i <= l) ? ldcg_t(Tm + (i64)l * ldt + i) : Sc<T>::zero();
     sT[i][l] = v;
   }
   const i64 j0 = (i64)blockIdx.x * 32;
@@ -518,8 +523,8 @@ __global__ void __launch_bounds__(256) apply_t_kernel(const T* __restrict__ Wp, 
     const int jj = e / kk, l = e - jj * kk;
     T w = Sc<T>::zero();
     if (j0 + jj < nA) {
-      w = Wp[(j0 + jj) * NB + l];
-      for (int z = 1; z < nsplit; ++z) w = w + Wp[(i64)z * wstride + (j0 + jj) * NB + l];
+      w = ldcg_t(Wp + (j0 + jj) * NB + l);
+      for (int z = 1; z < nsplit; ++z) w = w + ldcg_t(Wp + (i64)z * wstride + (j0 + jj) * NB + l);
     }
     sW[l][jj] = w;
   }
@@ -556,8 +561,8 @@ __global__ void __launch_bounds__(256)
   for (int l = rq; l < kbig; l += 8) {
     T w = Sc<T>::zero();
     if (col < nA) {
-      w = Wp[col * ldw + l];
-      for (int z = 1; z < nsplit; ++z) w = w + Wp[(i64)z * wstride + col * ldw + l];
+      w = ldcg_t(Wp + col * ldw + l);
+      for (int z = 1; z < nsplit; ++z) w = w + ldcg_t(Wp + (i64)z * wstride + col * ldw + l);
     }
     sW[l][jj] = w;
   }
@@ -568,7 +573,7 @@ __global__ void __launch_bounds__(256)
       __syncthreads();
       for (int e = tid; e < rows_j * NB; e += 256) {       // sM[r][l] = G(jNB + r, iNB + l)
         const int l = e / rows_j, r = e - l * rows_j;
-        sM[r][l] = G[(i64)(i * NB + l) * ldg + j * NB + r];
+        sM[r][l] = ldcg_t(G + (i64)(i * NB + l) * ldg + j * NB + r);
       }
       __syncthreads();
       // register tile: 8 rows (rq, rq+8, ...) per thread share every load of W (9 LDS per 8 FMA instead of 16)
@@ -591,7 +596,7 @@ __global__ void __launch_bounds__(256)
     const T* Tj = Tm + (i64)j * NB * NB;
     for (int e = tid; e < rows_j * rows_j; e += 256) {     // sM[r][l] = conj(T_j(l, r)), l <= r
       const int r = e / rows_j, l = e - r * rows_j;
-      sM[r][l] = l <= r ? cj(Tj[(i64)r * NB + l]) : Sc<T>::zero();
+      sM[r][l] = l <= r ? cj(ldcg_t(Tj + (i64)r * NB + l)) : Sc<T>::zero();
     }
     __syncthreads();
     T out[NB / 8];
@@ -902,7 +907,13 @@ int geqr_blocked_dev(T* dA, i64 m, i64 n, i64 lda, T* dtau, i64 /*blocksize_hint
   if (n < 0) return -3;
   if (lda < (m > 1 ? m : 1)) return -4;
   if (m == 0 || n == 0) return 0;
-  const bool overlap = n > 2 * NBO && m > 2 * NBO;   // small problems: one stream, one buffer
+  // The one-outer-block look-ahead (panel chain on a side stream, concurrently with the far update) is OFF by
+  // default: with it on, repeated factorisations of the same matrix are not bitwise reproducible and some are plainly
+  // wrong (n = 16384: 9 of 10), although every declared dependency holds and the same schedule is clean when both
+  // paths use the FMA contraction or share one stream.  See DESIGN.md, "Look-ahead and TMA kernels".
+  // GLA_QR_OVERLAP=1 re-enables it for investigation only.
+  static const bool want_overlap = getenv("GLA_QR_OVERLAP") != nullptr;
+  const bool overlap = want_overlap && n > 2 * NBO && m > 2 * NBO;
   QrWork<T> w;
   GLA_TRY(w.alloc(m, NBO, n > NBO ? n - NBO : 0, overlap ? 2 : 1, st));
   AuxStream aux;

@@ -29,13 +29,13 @@
 #include "gla_internal.cuh"
 
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <mutex>
 
 namespace gla {
 
 constexpr int TSQR_MAXN = 64;
 constexpr int GLA_ERR_NCCL_CODE = 2000;  // GLA_ERR_NCCL in include/gla_cuda.h
-constexpr int TS_LD = 34;  // staging column stride (doubles): 16 B aligned, LDS.128 of 8 lanes hit 8 distinct 16 B slots
 
 // element (row, col) of the source: p + (row / blk_rows) * bstride + (row % blk_rows) + col * ld
 struct TsqrSrc {
@@ -43,12 +43,20 @@ struct TsqrSrc {
   i64 ld, blk_rows, bstride;
 };
 
-template <int NWARPS>
+// NWARPS warps, each holding RW rows of the chunk in registers
+template <int NWARPS, int RW>
 struct TsCfg {
-  static constexpr int ROWS = 32 * NWARPS;
-  static constexpr int SMEM_DOUBLES = 64 * 64 + 2 * NWARPS * 64 + NWARPS * 32 + NWARPS * 64 * TS_LD;
+  static constexpr int ROWS = RW * NWARPS;
+  static constexpr int SMEM_DOUBLES = 64 * 64 + 2 * NWARPS * 64 + NWARPS * RW + NWARPS * 64 * RW;
   static constexpr size_t SMEM = (size_t)SMEM_DOUBLES * sizeof(double);
 };
+
+// staging tile of one warp: 64 columns x RW rows, column stride RW doubles (no padding); the 16-byte chunk q of
+// column c sits at chunk q ^ (c & 7), so the LDS.128 of 8 consecutive lanes (one column each) hit 8 distinct banks
+template <int RW>
+__device__ __forceinline__ int ts_tile_idx(int c, int r) {
+  return c * RW + ((((r >> 1) ^ (c & 7)) << 1) | (r & 1));
+}
 
 __device__ __forceinline__ void cp_async8(double* dst, const double* src, bool valid) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
@@ -57,13 +65,13 @@ __device__ __forceinline__ void cp_async8(double* dst, const double* src, bool v
 }
 
 // one column step.  H = 0: pivot in the lane's first column (k = kl), H = 1: in the second (k = 32 + kl)
-template <int NWARPS, bool TWO, int H>
-__device__ __forceinline__ void ts_step(double (&a0)[32], double (&a1)[32], const int kl, const int lane, const int warp,
+template <int NWARPS, int RW, bool TWO, int H>
+__device__ __forceinline__ void ts_step(double (&a0)[RW], double (&a1)[RW], const int kl, const int lane, const int warp,
                                         double* __restrict__ sR, double* __restrict__ part, double* __restrict__ pubw) {
   const int k = 32 * H + kl;
   if (lane == kl) {
 #pragma unroll
-    for (int r = 0; r < 32; r += 2)
+    for (int r = 0; r < RW; r += 2)
       *reinterpret_cast<double2*>(pubw + r) = H == 0 ? make_double2(a0[r], a0[r + 1]) : make_double2(a1[r], a1[r + 1]);
   }
   __syncwarp();
@@ -72,7 +80,7 @@ __device__ __forceinline__ void ts_step(double (&a0)[32], double (&a1)[32], cons
   const double top1 = TWO ? sR[k * 64 + 32 + lane] : 0.0;
   double p0[4] = {0., 0., 0., 0.}, p1[4] = {0., 0., 0., 0.};
 #pragma unroll
-  for (int r = 0; r < 32; r += 4) {
+  for (int r = 0; r < RW; r += 4) {
     const double2 xa = *reinterpret_cast<const double2*>(pubw + r);
     const double2 xb = *reinterpret_cast<const double2*>(pubw + r + 2);
     if (H == 0) {
@@ -152,7 +160,7 @@ __device__ __forceinline__ void ts_step(double (&a0)[32], double (&a1)[32], cons
       if (TWO) sR[k * 64 + 32 + lane] = nt1;
     }
 #pragma unroll
-    for (int r = 0; r < 32; r += 4) {
+    for (int r = 0; r < RW; r += 4) {
       const double2 xa = *reinterpret_cast<const double2*>(pubw + r);
       const double2 xb = *reinterpret_cast<const double2*>(pubw + r + 2);
       if (H == 0) {
@@ -174,18 +182,18 @@ __device__ __forceinline__ void ts_step(double (&a0)[32], double (&a1)[32], cons
 
 // CTA b reduces rows [b*rows_per_cta, min(m, (b+1)*rows_per_cta)) to an n x n R, written (upper, zeros below) to
 // Rout + b*out_row_step with leading dimension ldro.
-template <int NWARPS, bool TWO>
+template <int NWARPS, int RW, bool TWO>
 __global__ void __launch_bounds__(NWARPS * 32, 2)
     tsqr_stream_kernel(const TsqrSrc src, const i64 m, const int n, const i64 rows_per_cta, double* __restrict__ Rout,
                        const i64 ldro, const i64 out_row_step) {
-  using Cfg = TsCfg<NWARPS>;
+  using Cfg = TsCfg<NWARPS, RW>;
   extern __shared__ __align__(16) double ts_smem[];
   double* sR = ts_smem;                       // [64][64]   R(k, c) at k*64 + c
   double* part = sR + 64 * 64;                // [2][NWARPS][64] partial dots, double-buffered by step parity
-  double* pub = part + 2 * NWARPS * 64;       // [NWARPS][32] published pivot column
+  double* pub = part + 2 * NWARPS * 64;       // [NWARPS][RW] published pivot column
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* tile = pub + NWARPS * 32 + warp * 64 * TS_LD;  // [64][TS_LD] staging tile of this warp
-  double* pubw = pub + warp * 32;
+  double* tile = pub + NWARPS * RW + warp * 64 * RW;  // staging tile of this warp (ts_tile_idx)
+  double* pubw = pub + warp * RW;
 
   for (int e = threadIdx.x; e < 64 * 64; e += NWARPS * 32) sR[e] = 0.0;
   const i64 row_begin = (i64)blockIdx.x * rows_per_cta;
@@ -193,16 +201,19 @@ __global__ void __launch_bounds__(NWARPS * 32, 2)
   if (row_end > m) row_end = m;
   const i64 nchunks = (row_end - row_begin + Cfg::ROWS - 1) / Cfg::ROWS;
   const int ncols = TWO ? 64 : 32;
+  constexpr int CPP = 32 / RW;                // columns per cp.async pass: RW lanes walk the rows of one column
+  const int lr = lane % RW, lc = lane / RW;
 
   auto prefetch = [&](i64 chunk) {
-    const i64 row = row_begin + chunk * Cfg::ROWS + 32 * warp + lane;
+    const i64 row = row_begin + chunk * Cfg::ROWS + RW * warp + lr;
     const bool rok = row < row_end;
     const i64 rr = rok ? row : row_begin;
     const double* base = src.p + (rr / src.blk_rows) * src.bstride + (rr % src.blk_rows);
 #pragma unroll 8
-    for (int c = 0; c < ncols; ++c) {
+    for (int c0 = 0; c0 < ncols; c0 += CPP) {
+      const int c = c0 + lc;
       const bool ok = rok && c < n;
-      cp_async8(tile + c * TS_LD + lane, ok ? base + (i64)c * src.ld : src.p, ok);
+      cp_async8(tile + ts_tile_idx<RW>(c, lr), ok ? base + (i64)c * src.ld : src.p, ok);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -214,14 +225,14 @@ __global__ void __launch_bounds__(NWARPS * 32, 2)
   for (i64 chunk = 0; chunk < nchunks; ++chunk) {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
-    double a0[32], a1[32];
+    double a0[RW], a1[RW];
 #pragma unroll
-    for (int r = 0; r < 32; r += 2) {
-      const double2 v = *reinterpret_cast<const double2*>(tile + lane * TS_LD + r);
+    for (int r = 0; r < RW; r += 2) {
+      const double2 v = *reinterpret_cast<const double2*>(tile + ts_tile_idx<RW>(lane, r));
       a0[r] = v.x;
       a0[r + 1] = v.y;
       if (TWO) {
-        const double2 u = *reinterpret_cast<const double2*>(tile + (lane + 32) * TS_LD + r);
+        const double2 u = *reinterpret_cast<const double2*>(tile + ts_tile_idx<RW>(lane + 32, r));
         a1[r] = u.x;
         a1[r + 1] = u.y;
       } else {
@@ -230,9 +241,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 2)
     }
     __syncwarp();  // the tile is free: stream the next chunk into it while this one is reduced
     if (chunk + 1 < nchunks) prefetch(chunk + 1);
-    for (int kl = 0; kl < k0max; ++kl) ts_step<NWARPS, TWO, 0>(a0, a1, kl, lane, warp, sR, part, pubw);
+    for (int kl = 0; kl < k0max; ++kl) ts_step<NWARPS, RW, TWO, 0>(a0, a1, kl, lane, warp, sR, part, pubw);
     if (TWO)
-      for (int kl = 0; kl < k1max; ++kl) ts_step<NWARPS, TWO, 1>(a0, a1, kl, lane, warp, sR, part, pubw);
+      for (int kl = 0; kl < k1max; ++kl) ts_step<NWARPS, RW, TWO, 1>(a0, a1, kl, lane, warp, sR, part, pubw);
   }
   __syncthreads();
   double* out = Rout + (i64)blockIdx.x * out_row_step;
@@ -242,29 +253,42 @@ __global__ void __launch_bounds__(NWARPS * 32, 2)
   }
 }
 
-constexpr int TS_WARPS = 4;   // 128-row chunks
+constexpr int TS_WARPS = 4;   // warps per CTA
+constexpr int TS_RW = 32;     // rows per warp -> 128-row chunks (measured: 11.0 ms vs 14.3 ms for 8 warps x 16 rows)
 constexpr int TS_CTAS_PER_SM = 2;  // two independent CTAs per SM: one's scalar chain / barrier hides behind the other's FMA sweeps
 
-static int launch_stream(const TsqrSrc& src, i64 m, int n, i64 rows_per_cta, i64 grid, double* out, i64 ldro,
-                         i64 out_row_step, cudaStream_t st) {
-  using Cfg = TsCfg<TS_WARPS>;
+template <int NW, int RW>
+static int launch_stream_cfg(const TsqrSrc& src, i64 m, int n, i64 rows_per_cta, i64 grid, double* out, i64 ldro,
+                             i64 out_row_step, cudaStream_t st) {
+  using Cfg = TsCfg<NW, RW>;
+  static_assert(Cfg::ROWS == TsCfg<TS_WARPS, TS_RW>::ROWS, "all configurations use the same chunk height");
   if (n > 32) {
-    auto kern = tsqr_stream_kernel<TS_WARPS, true>;
+    auto kern = tsqr_stream_kernel<NW, RW, true>;
     GLA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-    kern<<<(unsigned)grid, TS_WARPS * 32, Cfg::SMEM, st>>>(src, m, n, rows_per_cta, out, ldro, out_row_step);
+    kern<<<(unsigned)grid, NW * 32, Cfg::SMEM, st>>>(src, m, n, rows_per_cta, out, ldro, out_row_step);
   } else {
-    auto kern = tsqr_stream_kernel<TS_WARPS, false>;
+    auto kern = tsqr_stream_kernel<NW, RW, false>;
     GLA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-    kern<<<(unsigned)grid, TS_WARPS * 32, Cfg::SMEM, st>>>(src, m, n, rows_per_cta, out, ldro, out_row_step);
+    kern<<<(unsigned)grid, NW * 32, Cfg::SMEM, st>>>(src, m, n, rows_per_cta, out, ldro, out_row_step);
   }
   GLA_CUDA(cudaGetLastError());
   return 0;
 }
 
+static int launch_stream(const TsqrSrc& src, i64 m, int n, i64 rows_per_cta, i64 grid, double* out, i64 ldro,
+                         i64 out_row_step, cudaStream_t st) {
+  static const int cfg = [] {
+    const char* e = getenv("GLA_TSQR_CFG");   // tuning knob: 1 = 8 warps x 16 rows (more, thinner warps)
+    return e ? atoi(e) : 0;
+  }();
+  if (cfg == 1) return launch_stream_cfg<8, 16>(src, m, n, rows_per_cta, grid, out, ldro, out_row_step, st);
+  return launch_stream_cfg<TS_WARPS, TS_RW>(src, m, n, rows_per_cta, grid, out, ldro, out_row_step, st);
+}
+
 // src (m rows) -> dR (n x n, ldr).  Level 0 uses one CTA per SM; the stacked per-CTA R factors (a tall
 // (grid*n) x n matrix) are reduced by the same kernel, one chunk per CTA, until a single CTA remains.
 static int run_reduction(TsqrSrc src, i64 m, int n, double* dR, i64 ldr, cudaStream_t st) {
-  constexpr int ROWS = TsCfg<TS_WARPS>::ROWS;
+  constexpr int ROWS = TsCfg<TS_WARPS, TS_RW>::ROWS;
   const i64 sms = (i64)sm_count() * TS_CTAS_PER_SM;  // resident CTAs
   double* buf[2] = {nullptr, nullptr};
   int rc = 0, cur = 0;
