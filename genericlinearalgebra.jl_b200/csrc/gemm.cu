@@ -51,8 +51,12 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, in
       "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
-// explicit shared-state-space loads on 32-bit addresses (a pointer derived from the aligned-up dynamic-smem base is a
-// GENERIC pointer to the compiler, which then emits LD.E plus 64-bit address arithmetic instead of LDS)
+// Fragment loads MUST be explicit shared-state-space loads on 32-bit addresses.  A pointer derived from the aligned-up
+// dynamic-smem base is a GENERIC pointer to the compiler, which then emits LD.E (generic) instead of LDS -- and generic
+// loads of shared memory that TMA has just written were observed to return stale tiles whenever other kernels ran
+// concurrently on the GPU (look-ahead stream of the blocked QR, or any unrelated stream), although the mbarrier wait
+// preceded them.  With ld.shared the same stress tests are bitwise reproducible (tools/stress_qr.py,
+// tools/stress_chol_concurrent.py, tests/test_determinism_gpu.py).  LDS also drops the 64-bit address arithmetic.
 __device__ __forceinline__ double lds_f64(uint32_t addr) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
@@ -81,7 +85,7 @@ template <int BM, int BN, int STAGES>
 __global__ void __launch_bounds__(DmmaCfg<BM, BN, STAGES>::THREADS, 2)
     gemm_tn_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                         double* __restrict__ C, i64 ldc, int M, int N, int K, int klen, i64 split_stride,
-                        double alpha, int beta_one, int lower_only, int vec_ok, int dbg) {
+                        double alpha, int beta_one, int lower_only, int vec_ok) {
   using Cfg = DmmaCfg<BM, BN, STAGES>;
   constexpr int WM = Cfg::WM, NCW = Cfg::NCW;
   extern __shared__ unsigned char smem_raw[];
@@ -101,18 +105,13 @@ __global__ void __launch_bounds__(DmmaCfg<BM, BN, STAGES>::THREADS, 2)
   const bool producer = threadIdx.x == 0;
 
   if (producer) {
-    if (!(dbg & 1)) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
-    }
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], NCW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (dbg & 2) __syncthreads();
-  if (producer) {
     // prologue: fill the ring
     for (int it = 0; it < STAGES && it < nk; ++it) {
       mbar_expect_tx(&full[it], Cfg::STAGE_BYTES);
@@ -199,7 +198,6 @@ __global__ void __launch_bounds__(DmmaCfg<BM, BN, STAGES>::THREADS, 2)
 #pragma unroll
         for (int y = 0; y < 4; ++y) dmma884(acc[x][y], a[x], b[y]);
     }
-    if (dbg & 4) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
   }
@@ -265,7 +263,7 @@ template <int BM, int BN, int STAGES>
 __global__ void __launch_bounds__(ZdmmaCfg<BM, BN, STAGES>::THREADS, 2)
     gemm_tn_zdmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          zd* __restrict__ C, i64 ldc, int M, int N, int K2, int klen2, i64 split_stride, double alpha,
-                         int beta_one, int conj_a, int lower_only, int dbg) {
+                         int beta_one, int conj_a, int lower_only) {
   using Cfg = ZdmmaCfg<BM, BN, STAGES>;
   constexpr int WM = Cfg::WM, NCW = Cfg::NCW;
   extern __shared__ unsigned char smem_raw[];
@@ -285,18 +283,13 @@ __global__ void __launch_bounds__(ZdmmaCfg<BM, BN, STAGES>::THREADS, 2)
   const bool producer = threadIdx.x == 0;
 
   if (producer) {
-    if (!(dbg & 1)) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
-    }
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], NCW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (dbg & 2) __syncthreads();
-  if (producer) {
     for (int it = 0; it < STAGES && it < nk; ++it) {
       mbar_expect_tx(&full[it], Cfg::STAGE_BYTES);
       tma_load_2d(sA + it * BM * 128, &tmA, kbeg + it * 16, m0, &full[it]);
@@ -382,7 +375,6 @@ __global__ void __launch_bounds__(ZdmmaCfg<BM, BN, STAGES>::THREADS, 2)
           dmma884(aim[x][y], a[x], bim[y]);
         }
     }
-    if (dbg & 4) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
   }
@@ -509,11 +501,6 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-int gemm_dbg() {
-  static const int f = [] { const char* e = getenv("GLA_GEMM_DBG"); return e ? atoi(e) : 0; }();
-  return f;
-}
-
 // K x R column-major f64 operand (K contiguous), box = 16 x rows
 int make_map(CUtensorMap* tm, const double* base, i64 K, i64 R, i64 ld, int box_rows) {
   EncodeTiledFn enc = get_encode();
@@ -551,7 +538,7 @@ int launch_dmma(const GemmTN<double>& g, int klen, cudaStream_t st) {
                       ((g.split_stride & 1) == 0)) ? 1 : 0;
   kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmA, tmB, g.C, g.ldc, (int)g.M, (int)g.N, (int)g.K, klen,
                                          g.split_stride, g.alpha, g.nsplit > 1 ? 0 : g.beta_one,
-                                         g.lower_only, vec_ok, gemm_dbg());
+                                         g.lower_only, vec_ok);
   GLA_CUDA(cudaGetLastError());
   return 0;
 }
@@ -634,7 +621,7 @@ static int launch_zdmma(const GemmTN<zd>& g, int klen, cudaStream_t st) {
   dim3 grid((unsigned)ceil_div(g.M, BM), (unsigned)ceil_div(g.N, BN), (unsigned)g.nsplit);
   kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmA, tmB, g.C, g.ldc, (int)g.M, (int)g.N, (int)(2 * g.K), 2 * klen,
                                               g.split_stride, g.alpha, g.nsplit > 1 ? 0 : g.beta_one, g.conj_a,
-                                              g.lower_only, gemm_dbg());
+                                              g.lower_only);
   GLA_CUDA(cudaGetLastError());
   return 0;
 }

@@ -907,13 +907,12 @@ int geqr_blocked_dev(T* dA, i64 m, i64 n, i64 lda, T* dtau, i64 /*blocksize_hint
   if (n < 0) return -3;
   if (lda < (m > 1 ? m : 1)) return -4;
   if (m == 0 || n == 0) return 0;
-  // The one-outer-block look-ahead (panel chain on a side stream, concurrently with the far update) is OFF by
-  // default: with it on, repeated factorisations of the same matrix are not bitwise reproducible and some are plainly
-  // wrong (n = 16384: 9 of 10), although every declared dependency holds and the same schedule is clean when both
-  // paths use the FMA contraction or share one stream.  See DESIGN.md, "Look-ahead and TMA kernels".
-  // GLA_QR_OVERLAP=1 re-enables it for investigation only.
-  static const bool want_overlap = getenv("GLA_QR_OVERLAP") != nullptr;
-  const bool overlap = want_overlap && n > 2 * NBO && m > 2 * NBO;
+  // One-outer-block look-ahead: the panel chain of block o+1 runs on a high-priority side stream concurrently with
+  // the far update of block o.  (History, see DESIGN.md "Generic loads of TMA-written shared memory": until the GEMM
+  // kernels read their fragments with explicit ld.shared, this concurrency exposed wrong tiles; the schedule itself
+  // was never at fault.)  GLA_QR_NO_OVERLAP=1 selects the single-stream schedule for A/B measurements.
+  static const bool no_overlap = getenv("GLA_QR_NO_OVERLAP") != nullptr;
+  const bool overlap = !no_overlap && n > 2 * NBO && m > 2 * NBO;   // small problems: one stream, one buffer
   QrWork<T> w;
   GLA_TRY(w.alloc(m, NBO, n > NBO ? n - NBO : 0, overlap ? 2 : 1, st));
   AuxStream aux;

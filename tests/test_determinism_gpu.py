@@ -1,0 +1,67 @@
+"""Reproducibility under concurrency.  Every reduction in the library runs in a fixed order, so repeated runs on the
+same input must be BITWISE equal -- also while the look-ahead stream of the blocked QR is active and while unrelated
+kernels run on other streams.  (Regression test for the generic-load-of-TMA-written-shared-memory bug, DESIGN.md.)"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("kind,n", [("d", 2304), ("z", 1600), ("d", 4096)])
+def test_blocked_qr_bitwise_reproducible_with_lookahead(gla, kind, n):
+    import torch
+    dt = torch.complex128 if kind == "z" else torch.float64
+    npdt = np.complex128 if kind == "z" else np.float64
+    g = torch.Generator(device="cuda").manual_seed(n)
+    src = torch.randn((n, n), generator=g, device="cuda", dtype=torch.float64).to(dt)
+    if kind == "z":
+        src = src + 1j * torch.randn((n, n), generator=g, device="cuda", dtype=torch.float64)
+    tau = torch.zeros(n, device="cuda", dtype=dt)
+    st = torch.cuda.current_stream().cuda_stream
+    ref = None
+    for _ in range(6):
+        dA = src.clone()
+        gla.qr_blocked_dev(dA.data_ptr(), n, n, n, tau.data_ptr(), 0, st, npdt)   # n > 512: look-ahead active
+        torch.cuda.synchronize()
+        if ref is None:
+            ref = dA
+            A0, R = src.t(), torch.triu(dA.t())          # storage is column-major: dA[j, i] = F[i, j]
+            G = A0.conj().t() @ A0
+            assert ((R.conj().t() @ R - G).abs().max() / G.abs().max()).item() < 1e-12
+        else:
+            assert torch.equal(torch.view_as_real(dA) if kind == "z" else dA,
+                               torch.view_as_real(ref) if kind == "z" else ref)
+
+
+def test_cholesky_bitwise_reproducible_under_foreign_streams(gla):
+    """The TMA/DMMA contraction chain while a high-priority stream floods the GPU with unrelated kernels."""
+    import torch
+    n = 4096
+    g = torch.Generator(device="cuda").manual_seed(7)
+    X = torch.randn((n, n), generator=g, device="cuda", dtype=torch.float64)
+    S = X.t() @ X + n * torch.eye(n, device="cuda", dtype=torch.float64)
+    info = torch.zeros(1, device="cuda", dtype=torch.int32)
+    main = torch.cuda.Stream()
+    noise = torch.cuda.Stream(priority=-1)
+    nz = [torch.zeros(1 << 22, device="cuda") for _ in range(4)]
+    big = torch.zeros((2048, 2048), device="cuda")
+    ref = None
+    torch.cuda.synchronize()
+    for _ in range(8):
+        dA = S.clone()
+        torch.cuda.synchronize()
+        with torch.cuda.stream(main):
+            gla.chol_recursive_dev(dA.data_ptr(), n, n, info.data_ptr(), 1, main.cuda_stream)
+        with torch.cuda.stream(noise):
+            for k in range(200):
+                nz[k & 3].add_(1.0)
+                if k % 40 == 0:
+                    torch.mm(big, big)
+        torch.cuda.synchronize()
+        assert int(info.item()) == 0
+        if ref is None:
+            ref = dA
+            L = torch.tril(dA.t())
+            assert ((L @ L.t() - S).norm() / S.norm()).item() < 1e-13
+        else:
+            assert torch.equal(torch.tril(dA.t()), torch.tril(ref.t()))
