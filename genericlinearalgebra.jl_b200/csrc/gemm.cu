@@ -51,12 +51,16 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, in
       "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
-// Fragment loads MUST be explicit shared-state-space loads on 32-bit addresses.  A pointer derived from the aligned-up
-// dynamic-smem base is a GENERIC pointer to the compiler, which then emits LD.E (generic) instead of LDS -- and generic
-// loads of shared memory that TMA has just written were observed to return stale tiles whenever other kernels ran
-// concurrently on the GPU (look-ahead stream of the blocked QR, or any unrelated stream), although the mbarrier wait
-// preceded them.  With ld.shared the same stress tests are bitwise reproducible (tools/stress_qr.py,
-// tools/stress_chol_concurrent.py, tests/test_determinism_gpu.py).  LDS also drops the 64-bit address arithmetic.
+// Two rules for shared memory that TMA (the async proxy) writes and the warps read (both learnt the hard way: without
+// them the kernels were bitwise reproducible alone on the GPU and produced wrong tiles as soon as ANY other kernel ran
+// concurrently -- the look-ahead stream of the blocked QR or an unrelated stream):
+//  1. fragment loads are explicit ld.shared on 32-bit addresses.  A pointer derived from the aligned-up dynamic-smem
+//     base is a GENERIC pointer to the compiler, which emits LD.E (generic) plus 64-bit address arithmetic;
+//  2. a stage is handed back to TMA only after fence.proxy.async (CUTLASS: fence_view_async_shared()).  The mbarrier
+//     arrive orders generic-proxy accesses only; without the cross-proxy fence ptxas schedules the arrive directly
+//     behind the ISSUE of the last LDS (ahead of the DMMAs that consume them), and a refill can overwrite the slab
+//     while those loads are still in flight.
+__device__ __forceinline__ void release_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ double lds_f64(uint32_t addr) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
@@ -198,6 +202,7 @@ __global__ void __launch_bounds__(DmmaCfg<BM, BN, STAGES>::THREADS, 2)
 #pragma unroll
         for (int y = 0; y < 4; ++y) dmma884(acc[x][y], a[x], b[y]);
     }
+    release_fence();
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
   }
@@ -375,6 +380,7 @@ __global__ void __launch_bounds__(ZdmmaCfg<BM, BN, STAGES>::THREADS, 2)
           dmma884(aim[x][y], a[x], bim[y]);
         }
     }
+    release_fence();
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
   }
@@ -537,8 +543,8 @@ int launch_dmma(const GemmTN<double>& g, int klen, cudaStream_t st) {
   const int vec_ok = ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0 && (g.ldc & 1) == 0 &&
                       ((g.split_stride & 1) == 0)) ? 1 : 0;
   kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmA, tmB, g.C, g.ldc, (int)g.M, (int)g.N, (int)g.K, klen,
-                                         g.split_stride, g.alpha, g.nsplit > 1 ? 0 : g.beta_one,
-                                         g.lower_only, vec_ok);
+                                              g.split_stride, g.alpha, g.nsplit > 1 ? 0 : g.beta_one,
+                                              g.lower_only, vec_ok);
   GLA_CUDA(cudaGetLastError());
   return 0;
 }

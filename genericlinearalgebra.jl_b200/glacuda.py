@@ -26,7 +26,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgla_cuda.so")
+LIB_PATH = os.environ.get("GLA_CUDA_LIB") or os.path.join(_HERE, "lib", "libgla_cuda.so")   # same override as julia/GLACuda.jl
 _LIB = None
 
 _I64 = C.c_int64

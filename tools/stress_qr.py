@@ -7,6 +7,7 @@ import torch
 import __graft_entry__ as ge
 g = ge.load()
 kind = sys.argv[1]; n = int(sys.argv[2]); reps = int(sys.argv[3])
+noise_mode = sys.argv[4] if len(sys.argv) > 4 else "none"     # none | normal | high: unrelated kernels on another stream
 dt = torch.complex128 if kind == "z" else torch.float64
 npdt = np.complex128 if kind == "z" else np.float64
 st = torch.cuda.current_stream().cuda_stream
@@ -14,9 +15,19 @@ src = torch.randn((n, n), device="cuda", dtype=dt)
 dtau = torch.zeros(n, device="cuda", dtype=dt)
 ref = None
 bad = 0
+noise = None if noise_mode == "none" else torch.cuda.Stream(priority=-1 if noise_mode == "high" else 0)
+nz = [torch.zeros(1 << 22, device="cuda") for _ in range(4)]
+big = torch.zeros((2048, 2048), device="cuda")
 for it in range(reps):
     dA = src.clone()
+    torch.cuda.synchronize()
     g.qr_blocked_dev(dA.data_ptr(), n, n, n, dtau.data_ptr(), 0, st, npdt)
+    if noise is not None:
+        with torch.cuda.stream(noise):
+            for k in range(300):
+                nz[k & 3].add_(1.0)
+                if k % 50 == 0:
+                    torch.mm(big, big)
     torch.cuda.synchronize()
     # cheap per-rep correctness probe: R^H R x = A^H A x for a random x (storage is column-major: dA[j, i] = F[i, j])
     xv = torch.randn(n, device="cuda", dtype=dt, generator=None)
