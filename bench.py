@@ -35,6 +35,8 @@ M = N_ = 32
 BATCH_PER_GPU = 1 << 20
 BYTES_PER_MATRIX = 8192 + 8192 + 256
 FLOPS_PER_MATRIX = 4.0 / 3.0 * 32 ** 3
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch (2^20 matrices), ncu --set full: profiles/r01_ncu_batched_ll_s4.txt
+NCU_DRAM_BYTES_PER_LAUNCH = 8.823852e9 + 8.818534e9
 FP64_TENSOR_PEAK_TFLOPS = 37.08               # measured on this pool: tools/fp64_peak.cu (profiles/fp64_peak_r01.txt)
 
 
@@ -257,7 +259,7 @@ def main():
                 "steps": e2e_steps, "api": "gla_dgeqr_batched (host pointers, pinned)"},
         "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": 17.39e9 * batch / BATCH_PER_GPU,
+                     "frac": achieved / hbm_peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH * batch / BATCH_PER_GPU,
                      "kernel": "batched_qr32_ll_kernel<double>", "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": BYTES_PER_MATRIX * batch,
                      "fp64_tflops": FLOPS_PER_MATRIX * batch / (kernel_ms * 1e-3) / 1e12},

@@ -1,14 +1,17 @@
-# One gpurun call: GPU parity tests, bench line, ncu launch lists and one full capture of the headline kernel.
+# One gpurun call: GPU parity tests, bench line (+ reference arm), ncu launch lists and full captures of the top kernels.
 set -x
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > gpurun_out/gpu.txt
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 > gpurun_out/pytest_gpu.txt
 cat gpurun_out/pytest_gpu.txt
-timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
-tail -c 3000 gpurun_out/bench.json
+timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
+tail -c 1500 gpurun_out/bench.json
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2>> gpurun_out/bench.err
+cat gpurun_out/bench_reference.json | head -c 600
 timeout 300 python tools/time_qr.py 1024 4096 8192 16384 > gpurun_out/time_qr.txt 2>&1
 cat gpurun_out/time_qr.txt
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/launches_bench.csv python bench.py --steps 2 --warmup 3 --skip-other --skip-cpu > gpurun_out/bench_ncu.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file gpurun_out/launches_qr16384.csv python tools/prof_qr.py 16384 > gpurun_out/prof_qr.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:batched_qr32 -s 3 -c 1 -o gpurun_out/prof_batched python bench.py --steps 2 --warmup 3 --skip-other --skip-cpu > gpurun_out/prof_batched.log 2>&1
+timeout 300 ncu --set full --clock-control none -k regex:gemm_tn_dmma_kernel -s 400 -c 2 -o gpurun_out/prof_gemm python tools/prof_qr.py 16384 > gpurun_out/prof_gemm.log 2>&1
 ls -la gpurun_out
