@@ -5,6 +5,7 @@
 #include "gla_internal.cuh"
 
 #include <new>
+#include <stdlib.h>
 
 using namespace gla;
 
@@ -56,8 +57,10 @@ int d2h_matrix(T* h, i64 ldh, const T* d, i64 ldd, i64 m, i64 n, cudaStream_t st
 }
 
 // ------------------------------------------------------------------ batched QR, host pointers
-// Chunked three-stream pipeline: H2D of chunk i+1 and D2H of chunk i-1 overlap the kernel of chunk i
-// (PCIe is full duplex), so the end-to-end time is max(H2D, D2H) rather than their sum.
+// Chunked multi-stream pipeline: H2D of later chunks and D2H of earlier ones overlap the kernel of chunk i (PCIe is
+// full duplex), so the end-to-end time tends to max(H2D, D2H) rather than their sum.  Measured on the B200 box
+// (tools/time_e2e.py; raw pinned copies run at 53 / 52 GB/s per direction): 64 MiB x 3 streams 4.6 M matrices/s,
+// 128 MiB x 6 streams 5.4 M matrices/s (90 GB/s both directions together) -> the default.
 template <class T>
 int geqr_batched_host(T* A, i64 m, i64 n, i64 batch, T* tau) {
   if (m < 0) return -2;
@@ -69,13 +72,16 @@ int geqr_batched_host(T* A, i64 m, i64 n, i64 batch, T* tau) {
   const i64 k = m < n ? m : n;
   const i64 mat_bytes = m * n * (i64)sizeof(T);
   if (mat_bytes > 96 * 1024) return -2;
-  i64 chunk = (64ll << 20) / mat_bytes;
+  static const i64 chunk_mb = [] { const char* e = getenv("GLA_BATCH_CHUNK_MB"); return e ? (i64)atoi(e) : 128ll; }();
+  static const int want_ns = [] { const char* e = getenv("GLA_BATCH_STREAMS"); return e ? atoi(e) : 6; }();
+  i64 chunk = ((chunk_mb > 0 ? chunk_mb : 64) << 20) / mat_bytes;
   if (chunk < 1) chunk = 1;
   if (chunk > batch) chunk = batch;
-  constexpr int NS = 3;
+  constexpr int NS = 8;
   Stream st[NS];
   DevBuf dA[NS], dtau[NS];
-  int ns = (int)((batch + chunk - 1) / chunk < NS ? (batch + chunk - 1) / chunk : NS);
+  const int ns_cap = want_ns < 1 ? 1 : (want_ns > NS ? NS : want_ns);
+  int ns = (int)((batch + chunk - 1) / chunk < ns_cap ? (batch + chunk - 1) / chunk : ns_cap);
   for (int s = 0; s < ns; ++s) {
     GLA_TRY(st[s].create());
     GLA_TRY(dA[s].alloc(chunk * mat_bytes));

@@ -226,7 +226,7 @@ template <class T>
 static int chol_rec(CholCtx<T>& cx, i64 r0, i64 n) {
   if (n <= CB) {
     const int smem = 2 * CB * (CB + 1) * (int)sizeof(T);
-    GLA_CUDA(cudaFuncSetAttribute(potrf_block_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    GLA_TRY(ensure_dyn_smem((const void*)potrf_block_kernel<T>, (int)(smem)));
     potrf_block_kernel<T><<<1, 256, smem, cx.st>>>(cx.W + r0 + r0 * cx.ldw, cx.ldw, (int)n,
                                                    cx.Uinv + (r0 / CB) * CB * CB, cx.info, (int)r0);
     GLA_CUDA(cudaGetLastError());

@@ -163,5 +163,8 @@ inline int ceil_div(i64 a, i64 b) { return (int)((a + b - 1) / b); }
 inline i64 round_up(i64 a, i64 b) { return (a + b - 1) / b * b; }
 
 int sm_count();  // of the current device (cached)
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel, size): the launch paths are host-bound for
+// small problems (hundreds of dependent launches), so the per-launch driver call is worth avoiding
+int ensure_dyn_smem(const void* func, int bytes);
 
 }  // namespace gla

@@ -2,7 +2,9 @@
 // lazily cached device properties).
 #include "common.cuh"
 
+#include <map>
 #include <mutex>
+#include <utility>
 
 namespace gla {
 
@@ -45,6 +47,24 @@ int sm_count() {
     (void)cudaGetLastError();
   }
   return cached[dev];
+}
+
+int ensure_dyn_smem(const void* func, int bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, int> done;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = done.find({dev, func});
+    if (it != done.end() && it->second >= bytes) return 0;
+  }
+  int rc = check_cuda(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes), __FILE__, __LINE__);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(mu);
+  int& v = done[{dev, func}];
+  if (v < bytes) v = bytes;
+  return 0;
 }
 
 }  // namespace gla

@@ -538,7 +538,7 @@ int launch_dmma(const GemmTN<double>& g, int klen, cudaStream_t st) {
   GLA_TRY(make_map(&tmA, g.At, g.K, g.M, g.ldat, BM));
   GLA_TRY(make_map(&tmB, g.B, g.K, g.N, g.ldb, BN));
   auto kern = gemm_tn_dmma_kernel<BM, BN, STAGES>;
-  GLA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+  GLA_TRY(ensure_dyn_smem((const void*)kern, (int)(Cfg::SMEM)));
   dim3 grid((unsigned)ceil_div(g.M, BM), (unsigned)ceil_div(g.N, BN), (unsigned)g.nsplit);
   const int vec_ok = ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0 && (g.ldc & 1) == 0 &&
                       ((g.split_stride & 1) == 0)) ? 1 : 0;
@@ -623,7 +623,7 @@ static int launch_zdmma(const GemmTN<zd>& g, int klen, cudaStream_t st) {
   GLA_TRY(make_map(&tmA, reinterpret_cast<const double*>(g.At), 2 * g.K, g.M, 2 * g.ldat, BM));
   GLA_TRY(make_map(&tmB, reinterpret_cast<const double*>(g.B), 2 * g.K, g.N, 2 * g.ldb, BN));
   auto kern = gemm_tn_zdmma_kernel<BM, BN, STAGES>;
-  GLA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+  GLA_TRY(ensure_dyn_smem((const void*)kern, (int)(Cfg::SMEM)));
   dim3 grid((unsigned)ceil_div(g.M, BM), (unsigned)ceil_div(g.N, BN), (unsigned)g.nsplit);
   kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmA, tmB, g.C, g.ldc, (int)g.M, (int)g.N, (int)(2 * g.K), 2 * klen,
                                               g.split_stride, g.alpha, g.nsplit > 1 ? 0 : g.beta_one, g.conj_a,

@@ -748,8 +748,10 @@ static int launch_panel(T* A, i64 lda, i64 mk, int nb, T* tau, QrWork<T>& w, int
   const i64 smem_cap = 176 * 1024;
   const i64 max_rows = (smem_cap / ((i64)nb * sizeof(T)) - 4) / 16 * 16;  // rows that fit one CTA
   const int sms = sm_count();
-  i64 rows_per = round_up((mk + PANEL_MAX_CTAS - 1) / PANEL_MAX_CTAS, 16);
-  if (rows_per < 64) rows_per = 64;
+  static const int min_rows = [] { const char* e = getenv("GLA_PANEL_MINROWS"); return e ? atoi(e) : 64; }();
+  static const int max_ctas = [] { const char* e = getenv("GLA_PANEL_MAXCTAS"); return e ? atoi(e) : PANEL_MAX_CTAS; }();
+  i64 rows_per = round_up((mk + max_ctas - 1) / max_ctas, 16);
+  if (rows_per < min_rows) rows_per = min_rows;
   int resident = 1;
   if (rows_per > max_rows) {
     rows_per = max_rows;
@@ -764,7 +766,7 @@ static int launch_panel(T* A, i64 lda, i64 mk, int nb, T* tau, QrWork<T>& w, int
   a.lds = (int)(round_up(rows_per, 16) + 4);
   size_t smem = resident ? (size_t)a.lds * nb * sizeof(T) : 0;
   auto kern = qr_panel_kernel<T>;
-  GLA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_cap + 8 * 1024)));
+  GLA_TRY(ensure_dyn_smem((const void*)kern, (int)((int)(smem_cap + 8 * 1024))));
   void* args[] = {&a};
   if (P > 1) {
     GLA_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(P), dim3(PANEL_THREADS), args, smem, st));
@@ -801,7 +803,7 @@ template <class T>
 static int build_T(QrWork<T>& w, const T* Vc, i64 ldvc, i64 mk, int kk, const T* tau, T* Tout, cudaStream_t st) {
   GLA_TRY(gram<T>(w, 0, Vc, ldvc, mk, kk, w.Gs, kk, st));
   const int smem = (2 * NB * (NB + 1) + NB) * (int)sizeof(T);
-  GLA_CUDA(cudaFuncSetAttribute(larft_finish_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  GLA_TRY(ensure_dyn_smem((const void*)larft_finish_kernel<T>, (int)(smem)));
   larft_finish_kernel<T><<<1, 256, smem, st>>>(w.Gs, 0, 1, kk, tau, Tout, NB);
   GLA_CUDA(cudaGetLastError());
   return 0;
@@ -829,7 +831,7 @@ static int apply_panel(QrWork<T>& w, const T* Vc, i64 ldvc, const T* VcT, i64 ld
   }
   GLA_TRY(gemm_tn<T>(g1, st));
   const int smem_t = (NB * (NB + 1) + NB * 33) * (int)sizeof(T);
-  GLA_CUDA(cudaFuncSetAttribute(apply_t_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_t));
+  GLA_TRY(ensure_dyn_smem((const void*)apply_t_kernel<T>, (int)(smem_t)));
   apply_t_kernel<T><<<(unsigned)ceil_div(nA, 32), 256, smem_t, st>>>(w.Wp[0], g1.split_stride, g1.nsplit, kk, nA, Tj, NB,
                                                                       adjoint, w.Z[0]);
   GLA_CUDA(cudaGetLastError());
@@ -863,7 +865,7 @@ static int apply_outer(QrWork<T>& w, int b, i64 mo, int kbig, T* A2, i64 lda, i6
   }
   GLA_TRY(gemm_tn<T>(g1, st));
   const int smem = (kbig * 33 + NB * (NB + 1)) * (int)sizeof(T);
-  GLA_CUDA(cudaFuncSetAttribute(wy_fixup_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  GLA_TRY(ensure_dyn_smem((const void*)wy_fixup_kernel<T>, (int)(smem)));
   wy_fixup_kernel<T><<<(unsigned)ceil_div(nA, 32), 256, smem, st>>>(w.Wp[1], g1.split_stride, g1.nsplit, kbig, nA, w.G[b],
                                                                      NBO, w.Tm[b], NBO, w.Z[1]);
   GLA_CUDA(cudaGetLastError());
