@@ -482,7 +482,8 @@ __global__ void __launch_bounds__(256) larft_finish_kernel(const T* __restrict__
     X[i][j] = (i == j) ? Sc<T>::one() : Sc<T>::zero();
   }
   __syncthreads();
-  // column recurrence X[:,j] = e_j - X[:,0:j] U[0:j,j]; 4 threads share one row i
+  // column recurrence X[:,j] = e_j - X[:,0:j] U[0:j,j]; 4 lanes of ONE warp share row i.  Row i of X depends on
+  // row i only (and on the constant U), so the 63 dependent steps need a warp-level barrier, not a CTA-level one.
   const int i = tid >> 2, part = tid & 3;
   for (int j = 1; j < kk; ++j) {
     T s = Sc<T>::zero();
@@ -492,8 +493,9 @@ __global__ void __launch_bounds__(256) larft_finish_kernel(const T* __restrict__
     s = s + shfl_xor_t<T>(s, 1);
     s = s + shfl_xor_t<T>(s, 2);
     if (i < j && part == 0) X[i][j] = -s;
-    __syncthreads();
+    __syncwarp();
   }
+  __syncthreads();
   for (int e = tid; e < kk * kk; e += blockDim.x) {
     const int j = e / kk, ii = e - j * kk;
     Tm[(i64)j * ldt + ii] = ii <= j ? X[ii][j] * st[j] : Sc<T>::zero();
@@ -830,11 +832,25 @@ static int apply_panel(QrWork<T>& w, const T* Vc, i64 ldvc, const T* VcT, i64 ld
     return GLA_ERR_INTERNAL;
   }
   GLA_TRY(gemm_tn<T>(g1, st));
-  const int smem_t = (NB * (NB + 1) + NB * 33) * (int)sizeof(T);
-  GLA_TRY(ensure_dyn_smem((const void*)apply_t_kernel<T>, (int)(smem_t)));
-  apply_t_kernel<T><<<(unsigned)ceil_div(nA, 32), 256, smem_t, st>>>(w.Wp[0], g1.split_stride, g1.nsplit, kk, nA, Tj, NB,
-                                                                      adjoint, w.Z[0]);
-  GLA_CUDA(cudaGetLastError());
+  static const bool fixup_kernel = getenv("GLA_QR_FIXUP_KERNEL") != nullptr;   // A/B switch: scalar T-apply kernel
+  if (adjoint && !fixup_kernel) {
+    // Z = T_j^H (sum of the split-K slices of W): T_j (column-major, zeros below the diagonal) is the K-contiguous
+    // operand of the TN contraction as it stands
+    if (g1.nsplit > 1) GLA_TRY(sum_splits<T>(w.Wp[0], NB, w.Wp[0], NB, g1.split_stride, g1.nsplit, kk, nA, st));
+    GemmTN<T> gz;
+    gz.At = Tj; gz.ldat = NB;
+    gz.B = w.Wp[0]; gz.ldb = NB;
+    gz.C = w.Z[0]; gz.ldc = NB;
+    gz.M = kk; gz.N = nA; gz.K = kk;
+    gz.conj_a = 1;
+    GLA_TRY(gemm_tn<T>(gz, st));
+  } else {
+    const int smem_t = (NB * (NB + 1) + NB * 33) * (int)sizeof(T);
+    GLA_TRY(ensure_dyn_smem((const void*)apply_t_kernel<T>, (int)(smem_t)));
+    apply_t_kernel<T><<<(unsigned)ceil_div(nA, 32), 256, smem_t, st>>>(w.Wp[0], g1.split_stride, g1.nsplit, kk, nA, Tj,
+                                                                        NB, adjoint, w.Z[0]);
+    GLA_CUDA(cudaGetLastError());
+  }
   GemmTN<T> g2;
   g2.At = VcT; g2.ldat = ldvct;
   g2.B = w.Z[0]; g2.ldb = NB;
@@ -864,11 +880,39 @@ static int apply_outer(QrWork<T>& w, int b, i64 mo, int kbig, T* A2, i64 lda, i6
     return GLA_ERR_INTERNAL;
   }
   GLA_TRY(gemm_tn<T>(g1, st));
-  const int smem = (kbig * 33 + NB * (NB + 1)) * (int)sizeof(T);
-  GLA_TRY(ensure_dyn_smem((const void*)wy_fixup_kernel<T>, (int)(smem)));
-  wy_fixup_kernel<T><<<(unsigned)ceil_div(nA, 32), 256, smem, st>>>(w.Wp[1], g1.split_stride, g1.nsplit, kbig, nA, w.G[b],
-                                                                     NBO, w.Tm[b], NBO, w.Z[1]);
-  GLA_CUDA(cudaGetLastError());
+  static const bool fixup_kernel = getenv("GLA_QR_FIXUP_KERNEL") != nullptr;   // A/B switch: scalar fix-up kernel
+  if (fixup_kernel) {
+    const int smem = (kbig * 33 + NB * (NB + 1)) * (int)sizeof(T);
+    GLA_TRY(ensure_dyn_smem((const void*)wy_fixup_kernel<T>, (int)(smem)));
+    wy_fixup_kernel<T><<<(unsigned)ceil_div(nA, 32), 256, smem, st>>>(w.Wp[1], g1.split_stride, g1.nsplit, kbig, nA,
+                                                                       w.G[b], NBO, w.Tm[b], NBO, w.Z[1]);
+    GLA_CUDA(cudaGetLastError());
+  } else {
+    // the block recurrence  Y_j = W_j - sum_{i<j} G_ji Z_i,  Z_j = T_j^H Y_j  as TN contractions on the tensor pipe:
+    //   G_ji = conj(G(iNB.., jNB..))^T is the K-contiguous operand G + jNB*ldg (G is Hermitian), T_j^H likewise T_j
+    if (g1.nsplit > 1)   // fixed-order sum of the split-K slices, in place into slice 0
+      GLA_TRY(sum_splits<T>(w.Wp[1], NBO, w.Wp[1], NBO, g1.split_stride, g1.nsplit, kbig, nA, st));
+    const int nj = (kbig + NB - 1) / NB;
+    for (int j = 0; j < nj; ++j) {
+      const int rows_j = (kbig - j * NB) < NB ? (kbig - j * NB) : NB;
+      if (j > 0) {
+        GemmTN<T> gy;
+        gy.At = w.G[b] + (i64)j * NB * NBO; gy.ldat = NBO;
+        gy.B = w.Z[1]; gy.ldb = NBO;
+        gy.C = w.Wp[1] + j * NB; gy.ldc = NBO;
+        gy.M = rows_j; gy.N = nA; gy.K = (i64)j * NB;
+        gy.alpha = -1; gy.beta_one = 1; gy.conj_a = 1;
+        GLA_TRY(gemm_tn<T>(gy, st));
+      }
+      GemmTN<T> gz;
+      gz.At = w.Tm[b] + (i64)j * NB * NB; gz.ldat = NB;
+      gz.B = w.Wp[1] + j * NB; gz.ldb = NBO;
+      gz.C = w.Z[1] + j * NB; gz.ldc = NBO;
+      gz.M = rows_j; gz.N = nA; gz.K = rows_j;
+      gz.conj_a = 1;
+      GLA_TRY(gemm_tn<T>(gz, st));
+    }
+  }
   GemmTN<T> g2;
   g2.At = w.VT[b]; g2.ldat = NBO;
   g2.B = w.Z[1]; g2.ldb = NBO;
