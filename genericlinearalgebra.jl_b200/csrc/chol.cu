@@ -15,6 +15,7 @@
 // is then the TN product  Y = (Ud^-1)^H Wd, done in place (one M tile reads exactly the columns it
 // writes).  At the end L = U^H is written back into the lower triangle of A; the strict upper
 // triangle of A is never touched, exactly like the reference.
+#include "fastmath.cuh"
 #include "gemm.cuh"
 #include "gla_internal.cuh"
 
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(256) potrf_block_kernel(T* __restrict__ W, i64
   Row* S = reinterpret_cast<Row*>(smem_raw);  // S[i][j]
   Row* X = S + CB;
   __shared__ T rowbuf[2][CB];
+  __shared__ R dinv[CB];   // 1 / U(j,j)
   const int tid = threadIdx.x;
   const int ty = tid >> 4, tx = tid & 15;
   T s[4][4];
@@ -126,8 +128,11 @@ __global__ void __launch_bounds__(256) potrf_block_kernel(T* __restrict__ W, i64
       bad = j + 1;
       break;
     }
-    const R d = sqrt(piv);
-    const R rd = R(1) / d;
+    // sqrt and reciprocal sqrt from the MUFU seed + FMA refinement (fastmath.cuh): every thread needs both, and the
+    // IEEE sqrt / division subroutines would sit on the critical path of all 64 dependent steps
+    const R rd = Fast<R>::rsqrt(piv);
+    const R d = Fast<R>::sqrt_from_rsqrt(piv, rd);
+    if (tid == 0) dinv[j] = rd;
     T ui[4], uc[4];
 #pragma unroll
     for (int a = 0; a < 4; ++a) ui[a] = cj(scale_real(rb[ty + 16 * a], rd));
@@ -160,16 +165,22 @@ __global__ void __launch_bounds__(256) potrf_block_kernel(T* __restrict__ W, i64
   __syncthreads();
   // inverse of the upper factor, column c by lanes 4c .. 4c+3 of one warp
   const int c = tid >> 2, part = tid & 3;
-  if (c < nb && part == 0) X[c][c] = Sc<T>::from_real(R(1) / re(S[c][c]));
+  if (c < nb && part == 0) X[c][c] = Sc<T>::from_real(dinv[c]);
   __syncwarp();
   for (int i = nb - 2; i >= 0; --i) {
-    T acc = Sc<T>::zero();
+    T acc = Sc<T>::zero(), acc2 = Sc<T>::zero();
     if (c < nb && c > i) {
-      for (int l = i + 1 + part; l <= c; l += 4) acc = fmad(S[i][l], X[l][c], acc);
+      int l = i + 1 + part;
+      for (; l + 4 <= c; l += 8) {   // two independent accumulators hide the LDS -> FMA latency
+        acc = fmad(S[i][l], X[l][c], acc);
+        acc2 = fmad(S[i][l + 4], X[l + 4][c], acc2);
+      }
+      if (l <= c) acc = fmad(S[i][l], X[l][c], acc);
     }
+    acc = acc + acc2;
     acc = acc + shfl_xor_t<T>(acc, 1);
     acc = acc + shfl_xor_t<T>(acc, 2);
-    if (c < nb && c > i && part == 0) X[i][c] = scale_real(-acc, R(1) / re(S[i][i]));
+    if (c < nb && c > i && part == 0) X[i][c] = scale_real(-acc, dinv[i]);
     __syncwarp();
   }
   __syncthreads();
