@@ -9,11 +9,16 @@ for n in [int(x) for x in sys.argv[1:]] or [1024, 4096, 8192]:
     S = X.t() @ X + n * torch.eye(n, device="cuda", dtype=torch.float64)
     dA = S.clone(); info = torch.zeros(1, device="cuda", dtype=torch.int32)
     ts = []
+    import time
     for it in range(5):
         dA.copy_(S)
+        torch.cuda.synchronize()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record(); g.chol_recursive_dev(dA.data_ptr(), n, n, info.data_ptr(), 1, st); e1.record(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e0.record(); g.chol_recursive_dev(dA.data_ptr(), n, n, info.data_ptr(), 1, st); e1.record()
+        t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
         ts.append(e0.elapsed_time(e1))
+        print(f"   it {it}: events {ts[-1]:.2f} ms, host enqueue {1e3*(t1-t0):.2f} ms, wall {1e3*(t2-t0):.2f} ms", flush=True)
     ms = min(ts[1:])
     L = torch.tril(dA.t())
     err = (L @ L.t() - S).norm() / S.norm()
