@@ -591,6 +591,238 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
   }
 }
 
+// ---------------------------------------------------------------------------------- 32x32, left-looking, half tile
+// Same algorithm and lane mapping as batched_qr32_ll_kernel, but only HALF a tile of shared memory per matrix and
+// the pivot column re-read in 16-byte chunks instead of being held in 64 registers: the shared-memory and register
+// footprints per matrix in flight are what bound this latency-bound kernel (24 matrices per SM before).
+//   S (16 padded columns) is, in turn: staging of the left half -> pivot buffer of phase 1 -> staging of the right
+//   half -> the finished left half (read by phase 2, stored to HBM) -> pivot buffer of phase 3 -> staging of the
+//   finished right half.
+template <class R, int K0>
+__device__ __forceinline__ void ll_factor_half_c(R (&a)[32], R* __restrict__ pub, const int c, R& tau_own, R& ixi_own) {
+  using VT = typename Vec16<R>::type;
+  constexpr int V = Vec16<R>::N;
+  constexpr int LD = HwCfg<R>::LD;
+#pragma unroll
+  for (int kk = 0; kk < 16; ++kk) {
+    const int k = K0 + kk;
+    const bool own = c == kk;
+    if (k == 31) {  // length-1 column: still reflected, x1 <- -x1, tau = 2 exactly (tau = 0 for a zero entry)
+      const bool z = a[31] == R(0);
+      tau_own = own ? (z ? R(0) : R(2)) : tau_own;
+      a[31] = (own && !z) ? -a[31] : a[31];
+      continue;
+    }
+    const int k0 = k & ~(V - 1);
+    R* vk = pub + kk * LD;   // column slot kk of the half tile
+    if (own) {
+#pragma unroll
+      for (int i = k0; i < 32; i += V) *reinterpret_cast<VT*>(vk + i) = arr_to_vec(a + i);
+    }
+    __syncwarp();
+    R alpha = R(0);
+    R acc[4] = {R(0), R(0), R(0), R(0)};
+#pragma unroll
+    for (int i = k0; i < 32; i += V) {
+      R y[V];
+      vec_to_arr<R>(*reinterpret_cast<const VT*>(vk + i), y);
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const int r = i + j;
+        if (r == k) alpha = y[j];
+        if (r > k) acc[(r - k) & 3] = fmad(y[j], a[r], acc[(r - k) & 3]);
+      }
+    }
+    const R d = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    const R dk = __shfl_sync(0xffffffffu, d, kk, 16);  // the owner's dot is the tail norm^2
+    const R n2 = fmad(alpha, alpha, dk);
+    const bool zero = n2 == R(0);
+    const R n2s = zero ? R(1) : n2;
+    const R y0 = Seed<R>::rsqrt0(n2s);
+    R g = n2s * y0, hh = R(0.5) * y0;
+    R r = Seed<R>::rcp0(alpha + copysign(g, alpha));
+#pragma unroll
+    for (int it = 0; it < Seed<R>::ITERS; ++it) {
+      const R e = fmad(-g, hh, R(0.5));
+      g = fmad(g, e, g);
+      hh = fmad(hh, e, hh);
+    }
+    const R nu = copysign(g, alpha);
+    const R inv_nu = copysign(hh + hh, alpha);
+    const R xi = alpha + nu;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const R e = fmad(-xi, r, R(1));
+      r = fmad(r, e, r);
+    }
+    const R tq = xi * inv_nu;  // tau = xi / nu
+    const R s = fmad(d, inv_nu, tq * a[k]);
+    const bool right = (c > kk) && !zero;
+    const bool mine = own && !zero;
+    const R nt = right ? -(s * r) : R(0);
+    a[k] = mine ? -nu : (right ? a[k] - s : a[k]);
+    tau_own = mine ? tq : tau_own;
+    ixi_own = mine ? r : ixi_own;
+#pragma unroll
+    for (int i = (k + 1) & ~(V - 1); i < 32; i += V) {
+      R y[V];
+      vec_to_arr<R>(*reinterpret_cast<const VT*>(vk + i), y);
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const int rr = i + j;
+        if (rr > k) a[rr] = fmad(nt, y[j], a[rr]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = K0 + 1; i < 32; ++i) a[i] = (i > K0 + c) ? a[i] * ixi_own : a[i];
+}
+
+template <class R>
+struct Ll2Cfg {
+  static constexpr int V = Vec16<R>::N;
+  static constexpr int LD = HwCfg<R>::LD;
+  static constexpr int HALF = 16 * LD + 16 / sizeof(R);   // +16 B: the two half tiles of a warp sit 4 banks apart
+  static constexpr int PER_WARP = 2 * HALF;
+};
+
+template <class R, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+    batched_qr32_ll2_kernel(R* __restrict__ A, R* __restrict__ tau, i64 batch) {
+  using Cfg = Ll2Cfg<R>;
+  using VT = typename Vec16<R>::type;
+  constexpr int V = Cfg::V;
+  constexpr int LD = Cfg::LD;
+  constexpr int NVH = 512 / V / 32;  // 16-byte vectors per lane per HALF matrix
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int h = lane >> 4, c = lane & 15;
+  R* sm = reinterpret_cast<R*>(smem_raw) + warp * Cfg::PER_WARP;
+  R* S = sm + h * Cfg::HALF;  // half tile of this half-warp's matrix
+
+  // coalesced HBM <-> half tile of matrix m, columns [16*half, 16*half + 16)
+  auto load_half = [&](const R* Ag, int m, int half, bool live) {
+    VT v[NVH];
+#pragma unroll
+    for (int u = 0; u < NVH; ++u)
+      v[u] = live ? __ldcs(reinterpret_cast<const VT*>(Ag + m * 1024 + half * 512) + lane + 32 * u) : VT{};
+#pragma unroll
+    for (int u = 0; u < NVH; ++u) {
+      const int e = (lane + 32 * u) * V;
+      *reinterpret_cast<VT*>(sm + m * Cfg::HALF + (e >> 5) * LD + (e & 31)) = v[u];
+    }
+  };
+  auto store_half = [&](R* Ag, int m, int half, bool live) {
+    if (!live) return;
+#pragma unroll
+    for (int u = 0; u < NVH; ++u) {
+      const int e = (lane + 32 * u) * V;
+      __stcs(reinterpret_cast<VT*>(Ag + m * 1024 + half * 512) + lane + 32 * u,
+             *reinterpret_cast<const VT*>(sm + m * Cfg::HALF + (e >> 5) * LD + (e & 31)));
+    }
+  };
+
+  const i64 npairs = (batch + 1) >> 1;
+  for (i64 pair = (i64)blockIdx.x * WARPS + warp; pair < npairs; pair += (i64)gridDim.x * WARPS) {
+    const i64 mat0 = pair * 2;
+    const bool both = mat0 + 1 < batch;
+    R* Ag = A + mat0 * 1024;
+    {  // pull the pair this warp handles next into L2 while this one is being factorised
+      const i64 nxt = pair + (i64)gridDim.x * WARPS;
+      if (nxt * 2 + 1 < batch) {
+        const char* pn = reinterpret_cast<const char*>(A + nxt * 2048);
+#pragma unroll
+        for (int u = 0; u < (int)(2048 * sizeof(R) / 128 / 32); ++u)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pn + (size_t)(lane + 32 * u) * 128));
+      }
+    }
+    R tau_l = R(0), tau_r = R(0), ixi = R(1);
+    R a[32];
+    // ---- phase 1: left half
+    load_half(Ag, 0, 0, true);
+    load_half(Ag, 1, 0, both);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 32; i += V) vec_to_arr<R>(*reinterpret_cast<const VT*>(S + c * LD + i), a + i);
+    __syncwarp();
+    ll_factor_half_c<R, 0>(a, S, c, tau_l, ixi);
+    __syncwarp();
+    // ---- transition: right half in (through S), finished left half out (through S, where phase 2 reads it)
+    R b[32];
+    load_half(Ag, 0, 1, true);
+    load_half(Ag, 1, 1, both);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 32; i += V) vec_to_arr<R>(*reinterpret_cast<const VT*>(S + c * LD + i), b + i);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 32; i += V) *reinterpret_cast<VT*>(S + c * LD + i) = arr_to_vec(a + i);
+    __syncwarp();
+    store_half(Ag, 0, 0, true);
+    store_half(Ag, 1, 0, both);
+    // ---- phase 2: the 16 reflectors applied to the right half (v_k broadcast from S, tau_k by shuffle)
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const R tk = __shfl_sync(0xffffffffu, tau_l, k, 16);
+      const R* vk = S + k * LD;
+      R acc[4] = {b[k], R(0), R(0), R(0)};
+#pragma unroll
+      for (int i = (k + 1) & ~(V - 1); i < 32; i += V) {
+        R y[V];
+        vec_to_arr<R>(*reinterpret_cast<const VT*>(vk + i), y);
+#pragma unroll
+        for (int j = 0; j < V; ++j)
+          if (i + j > k) acc[(i + j - k) & 3] = fmad(y[j], b[i + j], acc[(i + j - k) & 3]);
+      }
+      const R ns = -(tk * ((acc[0] + acc[1]) + (acc[2] + acc[3])));
+      b[k] += ns;
+#pragma unroll
+      for (int i = (k + 1) & ~(V - 1); i < 32; i += V) {
+        R y[V];
+        vec_to_arr<R>(*reinterpret_cast<const VT*>(vk + i), y);
+#pragma unroll
+        for (int j = 0; j < V; ++j)
+          if (i + j > k) b[i + j] = fmad(ns, y[j], b[i + j]);
+      }
+    }
+    __syncwarp();   // all lanes are done with the left half in S; phase 3 reuses S as its pivot buffer
+    // ---- phase 3: trailing 16 x 16 block of the right half
+    ixi = R(1);
+    ll_factor_half_c<R, 16>(b, S, c, tau_r, ixi);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 32; i += V) *reinterpret_cast<VT*>(S + c * LD + i) = arr_to_vec(b + i);
+    __syncwarp();
+    store_half(Ag, 0, 1, true);
+    store_half(Ag, 1, 1, both);
+    if (both || h == 0) {
+      tau[(mat0 + h) * 32 + c] = tau_l;
+      tau[(mat0 + h) * 32 + 16 + c] = tau_r;
+    }
+    __syncwarp();
+  }
+}
+
+template <class R, int MINB>
+static int launch_ll2_32(R* dA, R* dtau, i64 batch, cudaStream_t st) {
+  constexpr int WARPS = 4;
+  const size_t smem = (size_t)WARPS * Ll2Cfg<R>::PER_WARP * sizeof(R);
+  auto kern = batched_qr32_ll2_kernel<R, WARPS, MINB>;
+  GLA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  GLA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem));
+  if (occ < 1) occ = 1;
+  const i64 npairs = (batch + 1) / 2;
+  const i64 need = (npairs + WARPS - 1) / WARPS;
+  const i64 resident = (i64)sm_count() * occ;
+  const i64 grid = need < resident ? need : resident;   // one resident wave; warps stride over the pairs
+  kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(dA, dtau, batch);
+  GLA_CUDA(cudaGetLastError());
+  return 0;
+}
+
 template <class R>
 static int launch_ll32(R* dA, R* dtau, i64 batch, cudaStream_t st) {
   constexpr int WARPS = 4;
@@ -694,6 +926,9 @@ static int launch_reg32(R* dA, R* dtau, i64 batch, cudaStream_t st) {
   if (variant == 1) return launch_reg32_cfg<R, 4, 168>(dA, dtau, batch, st);
   if (variant == 2) return launch_reg32_cfg<R, 4, 200>(dA, dtau, batch, st);
   if (variant == 3) return launch_hw32<R>(dA, dtau, batch, st);
+  if (variant == 4) return launch_ll2_32<R, 4>(dA, dtau, batch, st);   // half-tile kernel, <= 128 registers
+  if (variant == 5) return launch_ll2_32<R, 5>(dA, dtau, batch, st);   // half-tile kernel, <= 96 registers
+  if (variant == 6) return launch_ll2_32<R, 3>(dA, dtau, batch, st);   // half-tile kernel, <= 168 registers
   return launch_ll32<R>(dA, dtau, batch, st);
 }
 
