@@ -260,7 +260,7 @@ def main():
         "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH * batch / BATCH_PER_GPU,
-                     "kernel": "batched_qr32_ll_kernel<double>", "peak_source": peak_src,
+                     "kernel": "batched_qr32_ll2_kernel<double>", "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": BYTES_PER_MATRIX * batch,
                      "fp64_tflops": FLOPS_PER_MATRIX * batch / (kernel_ms * 1e-3) / 1e12},
         "clocks": clocks,

@@ -918,7 +918,7 @@ static int launch_reg32_cfg(R* dA, R* dtau, i64 batch, cudaStream_t st) {
 
 template <class R>
 static int launch_reg32(R* dA, R* dtau, i64 batch, cudaStream_t st) {
-  // register cap <-> resident warps per SM: 128 -> 16, 112 -> 18, 96 -> 20 (tuning knob, default measured best)
+  // GLA_BATCHED_VARIANT selects the earlier kernels for A/B measurements (default = measured best)
   static const int variant = [] {
     const char* e = getenv("GLA_BATCHED_VARIANT");
     return e ? atoi(e) : 0;
@@ -926,10 +926,10 @@ static int launch_reg32(R* dA, R* dtau, i64 batch, cudaStream_t st) {
   if (variant == 1) return launch_reg32_cfg<R, 4, 168>(dA, dtau, batch, st);
   if (variant == 2) return launch_reg32_cfg<R, 4, 200>(dA, dtau, batch, st);
   if (variant == 3) return launch_hw32<R>(dA, dtau, batch, st);
-  if (variant == 4) return launch_ll2_32<R, 4>(dA, dtau, batch, st);   // half-tile kernel, <= 128 registers
-  if (variant == 5) return launch_ll2_32<R, 5>(dA, dtau, batch, st);   // half-tile kernel, <= 96 registers
-  if (variant == 6) return launch_ll2_32<R, 3>(dA, dtau, batch, st);   // half-tile kernel, <= 168 registers
-  return launch_ll32<R>(dA, dtau, batch, st);
+  if (variant == 4) return launch_ll2_32<R, 4>(dA, dtau, batch, st);   // half-tile kernel, <= 128 registers: 127 M/s (spills)
+  if (variant == 7) return launch_ll32<R>(dA, dtau, batch, st);        // full-tile left-looking kernel: 141 M/s
+  // default: half-tile left-looking kernel at <= 168 registers (3 CTAs of 4 warps per SM): 148 M matrices/s
+  return launch_ll2_32<R, 3>(dA, dtau, batch, st);
 }
 
 template <class T>

@@ -79,13 +79,23 @@ int geqr_batched_host(T* A, i64 m, i64 n, i64 batch, T* tau) {
   if (chunk > batch) chunk = batch;
   constexpr int NS = 8;
   Stream st[NS];
-  DevBuf dA[NS], dtau[NS];
+  // staging buffers from the stream-ordered pool (kept warm between calls, see sm_count()): no cudaMalloc / cudaFree
+  // device synchronisation per call
+  struct PoolBuf {
+    void* p = nullptr;
+    cudaStream_t s = nullptr;
+    ~PoolBuf() {
+      if (p) cudaFreeAsync(p, s);
+    }
+  } dA[NS], dtau[NS];
+  (void)sm_count();
   const int ns_cap = want_ns < 1 ? 1 : (want_ns > NS ? NS : want_ns);
   int ns = (int)((batch + chunk - 1) / chunk < ns_cap ? (batch + chunk - 1) / chunk : ns_cap);
   for (int s = 0; s < ns; ++s) {
     GLA_TRY(st[s].create());
-    GLA_TRY(dA[s].alloc(chunk * mat_bytes));
-    GLA_TRY(dtau[s].alloc(chunk * k * sizeof(T)));
+    dA[s].s = dtau[s].s = st[s].s;
+    GLA_CUDA(cudaMallocAsync(&dA[s].p, chunk * mat_bytes, st[s].s));
+    GLA_CUDA(cudaMallocAsync(&dtau[s].p, chunk * k * sizeof(T), st[s].s));
   }
   i64 done = 0;
   int it = 0;
@@ -95,7 +105,7 @@ int geqr_batched_host(T* A, i64 m, i64 n, i64 batch, T* tau) {
     T* hA = A + done * m * n;
     T* ht = tau + done * k;
     GLA_CUDA(cudaMemcpyAsync(dA[s].p, hA, nb * mat_bytes, cudaMemcpyHostToDevice, st[s].s));
-    GLA_TRY(geqr_batched_dev<T>(dA[s].as<T>(), m, n, nb, dtau[s].as<T>(), st[s].s));
+    GLA_TRY(geqr_batched_dev<T>(static_cast<T*>(dA[s].p), m, n, nb, static_cast<T*>(dtau[s].p), st[s].s));
     GLA_CUDA(cudaMemcpyAsync(hA, dA[s].p, nb * mat_bytes, cudaMemcpyDeviceToHost, st[s].s));
     GLA_CUDA(cudaMemcpyAsync(ht, dtau[s].p, nb * k * sizeof(T), cudaMemcpyDeviceToHost, st[s].s));
     done += nb;

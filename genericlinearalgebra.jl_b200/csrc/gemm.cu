@@ -606,7 +606,12 @@ int gemm_tn<double>(const GemmTN<double>& g, cudaStream_t st) {
   static const bool force_fma = getenv("GLA_DGEMM_FMA") != nullptr;   // A/B switch for profiling
   if (!force_fma && g.K > 0 && tma_ok(g)) {
     // 8 consumer warps (32x32 each) + 1 TMA warp, 4 x 24 KB stages -> two CTAs per SM
-    if (g.M <= 64) return launch_dmma<64, 128, 4>(g, klen, st);
+    if (g.M <= 64) {
+      // a short, wide product (the leaf solves / small updates of the Cholesky recursion) would put a handful of
+      // 64 x 128 tiles on a handful of SMs: 64 x 32 tiles (two warps per CTA) spread it over four times as many
+      if ((i64)ceil_div(g.N, 128) * g.nsplit * 2 < sm_count()) return launch_dmma<64, 32, 4>(g, klen, st);
+      return launch_dmma<64, 128, 4>(g, klen, st);
+    }
     return launch_dmma<128, 64, 4>(g, klen, st);
   }
   return launch_fma<double>(g, klen, st);
