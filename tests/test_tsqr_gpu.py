@@ -69,3 +69,26 @@ def test_tsqr_combine_of_stacked_blocks(gla, oracle, count, n):
     a, b = _normalise(Rh), _normalise(np.triu(ref_f)[:n])
     assert np.array_equal(np.tril(Rh, -1), np.zeros((n, n)))
     assert np.max(np.abs(a - b)) <= 1e-10 * np.max(np.abs(b))
+
+
+def test_tsqr_allreduce_entry_point_single_rank(gla, oracle):
+    """gla_nccl_* + gla_dtsqr_allreduce_dev with a one-rank communicator (the N>1 exchange path of bench.py, minus
+    the peers): local R -> ncclAllGather -> stack reduction must reproduce the single-shot R."""
+    import torch
+    m, n = 50000, 64
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = torch.randn((n, m), generator=g, device="cuda", dtype=torch.float64)   # column-major m x n
+    st = torch.cuda.current_stream().cuda_stream
+    Rloc = torch.zeros((n, n), device="cuda", dtype=torch.float64)
+    stack = torch.zeros((1, n, n), device="cuda", dtype=torch.float64)
+    R = torch.zeros((n, n), device="cuda", dtype=torch.float64)
+    gla.tsqr_local_dev(A.data_ptr(), m, n, m, Rloc.data_ptr(), n, st)
+    comm = gla.TsqrComm(0, 1, lambda raw: raw)
+    try:
+        comm.allreduce_R(Rloc.data_ptr(), n, stack.data_ptr(), R.data_ptr(), n, st)
+        torch.cuda.synchronize()
+    finally:
+        comm.destroy()
+    ref_f, _ = oracle.qr_blocked(np.asfortranarray(A.cpu().numpy().T), 12)
+    a, b = _normalise(R.cpu().numpy().T), _normalise(np.triu(ref_f)[:n])
+    assert np.max(np.abs(a - b)) <= 1e-10 * np.max(np.abs(b))

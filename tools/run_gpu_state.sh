@@ -2,6 +2,7 @@
 set -x
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > gpurun_out/gpu.txt
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 > gpurun_out/pytest_gpu.txt
 cat gpurun_out/pytest_gpu.txt
 timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
