@@ -35,8 +35,8 @@ M = N_ = 32
 BATCH_PER_GPU = 1 << 20
 BYTES_PER_MATRIX = 8192 + 8192 + 256
 FLOPS_PER_MATRIX = 4.0 / 3.0 * 32 ** 3
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch (2^20 matrices), ncu --set full: profiles/r01_ncu_batched_ll_s4.txt
-NCU_DRAM_BYTES_PER_LAUNCH = 8.823852e9 + 8.818534e9
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch (2^20 matrices), ncu --set full: profiles/r01_ncu_batched_ll2_s4.txt
+NCU_DRAM_BYTES_PER_LAUNCH = 9.086275e9 + 8.830338e9
 FP64_TENSOR_PEAK_TFLOPS = 37.08               # measured on this pool: tools/fp64_peak.cu (profiles/fp64_peak_r01.txt)
 
 
