@@ -65,3 +65,55 @@ def test_cholesky_bitwise_reproducible_under_foreign_streams(gla):
             assert ((L @ L.t() - S).norm() / S.norm()).item() < 1e-13
         else:
             assert torch.equal(torch.tril(dA.t()), torch.tril(ref.t()))
+
+
+def _noise(torch, stream, nz, big, rounds=150):
+    with torch.cuda.stream(stream):
+        for k in range(rounds):
+            nz[k & 3].add_(1.0)
+            if k % 40 == 0:
+                torch.mm(big, big)
+
+
+def test_batched_and_tsqr_bitwise_reproducible_under_foreign_streams(gla):
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(11)
+    noise = torch.cuda.Stream(priority=-1)
+    main = torch.cuda.Stream()
+    nz = [torch.zeros(1 << 22, device="cuda") for _ in range(4)]
+    big = torch.zeros((2048, 2048), device="cuda")
+    # batched 32x32
+    batch = 1 << 16
+    src = torch.randn((batch, 32, 32), generator=g, device="cuda", dtype=torch.float64)
+    tau = torch.zeros((batch, 32), device="cuda", dtype=torch.float64)
+    ref = ref_tau = None
+    for _ in range(4):
+        dA = src.clone()
+        torch.cuda.synchronize()
+        with torch.cuda.stream(main):
+            gla.qr_batched_dev(dA.data_ptr(), 32, 32, batch, tau.data_ptr(), main.cuda_stream)
+        _noise(torch, noise, nz, big)
+        torch.cuda.synchronize()
+        if ref is None:
+            ref, ref_tau = dA, tau.clone()
+        else:
+            assert torch.equal(dA, ref) and torch.equal(tau, ref_tau)
+    # TSQR
+    m, n = 1 << 20, 64
+    A = torch.randn((n, m), generator=g, device="cuda", dtype=torch.float64)
+    R = torch.zeros((n, n), device="cuda", dtype=torch.float64)
+    refR = None
+    for _ in range(4):
+        R.zero_()
+        torch.cuda.synchronize()
+        with torch.cuda.stream(main):
+            gla.tsqr_local_dev(A.data_ptr(), m, n, m, R.data_ptr(), n, main.cuda_stream)
+        _noise(torch, noise, nz, big)
+        torch.cuda.synchronize()
+        if refR is None:
+            refR = R.clone()
+            Ru = torch.triu(R.t())
+            G = A @ A.t()
+            assert ((Ru.t() @ Ru - G).abs().amax() / G.abs().amax()).item() < 1e-12
+        else:
+            assert torch.equal(R, refR)
