@@ -4,7 +4,7 @@
 // stdlib reflector!/reflectorApply! call sites :96/:102)  ->  T build (src/qr.jl:64-83, with the conj
 // the reference omits at :72)  ->  trailing update A2 <- (I - V T^H V^H) A2 (src/householder.jl:119-157).
 //
-// GPU structure: panels of NB = 64 columns, grouped four at a time into outer blocks of NBO = 256 whose
+// GPU structure: panels of NB = 64 columns, grouped six at a time into outer blocks of NBO = 384 whose
 // reflectors hit the far trailing matrix in one K = 256 pass (wy_fixup_kernel).  Per panel:
 //   qr_panel_kernel   cooperative, P CTAs each holding a row slab of the panel in shared memory;
 //                     ONE grid-wide reduction per column: every CTA publishes the partial dots
@@ -623,7 +623,7 @@ __global__ void __launch_bounds__(256)
 }
 
 // ------------------------------------------------------------------------------- workspace
-constexpr int NBO = 256;  // outer block: K of the far trailing contractions
+constexpr int NBO = 384;  // outer block: K of the far trailing contractions (measured at n=16384: 256 -> 258.8 ms, 384 -> 254.0 ms, 512 -> 258.3 ms)
 
 // Workspace of one factorisation.  The outer-block state (V, VT, per-panel T, Gram) is DOUBLE BUFFERED by outer
 // block parity and every scratch array exists once per execution path, because the driver overlaps two paths:
