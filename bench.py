@@ -35,8 +35,8 @@ M = N_ = 32
 BATCH_PER_GPU = 1 << 20
 BYTES_PER_MATRIX = 8192 + 8192 + 256
 FLOPS_PER_MATRIX = 4.0 / 3.0 * 32 ** 3
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch (2^20 matrices), ncu --set full: profiles/r01_ncu_batched_ll2_s4.txt
-NCU_DRAM_BYTES_PER_LAUNCH = 9.086275e9 + 8.830338e9
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch (2^20 matrices), ncu --set full: profiles/r01_ncu_batched_ll4_s5.txt
+NCU_DRAM_BYTES_PER_LAUNCH = 8.590219e9 + 8.802413e9
 FP64_TENSOR_PEAK_TFLOPS = 37.08               # measured on this pool: tools/fp64_peak.cu (profiles/fp64_peak_r01.txt)
 
 
@@ -260,7 +260,7 @@ def main():
         "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH * batch / BATCH_PER_GPU,
-                     "kernel": "batched_qr32_ll2_kernel<double>", "peak_source": peak_src,
+                     "kernel": "batched_qr32_ll4_kernel<double>", "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": BYTES_PER_MATRIX * batch,
                      "fp64_tflops": FLOPS_PER_MATRIX * batch / (kernel_ms * 1e-3) / 1e12},
         "clocks": clocks,

@@ -598,10 +598,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 //   S (16 padded columns) is, in turn: staging of the left half -> pivot buffer of phase 1 -> staging of the right
 //   half -> the finished left half (read by phase 2, stored to HBM) -> pivot buffer of phase 3 -> staging of the
 //   finished right half.
-// FAST: a shorter scalar chain per reflector (3 dependent FP64 operations fewer): alpha^2 rides in the owner's dot
-// accumulator, the first Newton step of 1/xi runs on the xi of the first Goldschmidt iterate (2^-40 accurate, enough
-// for a step that only has to reach 2^-40), and s = (d + xi a_k) / nu needs one product after xi instead of two.
-template <class R, int K0, bool FAST = false>
+template <class R, int K0>
 __device__ __forceinline__ void ll_factor_half_c(R (&a)[32], R* __restrict__ pub, const int c, R& tau_own, R& ixi_own) {
   using VT = typename Vec16<R>::type;
   constexpr int V = Vec16<R>::N;
@@ -632,69 +629,34 @@ __device__ __forceinline__ void ll_factor_half_c(R (&a)[32], R* __restrict__ pub
 #pragma unroll
       for (int j = 0; j < V; ++j) {
         const int r = i + j;
-        if (r == k) {
-          alpha = y[j];
-          if (FAST) acc[0] = own ? alpha * alpha : R(0);   // owner: d becomes the full norm^2 (it never uses s)
-        }
+        if (r == k) alpha = y[j];
         if (r > k) acc[(r - k) & 3] = fmad(y[j], a[r], acc[(r - k) & 3]);
       }
     }
     const R d = (acc[0] + acc[1]) + (acc[2] + acc[3]);
     const R dk = __shfl_sync(0xffffffffu, d, kk, 16);  // the owner's dot is the tail norm^2
-    const R n2 = FAST ? dk : fmad(alpha, alpha, dk);
+    const R n2 = fmad(alpha, alpha, dk);
     const bool zero = n2 == R(0);
     const R n2s = zero ? R(1) : n2;
-    R nu, inv_nu, xi, r, tq, s;
-    if (FAST) {
-      const R y0 = Seed<R>::rsqrt0(n2s);
-      R g = n2s * y0, hh = R(0.5) * y0;
-      r = Seed<R>::rcp0(alpha + copysign(g, alpha));
-      {
-        const R e = fmad(-g, hh, R(0.5));
-        g = fmad(g, e, g);
-        hh = fmad(hh, e, hh);
-      }
-      {  // Newton step 1 on the xi of the first iterate
-        const R xi1 = alpha + copysign(g, alpha);
-        const R e = fmad(-xi1, r, R(1));
-        r = fmad(r, e, r);
-      }
+    const R y0 = Seed<R>::rsqrt0(n2s);
+    R g = n2s * y0, hh = R(0.5) * y0;
+    R r = Seed<R>::rcp0(alpha + copysign(g, alpha));
 #pragma unroll
-      for (int it = 1; it < Seed<R>::ITERS; ++it) {
-        const R e = fmad(-g, hh, R(0.5));
-        g = fmad(g, e, g);
-        hh = fmad(hh, e, hh);
-      }
-      nu = copysign(g, alpha);
-      inv_nu = copysign(hh + hh, alpha);
-      xi = alpha + nu;
-      {
-        const R e = fmad(-xi, r, R(1));
-        r = fmad(r, e, r);
-      }
-      tq = xi * inv_nu;                       // tau = xi / nu
-      s = fmad(xi, a[k], d) * inv_nu;         // conj(tau) (a_kc + v^H a_c[k+1:]) = (xi a_kc + d) / nu
-    } else {
-      const R y0 = Seed<R>::rsqrt0(n2s);
-      R g = n2s * y0, hh = R(0.5) * y0;
-      r = Seed<R>::rcp0(alpha + copysign(g, alpha));
-#pragma unroll
-      for (int it = 0; it < Seed<R>::ITERS; ++it) {
-        const R e = fmad(-g, hh, R(0.5));
-        g = fmad(g, e, g);
-        hh = fmad(hh, e, hh);
-      }
-      nu = copysign(g, alpha);
-      inv_nu = copysign(hh + hh, alpha);
-      xi = alpha + nu;
-#pragma unroll
-      for (int it = 0; it < 2; ++it) {
-        const R e = fmad(-xi, r, R(1));
-        r = fmad(r, e, r);
-      }
-      tq = xi * inv_nu;  // tau = xi / nu
-      s = fmad(d, inv_nu, tq * a[k]);
+    for (int it = 0; it < Seed<R>::ITERS; ++it) {
+      const R e = fmad(-g, hh, R(0.5));
+      g = fmad(g, e, g);
+      hh = fmad(hh, e, hh);
     }
+    const R nu = copysign(g, alpha);
+    const R inv_nu = copysign(hh + hh, alpha);
+    const R xi = alpha + nu;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const R e = fmad(-xi, r, R(1));
+      r = fmad(r, e, r);
+    }
+    const R tq = xi * inv_nu;  // tau = xi / nu
+    const R s = fmad(d, inv_nu, tq * a[k]);
     const bool right = (c > kk) && !zero;
     const bool mine = own && !zero;
     const R nt = right ? -(s * r) : R(0);
@@ -728,7 +690,7 @@ struct Ll2Cfg {
 // together and share instruction-cache lines (the body is 2.5x the 32 KB L1.5 instruction cache and `no_instruction`
 // was 18 % of the stall cycles with free-running warps).  Measured, 2^20 matrices: free-running 3 CTAs x 4 warps 151.9,
 // barrier 3 x 4 159.6, 2 x 6 159.2, 1 x 12 167.0 M matrices/s; further barriers before phase 2 and 3: 153-158 (slower).
-template <class R, int WARPS, int SYNC, bool FAST, int STAG = 0>
+template <class R, int WARPS, int SYNC>
 __device__ __forceinline__ void batched_qr32_ll2_body(R* __restrict__ A, R* __restrict__ tau, i64 batch) {
   using Cfg = Ll2Cfg<R>;
   using VT = typename Vec16<R>::type;
@@ -771,11 +733,6 @@ __device__ __forceinline__ void batched_qr32_ll2_body(R* __restrict__ A, R* __re
     const bool any = base + warp < npairs;
     if (SYNC == 0 && !any) break;
     if (SYNC) __syncthreads();
-    if (STAG > 0 && (warp >> 2)) {   // the (up to) three warps of a scheduler leave the barrier STAG cycles apart
-      const long long t0 = clock64();
-      while (clock64() - t0 < (long long)(warp >> 2) * STAG) {
-      }
-    }
     const i64 pair = any ? base + warp : npairs - 1;
     const i64 mat0 = pair * 2;
     const bool both = any && (mat0 + 1 < batch);
@@ -798,7 +755,7 @@ __device__ __forceinline__ void batched_qr32_ll2_body(R* __restrict__ A, R* __re
 #pragma unroll
     for (int i = 0; i < 32; i += V) vec_to_arr<R>(*reinterpret_cast<const VT*>(S + c * LD + i), a + i);
     __syncwarp();
-    ll_factor_half_c<R, 0, FAST>(a, S, c, tau_l, ixi);
+    ll_factor_half_c<R, 0>(a, S, c, tau_l, ixi);
     __syncwarp();
     // ---- transition: right half in (through S), finished left half out (through S, where phase 2 reads it)
     R b[32];
@@ -843,7 +800,7 @@ __device__ __forceinline__ void batched_qr32_ll2_body(R* __restrict__ A, R* __re
     __syncwarp();   // all lanes are done with the left half in S; phase 3 reuses S as its pivot buffer
     // ---- phase 3: trailing 16 x 16 block of the right half
     ixi = R(1);
-    ll_factor_half_c<R, 16, FAST>(b, S, c, tau_r, ixi);
+    ll_factor_half_c<R, 16>(b, S, c, tau_r, ixi);
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < 32; i += V) *reinterpret_cast<VT*>(S + c * LD + i) = arr_to_vec(b + i);
@@ -858,16 +815,16 @@ __device__ __forceinline__ void batched_qr32_ll2_body(R* __restrict__ A, R* __re
   }
 }
 
-template <class R, int WARPS, int MINB, int SYNC = 0, bool FAST = false, int STAG = 0>
+template <class R, int WARPS, int MINB, int SYNC = 0>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
     batched_qr32_ll2_kernel(R* __restrict__ A, R* __restrict__ tau, i64 batch) {
-  batched_qr32_ll2_body<R, WARPS, SYNC, FAST, STAG>(A, tau, batch);
+  batched_qr32_ll2_body<R, WARPS, SYNC>(A, tau, batch);
 }
 
-template <class R, int MINB, int WARPS = 4, int SYNC = 0, bool FAST = false, int STAG = 0>
+template <class R, int MINB, int WARPS = 4, int SYNC = 0>
 static int launch_ll2_32(R* dA, R* dtau, i64 batch, cudaStream_t st) {
   const size_t smem = (size_t)WARPS * Ll2Cfg<R>::PER_WARP * sizeof(R);
-  auto kern = batched_qr32_ll2_kernel<R, WARPS, MINB, SYNC, FAST, STAG>;
+  auto kern = batched_qr32_ll2_kernel<R, WARPS, MINB, SYNC>;
   GLA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
   GLA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem));
@@ -881,98 +838,84 @@ static int launch_ll2_32(R* dA, R* dtau, i64 batch, cudaStream_t st) {
   return 0;
 }
 
-// ---------------------------------------------------------------------------------- 32x32, left-looking, bulk-copy staged
-// Same arithmetic as batched_qr32_ll2_kernel, but HBM <-> shared memory moves by the bulk-copy engine (cp.async.bulk,
-// one 32-element column per lane and copy, into / out of the padded tile) instead of LDG -> STS / LDS -> STG through the
-// register file.  The shared-memory <-> register path (128 B/clk per SM) is what bounds the ll2 kernel: every broadcast
-// LDS.128 of the pivot column returns 512 B to the register file, ~235 KB per pair, plus 64 KB of staging traffic and
-// the 32 KB of global loads / stores through the same pipe -- the staging share is what this variant removes.  A second
-// half tile P per matrix receives the NEXT half (right half during phase 1, left half of the next pair during phases 2
-// and 3), so no HBM latency is exposed.
-//   proxies: P and S are written / read by the async proxy (bulk copies) and by the warps (generic proxy).  Every hand-over
-//   generic -> async is behind fence.proxy.async (after a __syncwarp when other lanes' accesses are involved); async ->
-//   generic goes through the mbarrier (loads) or cp.async.bulk.wait_group.read (stores).  A lane only ever bulk-copies
-//   the column slot it reads / writes itself.
-__device__ __forceinline__ uint32_t bq_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void bq_mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bq_smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void bq_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bq_smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bq_mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}" ::"r"(bq_smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void bq_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   bq_smem_u32(dst)),
-               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bq_smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void bq_bulk_store(void* dst, const void* src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<uint64_t>(dst)),
-               "r"(bq_smem_u32(src)), "r"(bytes)
-               : "memory");
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void bq_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bq_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void bq_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
+// ---------------------------------------------------------------------------------- 32x32, left-looking, cp.async prefetch
+// batched_qr32_ll2_kernel with a second half tile P per matrix that receives the NEXT half by cp.async (LDGSTS, 16 bytes
+// per lane, the same coalesced pattern as the staging loads, no registers): the right half while phase 1 runs, the left
+// half of the warp's next pair while phases 2 and 3 run.  With the warps of a CTA in step (the barrier per pair), the
+// exposed global-load latency at the top of a pair and at the transition was 5 % of the stall samples of the ll2 kernel
+// (ncu source page: the staging STS behind the LDGs), and nobody was left to cover it.
+// STAG: after the barrier warp w waits w * STAG cycles, so the twelve warps walk the body as a train 11 * STAG cycles
+// long instead of in lock step -- short enough to keep sharing instruction-cache lines (at 6000 cycles between the
+// warps of a scheduler the gain of the barrier is gone: 161 M/s), long enough that the warps of a scheduler are not all
+// inside their scalar chains, or all bursting LDS / DFMA, at the same time.  Measured (2^20 matrices, M matrices/s):
+// no stagger 168; warps of a scheduler 750 .. 3000 cycles apart, the four schedulers together: 178-180; every warp
+// 200 / 300 / 375 / 450 / 550 cycles behind its predecessor: 181.5 / 187.5 / 185.6 / 181.7 / 178.2.
 template <class R>
-struct Ll3Cfg {
+struct Ll4Cfg {
   static constexpr int V = Vec16<R>::N;
   static constexpr int LD = HwCfg<R>::LD;
   static constexpr int HALF = Ll2Cfg<R>::HALF;
   static constexpr int PER_WARP = 4 * HALF;   // S (work) and P (incoming) half tiles of both matrices of the pair
-  static constexpr uint32_t COL_BYTES = 32 * sizeof(R);
 };
 
-template <class R, int WARPS, int SYNC>
+template <class R, int WARPS, int SYNC, int STAG>
 __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
-    batched_qr32_ll3_kernel(R* __restrict__ A, R* __restrict__ tau, i64 batch) {
-  using Cfg = Ll3Cfg<R>;
+    batched_qr32_ll4_kernel(R* __restrict__ A, R* __restrict__ tau, i64 batch) {
+  using Cfg = Ll4Cfg<R>;
   using VT = typename Vec16<R>::type;
   constexpr int V = Cfg::V;
   constexpr int LD = Cfg::LD;
+  constexpr int NVH = 512 / V / 32;  // 16-byte vectors per lane per HALF matrix
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int h = lane >> 4, c = lane & 15;
   R* sm = reinterpret_cast<R*>(smem_raw) + warp * Cfg::PER_WARP;
-  R* S = sm + h * Cfg::HALF;                    // work half tile of this half-warp's matrix
-  R* P = sm + (2 + h) * Cfg::HALF;              // incoming half tile
-  uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<R*>(smem_raw) + WARPS * Cfg::PER_WARP) + warp;
-  if (lane == 0) bq_mbar_init(bar, 1);
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  bq_fence_async();
-  __syncthreads();
+  R* S = sm + h * Cfg::HALF;          // work half tile of this half-warp's matrix
+  R* Pw = sm + 2 * Cfg::HALF;         // incoming half tiles of the warp's two matrices
+  R* P = Pw + h * Cfg::HALF;
 
   const i64 npairs = (batch + 1) >> 1;
   const i64 stride = (i64)gridDim.x * WARPS;
-  // columns [16*half, 16*half+16) of both matrices of pair pr -> P (lane c moves column c of its matrix)
-  auto issue_load = [&](i64 pr, int half) {
+  // columns [16*half, 16*half + 16) of both matrices of pair pr -> P, asynchronously (zero fill for a missing matrix)
+  auto prefetch_half = [&](i64 pr, int half) {
     const bool two = pr * 2 + 1 < batch;
-    if (lane == 0) bq_mbar_expect_tx(bar, (two ? 32u : 16u) * Cfg::COL_BYTES);
-    __syncwarp();
-    if (h == 0 || two) bq_bulk_load(P + c * LD, A + (pr * 2 + h) * 1024 + (half * 16 + c) * 32, Cfg::COL_BYTES, bar);
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      const R* src = A + (pr * 2 + ((m == 1 && !two) ? 0 : m)) * 1024 + half * 512;
+      const uint32_t nbytes = (m == 1 && !two) ? 0u : 16u;
+#pragma unroll
+      for (int u = 0; u < NVH; ++u) {
+        const int e = (lane + 32 * u) * V;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(Pw + m * Cfg::HALF + (e >> 5) * LD + (e & 31));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src + e), "r"(nbytes) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  uint32_t ph = 0;
-  if ((i64)blockIdx.x * WARPS + warp < npairs) issue_load((i64)blockIdx.x * WARPS + warp, 0);
+  auto wait_prefetch = [&]() {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+  };
+  auto store_half = [&](R* Ag, int m, int half, bool live) {
+    if (!live) return;
+#pragma unroll
+    for (int u = 0; u < NVH; ++u) {
+      const int e = (lane + 32 * u) * V;
+      __stcs(reinterpret_cast<VT*>(Ag + m * 1024 + half * 512) + lane + 32 * u,
+             *reinterpret_cast<const VT*>(sm + m * Cfg::HALF + (e >> 5) * LD + (e & 31)));
+    }
+  };
 
+  if ((i64)blockIdx.x * WARPS + warp < npairs) prefetch_half((i64)blockIdx.x * WARPS + warp, 0);
   for (i64 base = (i64)blockIdx.x * WARPS; base < npairs; base += stride) {
     if (SYNC) __syncthreads();
+    if (STAG > 0 && warp) {   // warp w leaves the barrier w * STAG cycles after warp 0 (see the note above the kernel)
+      const long long t0 = clock64();
+      while (clock64() - t0 < (long long)warp * STAG) {
+      }
+    }
     const i64 pair = base + warp;
     if (pair >= npairs) {
       if (SYNC) continue;
@@ -980,43 +923,29 @@ __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
     }
     const i64 mat0 = pair * 2;
     const bool both = mat0 + 1 < batch;
-    const bool live = both || h == 0;
-    R* Am = A + (mat0 + h) * 1024;
+    R* Ag = A + mat0 * 1024;
     R tau_l = R(0), tau_r = R(0), ixi = R(1);
     R a[32];
-    // ---- phase 1: left half (arrived in P)
-    bq_mbar_wait(bar, ph);
-    ph ^= 1;
+    // ---- phase 1: left half (prefetched into P)
+    wait_prefetch();
 #pragma unroll
     for (int i = 0; i < 32; i += V) vec_to_arr<R>(*reinterpret_cast<const VT*>(P + c * LD + i), a + i);
-    if (!live) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) a[i] = R(0);
-    }
-    bq_fence_async();     // P[c] read -> may be overwritten by the async proxy
-    __syncwarp();
-    issue_load(pair, 1);  // right half -> P while phase 1 runs
-    bq_bulk_wait_read();  // the previous pair's store of S[c] has left shared memory: S is the pivot buffer again
-    __syncwarp();
+    __syncwarp();              // every lane has its column: P may be refilled
+    prefetch_half(pair, 1);    // right half -> P while phase 1 runs
     ll_factor_half_c<R, 0>(a, S, c, tau_l, ixi);
     __syncwarp();
     // ---- transition: right half from P, finished left half into S (phase 2 reads it there) and out to HBM
     R b[32];
-    bq_mbar_wait(bar, ph);
-    ph ^= 1;
+    wait_prefetch();
 #pragma unroll
     for (int i = 0; i < 32; i += V) {
       vec_to_arr<R>(*reinterpret_cast<const VT*>(P + c * LD + i), b + i);
       *reinterpret_cast<VT*>(S + c * LD + i) = arr_to_vec(a + i);
     }
-    if (!live) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) b[i] = R(0);
-    }
-    bq_fence_async();     // P[c] read, S[c] written
     __syncwarp();
-    if (pair + stride < npairs) issue_load(pair + stride, 0);   // left half of the next pair -> P
-    if (live) bq_bulk_store(Am + c * 32, S + c * LD, Cfg::COL_BYTES);
+    if (pair + stride < npairs) prefetch_half(pair + stride, 0);   // left half of the warp's next pair -> P
+    store_half(Ag, 0, 0, true);
+    store_half(Ag, 1, 0, both);
     // ---- phase 2: the 16 reflectors applied to the right half (v_k broadcast from S, tau_k by shuffle)
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
@@ -1042,28 +971,29 @@ __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
           if (i + j > k) b[i + j] = fmad(ns, y[j], b[i + j]);
       }
     }
-    bq_bulk_wait_read();  // the left half has been read out of S[c]
-    __syncwarp();         // ... by every lane, and all lanes are done with phase 2: S is the pivot buffer again
+    __syncwarp();   // all lanes are done with the left half in S; phase 3 reuses S as its pivot buffer
     // ---- phase 3: trailing 16 x 16 block of the right half
     ixi = R(1);
     ll_factor_half_c<R, 16>(b, S, c, tau_r, ixi);
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < 32; i += V) *reinterpret_cast<VT*>(S + c * LD + i) = arr_to_vec(b + i);
-    bq_fence_async();
-    if (live) {
-      bq_bulk_store(Am + (16 + c) * 32, S + c * LD, Cfg::COL_BYTES);
+    __syncwarp();
+    store_half(Ag, 0, 1, true);
+    store_half(Ag, 1, 1, both);
+    if (both || h == 0) {
       tau[(mat0 + h) * 32 + c] = tau_l;
       tau[(mat0 + h) * 32 + 16 + c] = tau_r;
     }
+    __syncwarp();
   }
-  bq_bulk_wait_all();
+  asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
-template <class R, int WARPS, int SYNC>
-static int launch_ll3_32(R* dA, R* dtau, i64 batch, cudaStream_t st) {
-  const size_t smem = (size_t)WARPS * Ll3Cfg<R>::PER_WARP * sizeof(R) + WARPS * sizeof(uint64_t);
-  auto kern = batched_qr32_ll3_kernel<R, WARPS, SYNC>;
+template <class R, int WARPS, int SYNC, int STAG>
+static int launch_ll4_32(R* dA, R* dtau, i64 batch, cudaStream_t st) {
+  const size_t smem = (size_t)WARPS * Ll4Cfg<R>::PER_WARP * sizeof(R);
+  auto kern = batched_qr32_ll4_kernel<R, WARPS, SYNC, STAG>;
   GLA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
   GLA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem));
@@ -1182,19 +1112,14 @@ static int launch_reg32(R* dA, R* dtau, i64 batch, cudaStream_t st) {
   if (variant == 3) return launch_hw32<R>(dA, dtau, batch, st);
   if (variant == 4) return launch_ll2_32<R, 4>(dA, dtau, batch, st);   // half-tile kernel, <= 128 registers: 127 M/s (spills)
   if (variant == 7) return launch_ll32<R>(dA, dtau, batch, st);        // full-tile left-looking kernel: 141 M/s
-  if (variant == 8) return launch_ll2_32<R, 3, 4, 0>(dA, dtau, batch, st);   // free-running 3 CTAs x 4 warps: 152 M/s
-  if (variant == 10) return launch_ll2_32<R, 3, 4, 1>(dA, dtau, batch, st);  // barrier per pair, 3 CTAs x 4 warps: 160 M/s
-  if (variant == 40) return launch_ll2_32<R, 1, 12, 1, true>(dA, dtau, batch, st);   // default + shorter scalar chain
-  if (variant == 41) return launch_ll2_32<R, 1, 12, 1, false, 120>(dA, dtau, batch, st);
-  if (variant == 42) return launch_ll2_32<R, 1, 12, 1, true, 120>(dA, dtau, batch, st);
-  if (variant == 43) return launch_ll2_32<R, 1, 12, 1, true, 400>(dA, dtau, batch, st);
-  if (variant == 44) return launch_ll2_32<R, 1, 12, 1, true, 1500>(dA, dtau, batch, st);
-  if (variant == 30) return launch_ll3_32<R, 12, 1>(dA, dtau, batch, st);    // bulk-copy staged, 1 CTA x 12 warps, barrier
-  if (variant == 31) return launch_ll3_32<R, 12, 0>(dA, dtau, batch, st);    // ... free-running
-  if (variant == 32) return launch_ll3_32<R, 6, 1>(dA, dtau, batch, st);     // ... 2 CTAs x 6 warps
-  // default: half-tile left-looking kernel, ONE CTA of 12 warps per SM (<= 168 registers) meeting at a barrier before
-  // every pair: 167 M matrices/s
-  return launch_ll2_32<R, 1, 12, 1>(dA, dtau, batch, st);
+  if (variant == 8) return launch_ll2_32<R, 3, 4, 0>(dA, dtau, batch, st);    // half tile, free-running 3 CTAs x 4 warps: 152 M/s
+  if (variant == 9) return launch_ll2_32<R, 1, 12, 1>(dA, dtau, batch, st);   // half tile, 1 CTA x 12 warps, barrier per pair: 167 M/s
+  if (variant == 10) return launch_ll2_32<R, 3, 4, 1>(dA, dtau, batch, st);   // half tile, 3 CTAs x 4 warps, barrier per pair: 160 M/s
+  if (variant == 11) return launch_ll4_32<R, 12, 0, 0>(dA, dtau, batch, st);  // cp.async prefetch, free-running: 172 M/s
+  if (variant == 12) return launch_ll4_32<R, 12, 1, 0>(dA, dtau, batch, st);  // cp.async prefetch, barrier, lock step: 168 M/s
+  // default: half-tile left-looking kernel with cp.async prefetch of the next half, ONE CTA of 12 warps per SM (<= 168
+  // registers) meeting at a barrier before every pair and leaving it 300 cycles apart: 187.5 M matrices/s
+  return launch_ll4_32<R, 12, 1, 300>(dA, dtau, batch, st);
 }
 
 template <class T>
