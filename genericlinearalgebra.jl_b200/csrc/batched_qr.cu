@@ -850,6 +850,9 @@ static int launch_ll2_32(R* dA, R* dtau, i64 batch, cudaStream_t st) {
 // inside their scalar chains, or all bursting LDS / DFMA, at the same time.  Measured (2^20 matrices, M matrices/s):
 // no stagger 168; warps of a scheduler 750 .. 3000 cycles apart, the four schedulers together: 178-180; every warp
 // 200 / 300 / 375 / 450 / 550 cycles behind its predecessor: 181.5 / 187.5 / 185.6 / 181.7 / 178.2.
+// Tried and dropped: interleaved lanes (matrix = lane & 1, column = lane >> 1, so that the two publishing lanes share a
+// quarter-warp): 171 M/s -- a broadcast LDS.128 with two distinct addresses inside every quarter-warp costs more than
+// one address per half-warp.
 template <class R>
 struct Ll4Cfg {
   static constexpr int V = Vec16<R>::N;
@@ -994,10 +997,18 @@ template <class R, int WARPS, int SYNC, int STAG>
 static int launch_ll4_32(R* dA, R* dtau, i64 batch, cudaStream_t st) {
   const size_t smem = (size_t)WARPS * Ll4Cfg<R>::PER_WARP * sizeof(R);
   auto kern = batched_qr32_ll4_kernel<R, WARPS, SYNC, STAG>;
-  GLA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int occ = 0;
-  GLA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem));
-  if (occ < 1) occ = 1;
+  // attribute + occupancy query once per device and instantiation (the host-pointer pipeline launches per chunk)
+  static thread_local int cached_dev = -1, cached_occ = 0;
+  int dev = 0;
+  GLA_CUDA(cudaGetDevice(&dev));
+  if (dev != cached_dev) {
+    GLA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int o = 0;
+    GLA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, WARPS * 32, smem));
+    cached_occ = o < 1 ? 1 : o;
+    cached_dev = dev;
+  }
+  const int occ = cached_occ;
   const i64 npairs = (batch + 1) / 2;
   const i64 need = (npairs + WARPS - 1) / WARPS;
   const i64 resident = (i64)sm_count() * occ;

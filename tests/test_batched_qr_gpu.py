@@ -24,6 +24,24 @@ def test_batched_32x32_matches_oracle(gla, oracle, dtype, tol, batch):
     assert np.all(tau[:, -1] == 2)
 
 
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 2e-4)])
+@pytest.mark.parametrize("batch", [3551, 3553, 7107])
+def test_batched_32x32_wave_boundaries(gla, oracle, dtype, tol, batch):
+    """Ragged batches around the resident wave of the default kernel (148 SMs x 12 warps x 2 matrices = 3552): warps
+    without a pair in the last round, an odd last pair, several rounds with the cp.async prefetch of the next pair."""
+    rng = np.random.default_rng(batch)
+    A = rng.standard_normal((batch, 32, 32)).astype(dtype)
+    A[batch // 2, :, 3] = 0                                   # a zero column somewhere in the middle
+    buf = np.array(np.transpose(A, (0, 2, 1)), order="C", copy=True)
+    ref_f, ref_t = oracle.qr_batched(A, blocksize=12)
+    _, tau = gla.qr_batched_(buf)
+    got = np.transpose(buf, (0, 2, 1))
+    scale = np.max(np.abs(ref_f), axis=(1, 2), keepdims=True)
+    assert np.max(np.abs(got - ref_f) / scale) < tol          # per matrix, not only the global maximum
+    assert _rel(tau, ref_t) < tol
+    assert tau[batch // 2, 3] == 0
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.float32, np.complex128])
 @pytest.mark.parametrize("m,n", [(10, 5), (10, 10), (5, 10), (33, 17), (64, 64), (32, 32), (1, 1), (7, 1), (1, 7)])
 def test_batched_generic_shapes(gla, oracle, dtype, m, n):
