@@ -598,7 +598,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 //   S (16 padded columns) is, in turn: staging of the left half -> pivot buffer of phase 1 -> staging of the right
 //   half -> the finished left half (read by phase 2, stored to HBM) -> pivot buffer of phase 3 -> staging of the
 //   finished right half.
-template <class R, int K0>
+// NACC: accumulators of the dot sweep (2 is 1 % faster than 4 in the staggered kernel and saves two DADD per step; 1 is
+// slower again).  Publishing the pivot column with predicated stores instead of the `if (own)` branch was 7 % SLOWER.
+template <class R, int K0, int NACC = 4>
 __device__ __forceinline__ void ll_factor_half_c(R (&a)[32], R* __restrict__ pub, const int c, R& tau_own, R& ixi_own) {
   using VT = typename Vec16<R>::type;
   constexpr int V = Vec16<R>::N;
@@ -630,10 +632,10 @@ __device__ __forceinline__ void ll_factor_half_c(R (&a)[32], R* __restrict__ pub
       for (int j = 0; j < V; ++j) {
         const int r = i + j;
         if (r == k) alpha = y[j];
-        if (r > k) acc[(r - k) & 3] = fmad(y[j], a[r], acc[(r - k) & 3]);
+        if (r > k) acc[(r - k) & (NACC - 1)] = fmad(y[j], a[r], acc[(r - k) & (NACC - 1)]);
       }
     }
-    const R d = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    const R d = NACC == 4 ? (acc[0] + acc[1]) + (acc[2] + acc[3]) : NACC == 2 ? acc[0] + acc[1] : acc[0];
     const R dk = __shfl_sync(0xffffffffu, d, kk, 16);  // the owner's dot is the tail norm^2
     const R n2 = fmad(alpha, alpha, dk);
     const bool zero = n2 == R(0);
@@ -861,7 +863,7 @@ struct Ll4Cfg {
   static constexpr int PER_WARP = 4 * HALF;   // S (work) and P (incoming) half tiles of both matrices of the pair
 };
 
-template <class R, int WARPS, int SYNC, int STAG>
+template <class R, int WARPS, int SYNC, int STAG, int NACC = 2>
 __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
     batched_qr32_ll4_kernel(R* __restrict__ A, R* __restrict__ tau, i64 batch) {
   using Cfg = Ll4Cfg<R>;
@@ -935,7 +937,7 @@ __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
     for (int i = 0; i < 32; i += V) vec_to_arr<R>(*reinterpret_cast<const VT*>(P + c * LD + i), a + i);
     __syncwarp();              // every lane has its column: P may be refilled
     prefetch_half(pair, 1);    // right half -> P while phase 1 runs
-    ll_factor_half_c<R, 0>(a, S, c, tau_l, ixi);
+    ll_factor_half_c<R, 0, NACC>(a, S, c, tau_l, ixi);
     __syncwarp();
     // ---- transition: right half from P, finished left half into S (phase 2 reads it there) and out to HBM
     R b[32];
@@ -961,9 +963,9 @@ __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
         vec_to_arr<R>(*reinterpret_cast<const VT*>(vk + i), y);
 #pragma unroll
         for (int j = 0; j < V; ++j)
-          if (i + j > k) acc[(i + j - k) & 3] = fmad(y[j], b[i + j], acc[(i + j - k) & 3]);
+          if (i + j > k) acc[(i + j - k) & (NACC - 1)] = fmad(y[j], b[i + j], acc[(i + j - k) & (NACC - 1)]);
       }
-      const R ns = -(tk * ((acc[0] + acc[1]) + (acc[2] + acc[3])));
+      const R ns = -(tk * (NACC == 4 ? (acc[0] + acc[1]) + (acc[2] + acc[3]) : NACC == 2 ? acc[0] + acc[1] : acc[0]));
       b[k] += ns;
 #pragma unroll
       for (int i = (k + 1) & ~(V - 1); i < 32; i += V) {
@@ -977,7 +979,7 @@ __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
     __syncwarp();   // all lanes are done with the left half in S; phase 3 reuses S as its pivot buffer
     // ---- phase 3: trailing 16 x 16 block of the right half
     ixi = R(1);
-    ll_factor_half_c<R, 16>(b, S, c, tau_r, ixi);
+    ll_factor_half_c<R, 16, NACC>(b, S, c, tau_r, ixi);
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < 32; i += V) *reinterpret_cast<VT*>(S + c * LD + i) = arr_to_vec(b + i);
@@ -993,10 +995,10 @@ __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
   asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
-template <class R, int WARPS, int SYNC, int STAG>
+template <class R, int WARPS, int SYNC, int STAG, int NACC = 2>
 static int launch_ll4_32(R* dA, R* dtau, i64 batch, cudaStream_t st) {
   const size_t smem = (size_t)WARPS * Ll4Cfg<R>::PER_WARP * sizeof(R);
-  auto kern = batched_qr32_ll4_kernel<R, WARPS, SYNC, STAG>;
+  auto kern = batched_qr32_ll4_kernel<R, WARPS, SYNC, STAG, NACC>;
   // attribute + occupancy query once per device and instantiation (the host-pointer pipeline launches per chunk)
   static thread_local int cached_dev = -1, cached_occ = 0;
   int dev = 0;
@@ -1128,8 +1130,9 @@ static int launch_reg32(R* dA, R* dtau, i64 batch, cudaStream_t st) {
   if (variant == 10) return launch_ll2_32<R, 3, 4, 1>(dA, dtau, batch, st);   // half tile, 3 CTAs x 4 warps, barrier per pair: 160 M/s
   if (variant == 11) return launch_ll4_32<R, 12, 0, 0>(dA, dtau, batch, st);  // cp.async prefetch, free-running: 172 M/s
   if (variant == 12) return launch_ll4_32<R, 12, 1, 0>(dA, dtau, batch, st);  // cp.async prefetch, barrier, lock step: 168 M/s
+  if (variant == 13) return launch_ll4_32<R, 12, 1, 300, 4>(dA, dtau, batch, st);   // default with four dot accumulators: 187.5 M/s
   // default: half-tile left-looking kernel with cp.async prefetch of the next half, ONE CTA of 12 warps per SM (<= 168
-  // registers) meeting at a barrier before every pair and leaving it 300 cycles apart: 187.5 M matrices/s
+  // registers) meeting at a barrier before every pair and leaving it 300 cycles apart, two dot accumulators: 189-191 M matrices/s
   return launch_ll4_32<R, 12, 1, 300>(dA, dtau, batch, st);
 }
 
