@@ -852,6 +852,7 @@ static int launch_ll2_32(R* dA, R* dtau, i64 batch, cudaStream_t st) {
 // inside their scalar chains, or all bursting LDS / DFMA, at the same time.  Measured (2^20 matrices, M matrices/s):
 // no stagger 168; warps of a scheduler 750 .. 3000 cycles apart, the four schedulers together: 178-180; every warp
 // 200 / 300 / 375 / 450 / 550 cycles behind its predecessor: 181.5 / 187.5 / 185.6 / 181.7 / 178.2.
+// A barrier only every second / fourth pair: 178 / 180 (the train drifts apart).
 // Tried and dropped: interleaved lanes (matrix = lane & 1, column = lane >> 1, so that the two publishing lanes share a
 // quarter-warp): 171 M/s -- a broadcast LDS.128 with two distinct addresses inside every quarter-warp costs more than
 // one address per half-warp.
