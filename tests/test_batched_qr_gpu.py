@@ -28,18 +28,31 @@ def test_batched_32x32_matches_oracle(gla, oracle, dtype, tol, batch):
 @pytest.mark.parametrize("batch", [3551, 3553, 7107])
 def test_batched_32x32_wave_boundaries(gla, oracle, dtype, tol, batch):
     """Ragged batches around the resident wave of the default kernel (148 SMs x 12 warps x 2 matrices = 3552): warps
-    without a pair in the last round, an odd last pair, several rounds with the cp.async prefetch of the next pair."""
+    without a pair in the last round, an odd last pair, several rounds with the cp.async prefetch of the next pair.
+    Checked PER MATRIX.  Householder QR is discontinuous where a pivot is ~0 (nu = copysign(norm, pivot)): in Float32 one
+    of several thousand random matrices has such a pivot and the Float32 oracle itself then lands on the other row sign
+    than the Float64 oracle of the same input (seen: batch 7107, matrix 6883, cond 57).  Those matrices are identified
+    by oracle32-vs-oracle64 disagreement and checked through the sign-independent Gram identity instead."""
     rng = np.random.default_rng(batch)
     A = rng.standard_normal((batch, 32, 32)).astype(dtype)
     A[batch // 2, :, 3] = 0                                   # a zero column somewhere in the middle
     buf = np.array(np.transpose(A, (0, 2, 1)), order="C", copy=True)
     ref_f, ref_t = oracle.qr_batched(A, blocksize=12)
+    ref64_f, _ = oracle.qr_batched(A.astype(np.float64), blocksize=12)
     _, tau = gla.qr_batched_(buf)
     got = np.transpose(buf, (0, 2, 1))
-    scale = np.max(np.abs(ref_f), axis=(1, 2), keepdims=True)
-    assert np.max(np.abs(got - ref_f) / scale) < tol          # per matrix, not only the global maximum
-    assert _rel(tau, ref_t) < tol
+    scale = np.max(np.abs(ref_f), axis=(1, 2))
+    ambiguous = np.max(np.abs(ref_f - ref64_f), axis=(1, 2)) / scale > 1e-3
+    assert ambiguous.sum() <= 2
+    ok = ~ambiguous
+    per_matrix = np.max(np.abs(got - ref_f), axis=(1, 2)) / scale
+    assert per_matrix[ok].max() < tol
+    assert np.max(np.abs(tau[ok] - ref_t[ok])) < tol * 2
     assert tau[batch // 2, 3] == 0
+    for i in np.nonzero(ambiguous)[0]:
+        R = np.triu(got[i].astype(np.float64))
+        M = A[i].astype(np.float64)
+        assert np.max(np.abs(R.T @ R - M.T @ M)) / np.max(np.abs(M.T @ M)) < 1e-4
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32, np.complex128])
