@@ -864,7 +864,7 @@ struct Ll4Cfg {
   static constexpr int PER_WARP = 4 * HALF;   // S (work) and P (incoming) half tiles of both matrices of the pair
 };
 
-template <class R, int WARPS, int SYNC, int STAG, int NACC = 2>
+template <class R, int WARPS, int SYNC, int STAG, int NACC = 2, bool LATE = true>
 __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
     batched_qr32_ll4_kernel(R* __restrict__ A, R* __restrict__ tau, i64 batch) {
   using Cfg = Ll4Cfg<R>;
@@ -950,8 +950,10 @@ __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
     }
     __syncwarp();
     if (pair + stride < npairs) prefetch_half(pair + stride, 0);   // left half of the warp's next pair -> P
-    store_half(Ag, 0, 0, true);
-    store_half(Ag, 1, 0, both);
+    if (!LATE) {
+      store_half(Ag, 0, 0, true);
+      store_half(Ag, 1, 0, both);
+    }
     // ---- phase 2: the 16 reflectors applied to the right half (v_k broadcast from S, tau_k by shuffle)
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
@@ -977,6 +979,11 @@ __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
           if (i + j > k) b[i + j] = fmad(ns, y[j], b[i + j]);
       }
     }
+    if (LATE) {     // the finished left half leaves for HBM after phase 2 (S is read-only until here): spreads the LSU burst
+                    // of the transition (swap + prefetch issue + store): 189.6 -> 194.1 M/s; slice by slice inside phase 2: 193.4
+      store_half(Ag, 0, 0, true);
+      store_half(Ag, 1, 0, both);
+    }
     __syncwarp();   // all lanes are done with the left half in S; phase 3 reuses S as its pivot buffer
     // ---- phase 3: trailing 16 x 16 block of the right half
     ixi = R(1);
@@ -996,10 +1003,10 @@ __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
   asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
-template <class R, int WARPS, int SYNC, int STAG, int NACC = 2>
+template <class R, int WARPS, int SYNC, int STAG, int NACC = 2, bool LATE = true>
 static int launch_ll4_32(R* dA, R* dtau, i64 batch, cudaStream_t st) {
   const size_t smem = (size_t)WARPS * Ll4Cfg<R>::PER_WARP * sizeof(R);
-  auto kern = batched_qr32_ll4_kernel<R, WARPS, SYNC, STAG, NACC>;
+  auto kern = batched_qr32_ll4_kernel<R, WARPS, SYNC, STAG, NACC, LATE>;
   // attribute + occupancy query once per device and instantiation (the host-pointer pipeline launches per chunk)
   static thread_local int cached_dev = -1, cached_occ = 0;
   int dev = 0;
@@ -1131,9 +1138,10 @@ static int launch_reg32(R* dA, R* dtau, i64 batch, cudaStream_t st) {
   if (variant == 10) return launch_ll2_32<R, 3, 4, 1>(dA, dtau, batch, st);   // half tile, 3 CTAs x 4 warps, barrier per pair: 160 M/s
   if (variant == 11) return launch_ll4_32<R, 12, 0, 0>(dA, dtau, batch, st);  // cp.async prefetch, free-running: 172 M/s
   if (variant == 12) return launch_ll4_32<R, 12, 1, 0>(dA, dtau, batch, st);  // cp.async prefetch, barrier, lock step: 168 M/s
-  if (variant == 13) return launch_ll4_32<R, 12, 1, 300, 4>(dA, dtau, batch, st);   // default with four dot accumulators: 187.5 M/s
+  if (variant == 14) return launch_ll4_32<R, 12, 1, 300, 2, false>(dA, dtau, batch, st);   // left half stored at the transition: 189.6 M/s
+  if (variant == 13) return launch_ll4_32<R, 12, 1, 300, 4, false>(dA, dtau, batch, st);   // four dot accumulators, early store: 187.5 M/s
   // default: half-tile left-looking kernel with cp.async prefetch of the next half, ONE CTA of 12 warps per SM (<= 168
-  // registers) meeting at a barrier before every pair and leaving it 300 cycles apart, two dot accumulators: 189-191 M matrices/s
+  // registers) meeting at a barrier before every pair and leaving it 300 cycles apart, two dot accumulators, left half stored after phase 2: 194 M matrices/s
   return launch_ll4_32<R, 12, 1, 300>(dA, dtau, batch, st);
 }
 
