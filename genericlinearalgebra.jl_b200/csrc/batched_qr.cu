@@ -981,6 +981,7 @@ __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
     }
     if (LATE) {     // the finished left half leaves for HBM after phase 2 (S is read-only until here): spreads the LSU burst
                     // of the transition (swap + prefetch issue + store): 189.6 -> 194.1 M/s; slice by slice inside phase 2: 193.4
+                    // (issuing the two prefetches a few reflector steps INSIDE phases 1 and 2 instead: 190.8, slower)
       store_half(Ag, 0, 0, true);
       store_half(Ag, 1, 0, both);
     }
