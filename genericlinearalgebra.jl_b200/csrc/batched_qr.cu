@@ -5,18 +5,18 @@
 //   nu = copysign(||x||, Re x1); x1 <- -nu; x[2:] /= (x1+nu); tau = (x1+nu)/nu  (tau=0 for a zero
 //   column, tau=2 for a length-1 column), trailing columns <- (I - conj(tau) v v^H) * columns.
 //
-// Two kernels:
-//  * batched_qr32_reg_kernel<R>: 32x32 real matrices, ONE MATRIX PER WARP, register resident.
-//    lane c owns column c (32 registers-worth of rows).  HBM -> smem with 128-bit coalesced loads
-//    into a padded (conflict-free) staging tile, smem -> registers, 32 reflector steps where the
-//    pivot column is published once through shared memory (broadcast LDS.128), results go back
-//    through the same staging tile with 128-bit coalesced stores.  The column scaling by 1/xi is
-//    deferred to one pass at the end and folded into the coefficients meanwhile, so each step is
-//    two FMA sweeps (dot, axpy) plus a Goldschmidt sqrt/rsqrt and a Newton reciprocal whose MUFU
-//    seeds issue together.  The kernel is LATENCY bound (32 dependent reflector steps per matrix),
-//    so the register budget (= matrices in flight per SM) is tuned as carefully as the arithmetic.
-//  * batched_qr_smem_kernel<T>: any (m,n) whose matrix fits in shared memory, one CTA per matrix
-//    (also used for ComplexF64).
+// Kernels (the 32x32 real case has a lineage; GLA_BATCHED_VARIANT selects the predecessors for A/B runs, see launch_reg32):
+//  * batched_qr32_ll4_kernel<R, 12, 1, 300, 2, true>  -- DEFAULT for 32x32 Float32/Float64 (195 M matrices/s in Float64):
+//    two matrices per warp (one per half-warp), lane = column, left-looking in two 16-column halves, one padded work
+//    half tile S and one incoming half tile P per matrix, P filled by cp.async with the next half while the current one is
+//    factorised, ONE CTA of 12 warps per SM whose warps meet at a barrier before every pair and leave it 300 cycles apart
+//    (instruction-cache sharing without lock step), two dot accumulators, the finished left half stored after phase 2.
+//  * batched_qr32_ll2_kernel (no prefetch tile: 152-167 M/s), batched_qr32_ll_kernel (full tile per matrix: 141),
+//    batched_qr32_hw_kernel (both columns of a lane pair in registers: 125-132), batched_qr32_reg_kernel (one matrix per
+//    warp: the first design).  All share the reflector conventions above and the deferred 1/xi normalisation; the scalar
+//    chain per reflector is a Goldschmidt sqrt/rsqrt plus a Newton reciprocal whose MUFU seeds issue together.
+//  * batched_qr_smem_kernel<T>: any (m,n) whose matrix fits in shared memory, one CTA per matrix (also ComplexF64).
+// What bounds the default kernel and what was tried is in DESIGN.md section 8 (1) and profiles/r01_s5_sweep_*.txt.
 #include "common.cuh"
 #include "smallqr.cuh"
 #include "fastmath.cuh"
