@@ -1,8 +1,8 @@
 // sweep_batched.cu -- torch-free timing harness for the batched 32x32 Float64 QR entry point (one process = one
 // GLA_BATCHED_VARIANT).  Times gla_dgeqr_batched_dev with CUDA events on fresh input every repetition and dumps the
 // first / last NDUMP matrices (input, factors, tau) so that tools/sweep_check.py can compare variants with the oracle.
-//   nvcc -O2 -gencode arch=compute_100a,code=sm_100a tools/sweep_batched.cu -o tools/sweep_batched \
-//        -Igenericlinearalgebra.jl_b200/../include -Lgenericlinearalgebra.jl_b200/lib -lgla_cuda
+//   make -C tools     (or: nvcc -O2 -gencode arch=compute_100a,code=sm_100a tools/sweep_batched.cu -o tools/sweep_batched \
+//        -Iinclude -Lgenericlinearalgebra.jl_b200/lib -lgla_cuda)
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
