@@ -1153,7 +1153,9 @@ int geqr_batched_dev(T* dA, i64 m, i64 n, i64 batch, T* dtau, cudaStream_t st) {
   if (batch < 0) return -4;
   if (m == 0 || n == 0 || batch == 0) return 0;
   if constexpr (IsReal<T>::v) {
-    if (m == 32 && n == 32) return launch_reg32<T>(dA, dtau, batch, st);
+    // the register kernels move 16-byte vectors (cp.async / LDG.128 / STG.128); a matrix stack that is not 16-byte aligned
+    // (an offset view) goes through the generic shared-memory kernel below, which only uses element accesses
+    if (m == 32 && n == 32 && (reinterpret_cast<uintptr_t>(dA) & 15) == 0) return launch_reg32<T>(dA, dtau, batch, st);
   }
   size_t smem = (size_t)m * n * sizeof(T);
   if (smem > 96 * 1024) return -2;

@@ -111,3 +111,25 @@ def test_batched_full_size_properties(gla):
     assert err.item() < 1e-12
     assert dtau.min().item() >= 1.0 and dtau.max().item() <= 2.0
     assert torch.all(dtau[:, -1] == 2.0)
+
+
+def test_batched_32x32_unaligned_stack(gla, oracle):
+    """A 32x32 stack that starts 8 bytes into an allocation (an offset view on the Julia side) is not 16-byte aligned:
+    the vectorised register kernel must not be used; the result is the same."""
+    import torch
+    batch = 37
+    rng = np.random.default_rng(11)
+    A = rng.standard_normal((batch, 32, 32))
+    ref_f, ref_t = oracle.qr_batched(A, blocksize=12)
+    host = np.ascontiguousarray(np.transpose(A, (0, 2, 1))).reshape(-1)
+    dev = torch.zeros(batch * 1024 + 1, device="cuda", dtype=torch.float64)
+    dev[1:].copy_(torch.from_numpy(host))
+    dtau = torch.zeros(batch * 32 + 1, device="cuda", dtype=torch.float64)
+    ptr = dev.data_ptr() + 8
+    assert ptr % 16 == 8
+    gla.qr_batched_dev(ptr, 32, 32, batch, dtau.data_ptr() + 8, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = np.transpose(dev[1:].cpu().numpy().reshape(batch, 32, 32), (0, 2, 1))
+    assert _rel(got, ref_f) < 1e-12
+    assert _rel(dtau[1:].cpu().numpy().reshape(batch, 32), ref_t) < 1e-12
+    assert dev[0].item() == 0 and dtau[0].item() == 0
