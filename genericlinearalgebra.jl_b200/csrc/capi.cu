@@ -249,9 +249,14 @@ int potrf_host(T* A, i64 n, i64 lda, i64 cutoff) {
   float ms = 0;
   GLA_CUDA(cudaEventElapsedTime(&ms, e0.e, e1.e));
   g_last_ms = ms;
-  if (info != 0) return info;  // leading minor `info` not positive definite: A is left untouched on the host
+  // like the reference (DomainError out of sqrt at src/cholesky.jl:40 with A partially overwritten), a failed call
+  // still returns the partially factorised lower triangle; the index of the minor goes out of band (gla_last_info)
   GLA_TRY(dA.download(A, lda, n, n, st.s));
   GLA_CUDA(cudaStreamSynchronize(st.s));
+  if (info != 0) {
+    g_last_info = info;
+    return GLA_ERR_NOT_POSDEF;
+  }
   return 0;
 }
 
@@ -315,6 +320,7 @@ int gla_set_device(int device) {
 }
 
 double gla_last_device_ms(void) { return g_last_ms; }
+int64_t gla_last_info(void) { return g_last_info; }
 
 // ---- batched
 int gla_sgeqr_batched(float* A, int64_t m, int64_t n, int64_t batch, float* tau) {

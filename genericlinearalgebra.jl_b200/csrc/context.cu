@@ -10,6 +10,7 @@ namespace gla {
 
 static thread_local char g_err[512] = "";
 thread_local double g_last_ms = 0.0;
+thread_local i64 g_last_info = 0;
 
 void set_error(int code, const char* what, const char* file, int line) {
   snprintf(g_err, sizeof(g_err), "gla error %d: %s (%s:%d)", code, what, file, line);

@@ -6,6 +6,7 @@ namespace gla {
 
 const char* last_error();
 extern thread_local double g_last_ms;
+extern thread_local i64 g_last_info;   // 1-based failing minor of the last potrf that returned GLA_ERR_NOT_POSDEF
 
 // K4: batched small QR (batched_qr.cu)
 template <class T>

@@ -15,6 +15,24 @@ namespace gla {
 
 constexpr int SMALLQR_THREADS = 256;
 
+template <class R>
+struct SafeRange;
+template <>
+struct SafeRange<double> {
+  __host__ __device__ static double lo() { return 1e-280; }
+  __host__ __device__ static double hi() { return 1e280; }
+  __host__ __device__ static double fmax() { return 1.7976931348623157e308; }
+};
+template <>
+struct SafeRange<float> {
+  __host__ __device__ static float lo() { return 1e-30f; }
+  __host__ __device__ static float hi() { return 1e30f; }
+  __host__ __device__ static float fmax() { return 3.402823466e38f; }
+};
+__device__ __forceinline__ float absmax_part(float a) { return fabsf(a); }
+__device__ __forceinline__ double absmax_part(double a) { return fabs(a); }
+__device__ __forceinline__ double absmax_part(zd a) { return fmax(fabs(a.x), fabs(a.y)); }
+
 template <class T>
 struct ReflScalars {
   typename Sc<T>::real nu;  // copysign(norm, re(alpha))
@@ -69,19 +87,48 @@ __device__ void cta_qr_smem(T* sA, int m, int n, int ld, T* tau) {
     for (int i = k + 1 + lane; i < m; i += 32) part += abs2(ck[i]);
     part = warp_sum(part);
     const T alpha = ck[k];
-    const R n2 = abs2(alpha) + part;
-    const ReflScalars<T> rs = reflector_scalars<T>(alpha, n2);
+    R n2 = abs2(alpha) + part;
+    // Julia's reflector! uses the scaled norm(x): when the plain sum of squares leaves the safe range (columns around
+    // 1e-160 / 1e160, 1e-20 / 1e20 in Float32) redo it on x * 2^-e and carry the power of two separately (warp-uniform branch)
+    R up = R(1);   // nu, xi are those of the scaled column times `up`
+    if (!(n2 >= SafeRange<R>::lo() && n2 <= SafeRange<R>::hi())) {
+      R amax = absmax_part(alpha);
+      for (int i = k + 1 + lane; i < m; i += 32) amax = fmax(amax, absmax_part(ck[i]));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+      if (amax > R(0) && amax <= SafeRange<R>::fmax()) {
+        int e;
+        (void)frexp(amax, &e);
+        const R sc = ldexp(R(1), -e);
+        up = ldexp(R(1), e);
+        R p2 = R(0);
+        for (int i = k + 1 + lane; i < m; i += 32) p2 += abs2(scale_real(ck[i], sc));
+        p2 = warp_sum(p2);
+        n2 = abs2(scale_real(alpha, sc)) + p2;
+      }
+    }
+    ReflScalars<T> rs = reflector_scalars<T>(up == R(1) ? alpha : scale_real(alpha, R(1) / up), n2);
+    if (up != R(1)) {   // back to the unscaled column: nu * 2^e, 1/xi * 2^-e; tau is scale free
+      rs.nu *= up;
+      rs.ixi = scale_real(rs.ixi, R(1) / up);
+    }
     prev_nonzero = rs.nonzero;
     prev_ixi = rs.ixi;
     prev_nu = rs.nu;
     if (tau && threadIdx.x == 0) tau[k] = rs.tau;
     if (rs.nonzero) {
       const T ctau = cj(rs.tau);
-      const T cixi = cj(rs.ixi);
+      // rescaled column: the dot runs on x * 2^-e (no overflow of x_i * c_i) against 1/xi of the scaled column
+      const R isup = R(1) / up;
+      const T cixi = cj(up == R(1) ? rs.ixi : scale_real(rs.ixi, up));
       for (int c = k + 1 + warp; c < n; c += nwarps) {
         T* cc = sA + c * ld;
         T d = Sc<T>::zero();
-        for (int i = k + 1 + lane; i < m; i += 32) d = fmad(cj(ck[i]), cc[i], d);
+        if (up == R(1)) {
+          for (int i = k + 1 + lane; i < m; i += 32) d = fmad(cj(ck[i]), cc[i], d);
+        } else {
+          for (int i = k + 1 + lane; i < m; i += 32) d = fmad(cj(scale_real(ck[i], isup)), cc[i], d);
+        }
         d = warp_sum(d);
         const T s = ctau * (cc[k] + cixi * d);
         const T t = s * rs.ixi;

@@ -41,6 +41,9 @@ class ArgumentError(ValueError):
     """Julia's ArgumentError."""
 
 
+GLA_ERR_NOT_POSDEF = 900
+
+
 class DomainError(ArithmeticError):
     """Julia's DomainError (sqrt of a negative pivot inside cholRecursive!)."""
 
@@ -60,6 +63,7 @@ def lib():
         _LIB = C.CDLL(LIB_PATH)
         _LIB.gla_last_error_string.restype = C.c_char_p
         _LIB.gla_last_device_ms.restype = C.c_double
+        _LIB.gla_last_info.restype = C.c_int64
     return _LIB
 
 
@@ -70,7 +74,10 @@ def _check(rc, what, neg=DimensionMismatch):
         raise GLACudaError(f"{what}: {lib().gla_last_error_string().decode()}")
     if rc < 0:
         raise neg(f"{what}: argument {-rc} is illegal")
-    raise DomainError(f"{what}: leading minor {rc} is not positive definite (sqrt of a non-positive pivot)")
+    if rc == GLA_ERR_NOT_POSDEF:
+        k = int(lib().gla_last_info())
+        raise DomainError(f"{what}: leading minor {k} is not positive definite (sqrt of a non-positive pivot)", k)
+    raise GLACudaError(f"{what}: unexpected return code {rc}")
 
 
 def _fn(name, dtype):

@@ -32,14 +32,19 @@ end
 
 last_error() = unsafe_string(ccall((:gla_last_error_string, libgla), Cstring, ()))
 
-# return-code convention of include/gla_cuda.h: 0 ok, -k illegal argument k, +k (potrf) minor k not
-# positive definite, >= 1000 CUDA/NCCL runtime failure
-function chk(rc::Cint, what::AbstractString; posdef::Bool = false)
+# return-code convention of include/gla_cuda.h: 0 ok, -k illegal argument k, GLA_ERR_NOT_POSDEF (900) from potrf
+# with the failing minor out of band in gla_last_info(), >= 1000 CUDA/NCCL runtime failure
+const GLA_ERR_NOT_POSDEF = Cint(900)
+last_info() = ccall((:gla_last_info, libgla), Int64, ())
+function chk(rc::Cint, what::AbstractString)
     rc == 0 && return nothing
     rc >= 1000 && throw(GLACudaError(rc, "$what: $(last_error())"))
     rc < 0 && throw(DimensionMismatch("$what: argument $(-rc) is illegal"))
-    # the reference fails with DomainError from sqrt of a negative real (src/cholesky.jl:40)
-    posdef && throw(DomainError(rc, "$what: leading minor $rc is not positive definite"))
+    if rc == GLA_ERR_NOT_POSDEF
+        # the reference fails with DomainError from sqrt of a negative real (src/cholesky.jl:40)
+        k = last_info()
+        throw(DomainError(k, "$what: leading minor $k is not positive definite"))
+    end
     throw(GLACudaError(rc, what))
 end
 
@@ -136,7 +141,7 @@ for T in (Float32, Float64, ComplexF64)
             rc = GC.@preserve A ccall(
                 ($(QuoteNode(potrf)), libgla), Cint,
                 (Ptr{$T}, Int64, Int64, Int64), A, n, max(1, stride(A, 2)), cutoff)
-            chk(rc, "cholRecursive!"; posdef = true)
+            chk(rc, "cholRecursive!")
             return LowerTriangular(A)
         end
 

@@ -20,9 +20,18 @@
  *    `_dev` twins take DEVICE pointers plus a cudaStream_t (passed as void*) and are
  *    asynchronous on that stream;
  *  - return value: 0 ok; -k = k-th argument illegal (shim throws DimensionMismatch /
- *    ArgumentError); +k from potrf = leading minor k not positive definite (shim throws
- *    DomainError, like sqrt of a negative real at src/cholesky.jl:40); >= 1000 = CUDA/NCCL
+ *    ArgumentError); GLA_ERR_NOT_POSDEF (900) from potrf = a leading minor is not positive
+ *    definite, its 1-based index is returned OUT OF BAND by gla_last_info() (shim throws
+ *    DomainError, like sqrt of a negative real at src/cholesky.jl:40; the index can exceed any
+ *    fixed code range, so it is never folded into the return value); >= 1000 = CUDA/NCCL
  *    runtime failure, text via gla_last_error_string().
+ *  - magnitude range: the generic small-matrix QR kernel (batched shapes other than real
+ *    32x32, ComplexF64, TSQR tree nodes) takes the scaled column norm like Julia's norm(x)
+ *    (columns around 1e-160 / 1e160, 1e-20 / 1e20 in Float32, are rescaled by an exact power
+ *    of two).  The 32x32 register kernel of the batched QR, the panel kernel of the blocked QR
+ *    and the TSQR streaming kernel square the entries unscaled: every column (and column tail)
+ *    must satisfy 1e-140 < ||x|| < 1e140 (1e-15 .. 1e15 in Float32) or be exactly zero; outside
+ *    that range scale the matrix by a power of two first (R scales with it, V and tau do not).
  *  - there is NO CPU fallback anywhere in this library.
  */
 #ifndef GLA_CUDA_H
@@ -40,6 +49,7 @@ extern "C" {
 #define GLA_API
 #endif
 
+#define GLA_ERR_NOT_POSDEF 900
 #define GLA_ERR_CUDA 1000
 #define GLA_ERR_NCCL 2000
 
@@ -48,6 +58,8 @@ GLA_API int gla_version(void);                       /* 100*major + minor */
 GLA_API int gla_device_count(void);                  /* number of visible CUDA devices, <0 on error */
 GLA_API const char* gla_last_error_string(void);     /* thread-local text of the last >=1000 error */
 GLA_API int gla_set_device(int device);              /* device used by host-pointer entry points */
+/* thread-local detail of the last GLA_ERR_NOT_POSDEF: 1-based index of the leading minor that failed */
+GLA_API int64_t gla_last_info(void);
 /* average device time (ms) of the compute part of the last host-pointer call on this thread */
 GLA_API double gla_last_device_ms(void);
 

@@ -25,6 +25,7 @@
 #include <cstring>
 #include <vector>
 #include <algorithm>
+#include <omp.h>
 
 namespace {
 
@@ -43,6 +44,9 @@ inline double re(zd x) { return x.real(); }
 inline float abs2(float x) { return x * x; }
 inline double abs2(double x) { return x * x; }
 inline double abs2(zd x) { return x.real() * x.real() + x.imag() * x.imag(); }
+inline float absmax_part(float x) { return std::fabs(x); }
+inline double absmax_part(double x) { return std::fabs(x); }
+inline double absmax_part(zd x) { return std::max(std::fabs(x.real()), std::fabs(x.imag())); }
 
 // ---------------------------------------------------------------------------------
 // Julia stdlib LinearAlgebra.reflector!(x)          call site: src/qr.jl:96
@@ -59,6 +63,22 @@ T reflector(T* x, i64 n) {
   R ss = 0;
   for (i64 i = 0; i < n; ++i) ss += abs2(x[i]);
   R nrm = std::sqrt(ss);
+  // Julia >= 1.9 calls norm(x), which rescales when the plain sum of squares leaves the safe range; restated as:
+  // outside [tiny, huge] redo the sum on x / 2^e with 2^e ~ max|x_i| (an exact power of two, so in-range data are
+  // bitwise unaffected and scaled data give exactly the scaled result).
+  const R tiny = sizeof(R) == 8 ? R(1e-280) : R(1e-30), huge = sizeof(R) == 8 ? R(1e280) : R(1e30);
+  if (!(ss >= tiny && ss <= huge)) {
+    R amax = 0;
+    for (i64 i = 0; i < n; ++i) amax = std::max(amax, absmax_part(x[i]));
+    if (amax > 0 && std::isfinite(amax)) {
+      int e;
+      (void)std::frexp(amax, &e);
+      const R sc = std::ldexp(R(1), -e);
+      R s2 = 0;
+      for (i64 i = 0; i < n; ++i) s2 += abs2(x[i] * sc);
+      nrm = std::ldexp(std::sqrt(s2), e);
+    }
+  }
   if (nrm == R(0)) return T(0);
   R nu = std::copysign(nrm, re(xi));
   xi += nu;
@@ -401,4 +421,7 @@ DEFINE_TYPE(s, float, float)
 DEFINE_TYPE(d, double, double)
 DEFINE_TYPE(z, zd, double)
 
-ORACLE_API int oracle_version() { return 1; }
+ORACLE_API int oracle_version() { return 2; }
+// OpenMP team size actually in effect (bench.py reports it; torchrun exports OMP_NUM_THREADS=1, which bench.py overrides)
+ORACLE_API int oracle_max_threads() { return omp_get_max_threads(); }
+ORACLE_API void oracle_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }

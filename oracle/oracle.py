@@ -38,6 +38,15 @@ def lib():
     return _LIB
 
 
+def max_threads() -> int:
+    """OpenMP team size the oracle's parallel loops will use."""
+    return int(lib().oracle_max_threads())
+
+
+def set_threads(n: int) -> None:
+    lib().oracle_set_threads(C.c_int(int(n)))
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 

@@ -9,7 +9,7 @@ def _rel(a, b):
     return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
 
 
-@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 2e-4)])
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 1e-4)])   # north_star tolerances
 @pytest.mark.parametrize("batch", [1, 5, 1000])
 def test_batched_32x32_matches_oracle(gla, oracle, dtype, tol, batch):
     rng = np.random.default_rng(123 + batch)
@@ -24,7 +24,7 @@ def test_batched_32x32_matches_oracle(gla, oracle, dtype, tol, batch):
     assert np.all(tau[:, -1] == 2)
 
 
-@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 2e-4)])
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 1e-4)])
 @pytest.mark.parametrize("batch", [3551, 3553, 7107])
 def test_batched_32x32_wave_boundaries(gla, oracle, dtype, tol, batch):
     """Ragged batches around the resident wave of the default kernel (148 SMs x 12 warps x 2 matrices = 3552): warps
@@ -71,7 +71,7 @@ def test_batched_generic_shapes(gla, oracle, dtype, m, n):
     ref_f, ref_t = oracle.qr_batched(A, blocksize=max(m, n) + 1)
     _, tau = gla.qr_batched_(buf)
     got = np.transpose(buf, (0, 2, 1))
-    tol = 2e-4 if dtype == np.float32 else 1e-12
+    tol = 1e-4 if dtype == np.float32 else 1e-12
     assert _rel(got, ref_f) < tol
     assert _rel(tau, ref_t) < tol
 
@@ -133,3 +133,33 @@ def test_batched_32x32_unaligned_stack(gla, oracle):
     assert _rel(got, ref_f) < 1e-12
     assert _rel(dtau[1:].cpu().numpy().reshape(batch, 32), ref_t) < 1e-12
     assert dev[0].item() == 0 and dtau[0].item() == 0
+
+
+@pytest.mark.parametrize("dtype,shift", [(np.float64, 530), (np.float64, -530), (np.float32, 70), (np.float32, -70)])
+@pytest.mark.parametrize("shape", [(33, 32), (20, 9)])
+def test_batched_extreme_scaling(gla, oracle, dtype, shift, shape):
+    """Julia's reflector! takes the scaled norm(x) (call site src/qr.jl:96), so a matrix scaled by 2^+-530 (2^+-70 in
+    Float32) factorises to EXACTLY the scaled R with bitwise identical reflectors and taus; an unscaled sum of squares
+    would under- / overflow there.  Covered: the generic shared-memory kernel (every shape but real 32x32; the 32x32
+    register kernel documents its magnitude range in include/gla_cuda.h instead).  One matrix of the batch keeps its
+    natural scale and one has a single badly scaled column."""
+    m, n = shape
+    rng = np.random.default_rng(abs(shift) + m)
+    A = rng.standard_normal((6, m, n)).astype(dtype)
+    S = A.copy()
+    S[:4] = np.ldexp(S[:4], shift).astype(dtype)
+    S[4, :, n // 2] = np.ldexp(S[4, :, n // 2], shift).astype(dtype)
+    assert np.all(np.isfinite(S))
+    buf = np.array(np.transpose(S, (0, 2, 1)), order="C", copy=True)
+    ref_f, ref_t = oracle.qr_batched(S, blocksize=max(m, n) + 1)
+    base_f, base_t = oracle.qr_batched(A, blocksize=max(m, n) + 1)
+    _, tau = gla.qr_batched_(buf)
+    got = np.transpose(buf, (0, 2, 1))
+    assert np.all(np.isfinite(got)) and np.all(np.isfinite(tau))
+    tol = 1e-4 if dtype == np.float32 else 1e-12
+    for b in range(6):
+        sc = np.max(np.abs(ref_f[b]))
+        assert np.max(np.abs(got[b] - ref_f[b])) <= tol * sc
+    assert np.max(np.abs(tau - ref_t)) <= tol
+    # the oracle itself: scaling by a power of two only scales R
+    assert np.array_equal(np.tril(ref_f[0], -1), np.tril(base_f[0], -1)) and np.array_equal(ref_t[0], base_t[0])

@@ -58,6 +58,14 @@ def test_not_positive_definite_raises_domain_error(gla):
     with pytest.raises(gla.DomainError) as ei:
         gla.cholRecursive_(A)
     assert "71" in str(ei.value)
+    # a failing minor beyond 1000 must not collide with the >= 1000 CUDA/NCCL code range of the ABI: the index travels out
+    # of band (gla_last_info); and like the reference (src/cholesky.jl:40) the call leaves A partially factorised
+    B = np.asfortranarray(np.eye(2304) * 4.0)
+    B[1500, 1500] = -1.0
+    with pytest.raises(gla.DomainError) as ei:
+        gla.cholRecursive_(B)
+    assert ei.value.args[1] == 1501 and "1501" in str(ei.value)
+    assert B[0, 0] == 2.0 and np.array_equal(np.triu(B, 1), np.zeros_like(B))
     with pytest.raises(gla.DimensionMismatch):
         gla.cholRecursive_(np.zeros((3, 4), order="F"))
 
