@@ -19,6 +19,8 @@
 #include "gemm.cuh"
 #include "gla_internal.cuh"
 
+#include <stdlib.h>
+
 namespace gla {
 
 constexpr int CB = 64;  // diagonal block
@@ -190,6 +192,214 @@ __global__ void __launch_bounds__(256) potrf_block_kernel(T* __restrict__ W, i64
   }
 }
 
+// ------------------------------------------------------------------------------- fused row-panel kernel (real types)
+// Right-looking step for the row panel U(r : r+nb, r : n) of the mirror (nb <= 64).  The 64 x 64 diagonal block is the
+// sequential part of the whole factorisation (4096 dependent column steps at n = 4096), so it must not also pay kernel
+// boundaries: EVERY CTA of the launch factorises and inverts the diagonal block redundantly (same arithmetic, so bitwise
+// the same factor; no inter-CTA synchronisation) and then solves ITS OWN 32-column slice of the row panel,
+//     Y = U_D^-H * W(r : r+nb, slice)            (rdiv!, src/cholesky.jl:48, as a product with the explicit inverse).
+// kpend > 0: the panel has not yet received the update of the previous panel of its outer block (rows rp : rp+kpend):
+//     W(r : r+nb, r : n) -= U(rp : rp+kpend, r : r+nb)^H * U(rp : rp+kpend, r : n)     (rankUpdate!, :51, K = 64)
+// is applied first, to the diagonal block by every CTA and to the slice by its owner.  The factor of the diagonal block
+// goes to a scratch copy (Ud), not into W: other CTAs of the same launch may still be reading the block.
+//   inverse: recursive doubling, X12 = -X11 U12 X22 for blocks of 1, 2, 4 .. 32 (12 barriers, all threads busy) instead of
+//   63 dependent back-substitution steps.
+constexpr int SW = 32;  // slice width
+
+template <class T>
+struct PanelSmem {
+  using R = typename Sc<T>::real;
+  T S[CB][CB + 1];     // U_D, S[i][c]
+  T X[CB][CB + 1];     // U_D^-1 (upper); the strict lower triangle is scratch of the doubling steps
+  T P[CB][CB + 1];     // pending operand U(rp + k, r + c) as P[k][c]
+  T Ys[CB][SW + 1];    // slice of the row panel
+  T Ps[CB][SW + 1];    // pending operand of the slice
+  T rowbuf[2][CB];
+  R dinv[CB];
+};
+
+// upper Cholesky of the block held in registers: thread (ty, tx) of a 16 x 16 grid owns the cyclic 4 x 4 sub-grid
+// S(ty + 16a, tx + 16b).  Returns 0 or (index of the non-positive pivot) + 1 (uniform over the CTA).
+template <class T>
+__device__ __forceinline__ int factor_block_regs(T (&s)[4][4], const int nb, T (*rowbuf)[CB], typename Sc<T>::real* dinv) {
+  using R = typename Sc<T>::real;
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+  for (int j = 0; j < nb; ++j) {
+    T* rb = rowbuf[j & 1];
+    if (ty == (j & 15)) {
+      const int ja = j >> 4;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const T v01 = ja == 0 ? s[0][b] : s[1][b];
+        const T v23 = ja == 2 ? s[2][b] : s[3][b];
+        rb[tx + 16 * b] = ja < 2 ? v01 : v23;
+      }
+    }
+    __syncthreads();
+    const R piv = re(rb[j]);
+    if (!(piv > R(0))) return j + 1;  // uniform: every thread reads the same pivot
+    const R rd = Fast<R>::rsqrt(piv);
+    const R d = Fast<R>::sqrt_from_rsqrt(piv, rd);
+    if (tid == 0) dinv[j] = rd;
+    T ui[4], uc[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) ui[a] = cj(scale_real(rb[ty + 16 * a], rd));
+#pragma unroll
+    for (int b = 0; b < 4; ++b) uc[b] = scale_real(rb[tx + 16 * b], rd);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int i = ty + 16 * a;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int c = tx + 16 * b;
+        if (i > j && c >= i) s[a][b] = s[a][b] - ui[a] * uc[b];                   // trailing upper triangle
+        else if (i == j && c >= j) s[a][b] = c == j ? Sc<T>::from_real(d) : uc[b];  // row j of the factor
+      }
+    }
+  }
+  return 0;
+}
+
+template <class T>
+__global__ void __launch_bounds__(256) chol_panel_kernel(T* __restrict__ W, i64 ldw, int n, int r, int nb, int rp, int kpend,
+                                                         T* __restrict__ Ud, int* __restrict__ info) {
+  using R = typename Sc<T>::real;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PanelSmem<T>& sm = *reinterpret_cast<PanelSmem<T>*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+  const int c0 = r + nb + SW * blockIdx.x;            // first column of this CTA's slice
+  const int sw = min(SW, n - c0);                     // <= 0: no slice (the panel is the last one)
+  // ---- loads: diagonal block (registers; identity padding beyond nb), pending operands, slice
+  T s[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int i = ty + 16 * a, c = tx + 16 * b;
+      s[a][b] = (i <= c && c < nb) ? W[(i64)(r + c) * ldw + r + i] : ((i == c && i >= nb) ? Sc<T>::one() : Sc<T>::zero());
+    }
+  for (int e = tid; e < CB * CB; e += 256) {
+    const int k = e & (CB - 1), c = e >> 6;
+    sm.P[k][c] = (k < kpend && c < nb) ? W[(i64)(r + c) * ldw + rp + k] : Sc<T>::zero();
+  }
+  for (int e = tid; e < CB * SW; e += 256) {
+    const int k = e & (CB - 1), c = e >> 6;
+    const bool in = c < sw;
+    sm.Ys[k][c] = (in && k < nb) ? W[(i64)(c0 + c) * ldw + r + k] : Sc<T>::zero();
+    sm.Ps[k][c] = (in && k < kpend) ? W[(i64)(c0 + c) * ldw + rp + k] : Sc<T>::zero();
+  }
+  __syncthreads();
+  // ---- pending rank-kpend update: diagonal block (upper 16 x 16 sub-blocks only) and slice
+  T ys[4][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) ys[a][b] = sm.Ys[ty + 16 * a][tx + 16 * b];
+  if (kpend > 0) {
+    for (int k = 0; k < kpend; ++k) {
+      T ui[4], uc[4], us[2];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) ui[a] = cj(sm.P[k][ty + 16 * a]);
+#pragma unroll
+      for (int b = 0; b < 4; ++b) uc[b] = sm.P[k][tx + 16 * b];
+#pragma unroll
+      for (int b = 0; b < 2; ++b) us[b] = sm.Ps[k][tx + 16 * b];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          if (a <= b) s[a][b] = s[a][b] - ui[a] * uc[b];
+#pragma unroll
+        for (int b = 0; b < 2; ++b) ys[a][b] = ys[a][b] - ui[a] * us[b];
+      }
+    }
+  }
+  // ---- factorisation of the diagonal block (registers), redundantly in every CTA
+  const int bad = factor_block_regs<T>(s, nb, sm.rowbuf, sm.dinv);
+  if (bad) {
+    if (blockIdx.x == 0 && tid == 0) atomicCAS(info, 0, r + bad);
+    return;
+  }
+  __syncthreads();   // dinv complete, rowbuf free
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int i = ty + 16 * a, c = tx + 16 * b;
+      sm.S[i][c] = s[a][b];
+      sm.X[i][c] = (i == c) ? Sc<T>::from_real(i < nb ? sm.dinv[i] : R(1)) : Sc<T>::zero();
+      if (blockIdx.x == 0 && i <= c && c < nb) Ud[(i64)c * CB + i] = s[a][b];
+    }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) sm.Ys[ty + 16 * a][tx + 16 * b] = ys[a][b];
+  __syncthreads();
+  // ---- X = U_D^-1 by recursive doubling: X12 = -X11 (U12 X22); T = U12 X22 is parked at X[c][i] (strict lower part)
+  for (int b = 1; b < CB; b <<= 1) {
+    const int elems = (CB / 2) * b;   // (CB / 2b) pairs x b x b
+    for (int e = tid; e < elems; e += 256) {
+      const int p = e / (b * b), rem = e - p * b * b;
+      const int i = p * 2 * b + rem / b, c = p * 2 * b + b + rem % b;
+      T acc = Sc<T>::zero();
+      for (int l = p * 2 * b + b; l <= c; ++l) acc = fmad(sm.S[i][l], sm.X[l][c], acc);
+      sm.X[c][i] = acc;
+    }
+    __syncthreads();
+    for (int e = tid; e < elems; e += 256) {
+      const int p = e / (b * b), rem = e - p * b * b;
+      const int i = p * 2 * b + rem / b, c = p * 2 * b + b + rem % b;
+      T acc = Sc<T>::zero();
+      for (int l = i; l < p * 2 * b + b; ++l) acc = fmad(sm.X[i][l], sm.X[c][l], acc);
+      // reads: X11 (upper, block 1) and T(l, c) parked at X[c][l] (strict lower); the write goes to the X12 block
+      sm.X[i][c] = -acc;
+    }
+    __syncthreads();
+  }
+  // ---- slice solve: Y(i, c) = sum_{l <= i} conj(X(l, i)) * Ys(l, c)
+  if (sw > 0) {
+    T acc[4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) acc[a][b] = Sc<T>::zero();
+    for (int l = 0; l < nb; ++l) {
+      T xi[4], y[2];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) xi[a] = (l <= ty + 16 * a) ? cj(sm.X[l][ty + 16 * a]) : Sc<T>::zero();
+#pragma unroll
+      for (int b = 0; b < 2; ++b) y[b] = sm.Ys[l][tx + 16 * b];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) acc[a][b] = fmad(xi[a], y[b], acc[a][b]);
+    }
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int c = tx + 16 * b;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int i = ty + 16 * a;
+        if (c < sw && i < nb) W[(i64)(c0 + c) * ldw + r + i] = acc[a][b];
+      }
+    }
+  }
+}
+
+// the diagonal blocks factorised by chol_panel_kernel go back into the mirror (upper triangles)
+template <class T>
+__global__ void __launch_bounds__(256) put_diag_blocks_kernel(T* __restrict__ W, i64 ldw, int n, const T* __restrict__ Ud) {
+  const int r = blockIdx.x * CB;
+  const int nb = min(CB, n - r);
+  const T* U = Ud + (i64)blockIdx.x * CB * CB;
+  for (int e = threadIdx.x; e < CB * CB; e += 256) {
+    const int i = e & (CB - 1), c = e >> 6;
+    if (i <= c && c < nb) W[(i64)(r + c) * ldw + r + i] = U[(i64)c * CB + i];
+  }
+}
+
 // ------------------------------------------------------------------------------- recursion (host)
 template <class T>
 struct CholCtx {
@@ -256,11 +466,65 @@ static int chol_rec(CholCtx<T>& cx, i64 r0, i64 n) {
   return chol_rec<T>(cx, r0 + n1, n2);
 }
 
+// Right-looking driver on the fused panel kernel (Float32 / Float64): outer blocks of two 64-row panels; the second
+// panel takes the update of the first inside its own kernel (K = 64), everything beyond the outer block gets ONE
+// K = 128 trailing update on the tensor pipe.  96 launches at n = 4096 instead of ~450 for the recursion, none of them
+// a single-CTA kernel.  The result equals the recursion's (and the reference's) up to rounding: the same U^H U = W.
+template <class T>
+static bool use_panel_path() {
+  static const bool off = [] {
+    const char* e = getenv("GLA_CHOL_RECURSIVE");
+    return e && atoi(e) != 0;
+  }();
+  return !Sc<T>::is_complex && !off;   // ComplexF64: the panel kernel's tiles do not fit in shared memory
+}
+
+template <class T>
+static int chol_right_looking(CholCtx<T>& cx, i64 n) {
+  if constexpr (Sc<T>::is_complex) {
+    return GLA_ERR_INTERNAL;
+  } else {
+    const int smem = (int)sizeof(PanelSmem<T>);
+    GLA_TRY(ensure_dyn_smem((const void*)chol_panel_kernel<T>, smem));
+    auto panel = [&](i64 r, i64 nb, i64 rp, i64 kpend) -> int {
+      const i64 ncols = n - (r + nb);
+      const unsigned grid = (unsigned)(ncols > 0 ? ceil_div(ncols, SW) : 1);
+      chol_panel_kernel<T><<<grid, 256, smem, cx.st>>>(cx.W, cx.ldw, (int)n, (int)r, (int)nb, (int)rp, (int)kpend,
+                                                       cx.Uinv + (r / CB) * CB * CB, cx.info);
+      return check_cuda(cudaGetLastError(), __FILE__, __LINE__);
+    };
+    for (i64 r0 = 0; r0 < n; r0 += 2 * CB) {
+      const i64 nbA = n - r0 < CB ? n - r0 : CB;
+      GLA_TRY(panel(r0, nbA, r0, 0));
+      i64 done = nbA;
+      if (n - r0 > CB) {
+        const i64 nbB = n - r0 - CB < CB ? n - r0 - CB : CB;
+        GLA_TRY(panel(r0 + CB, nbB, r0, CB));
+        done += nbB;
+      }
+      const i64 t0 = r0 + done, nt = n - t0;
+      if (nt > 0) {
+        GemmTN<T> g;                                                 // W22 -= U12^H U12     (rankUpdate!, :51)
+        g.At = cx.W + r0 + t0 * cx.ldw; g.ldat = cx.ldw;
+        g.B = g.At; g.ldb = cx.ldw;
+        g.C = cx.W + t0 + t0 * cx.ldw; g.ldc = cx.ldw;
+        g.M = nt; g.N = nt; g.K = done;
+        g.alpha = -1; g.beta_one = 1; g.conj_a = 1; g.lower_only = 2;
+        GLA_TRY(gemm_tn<T>(g, cx.st));
+      }
+    }
+    put_diag_blocks_kernel<T><<<(unsigned)ceil_div(n, CB), 256, 0, cx.st>>>(cx.W, cx.ldw, (int)n, cx.Uinv);
+    return check_cuda(cudaGetLastError(), __FILE__, __LINE__);
+  }
+}
+
 template <class T>
 int potrf_recursive_L_dev(T* dA, i64 n, i64 lda, i64 /*cutoff*/, int* dinfo, cudaStream_t st) {
   if (n < 0) return -2;
   if (lda < (n > 1 ? n : 1)) return -3;
   if (n == 0) return 0;
+  if (!dA) return -1;
+  if (!dinfo) return -5;
   CholCtx<T> cx;
   cx.ldw = round_up(n, 16);
   cx.st = st;
@@ -271,11 +535,13 @@ int potrf_recursive_L_dev(T* dA, i64 n, i64 lda, i64 /*cutoff*/, int* dinfo, cud
   GLA_CUDA(cudaMallocAsync(&block, wbytes + nblk * CB * CB * sizeof(T), st));
   cx.W = static_cast<T*>(block);
   cx.Uinv = reinterpret_cast<T*>(static_cast<char*>(block) + wbytes);
-  GLA_CUDA(cudaMemsetAsync(dinfo, 0, sizeof(int), st));
   dim3 tb(32, 8), grid((unsigned)ceil_div(n, 32), (unsigned)ceil_div(n, 32));
-  mirror_in_kernel<T><<<grid, tb, 0, st>>>(dA, lda, cx.W, cx.ldw, (int)n);
-  int rc = check_cuda(cudaGetLastError(), __FILE__, __LINE__);
-  if (!rc) rc = chol_rec<T>(cx, 0, n);
+  int rc = check_cuda(cudaMemsetAsync(dinfo, 0, sizeof(int), st), __FILE__, __LINE__);
+  if (!rc) {
+    mirror_in_kernel<T><<<grid, tb, 0, st>>>(dA, lda, cx.W, cx.ldw, (int)n);
+    rc = check_cuda(cudaGetLastError(), __FILE__, __LINE__);
+  }
+  if (!rc) rc = use_panel_path<T>() ? chol_right_looking<T>(cx, n) : chol_rec<T>(cx, 0, n);
   if (!rc) {
     mirror_out_kernel<T><<<grid, tb, 0, st>>>(dA, lda, cx.W, cx.ldw, (int)n);
     rc = check_cuda(cudaGetLastError(), __FILE__, __LINE__);

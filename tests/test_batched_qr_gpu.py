@@ -161,5 +161,8 @@ def test_batched_extreme_scaling(gla, oracle, dtype, shift, shape):
         sc = np.max(np.abs(ref_f[b]))
         assert np.max(np.abs(got[b] - ref_f[b])) <= tol * sc
     assert np.max(np.abs(tau - ref_t)) <= tol
-    # the oracle itself: scaling by a power of two only scales R
-    assert np.array_equal(np.tril(ref_f[0], -1), np.tril(base_f[0], -1)) and np.array_equal(ref_t[0], base_t[0])
+    # the oracle itself: scaling by a power of two only scales R (to the last bits: the rescaled and the plain sum of
+    # squares are separate loops and may contract to FMA differently)
+    eps = np.finfo(dtype).eps
+    assert np.max(np.abs(np.tril(ref_f[0], -1) - np.tril(base_f[0], -1))) <= 64 * eps
+    assert np.max(np.abs(ref_t[0] - base_t[0])) <= 64 * eps
