@@ -198,9 +198,10 @@ __global__ void __launch_bounds__(256) potrf_block_kernel(T* __restrict__ W, i64
 // boundaries: EVERY CTA of the launch factorises and inverts the diagonal block redundantly (same arithmetic, so bitwise
 // the same factor; no inter-CTA synchronisation) and then solves ITS OWN 32-column slice of the row panel,
 //     Y = U_D^-H * W(r : r+nb, slice)            (rdiv!, src/cholesky.jl:48, as a product with the explicit inverse).
-// kpend > 0: the panel has not yet received the update of the previous panel of its outer block (rows rp : rp+kpend):
-//     W(r : r+nb, r : n) -= U(rp : rp+kpend, r : r+nb)^H * U(rp : rp+kpend, r : n)     (rankUpdate!, :51, K = 64)
-// is applied first, to the diagonal block by every CTA and to the slice by its owner.  The factor of the diagonal block
+// kpend > 0: the panel has not yet received the update of the finished rows rp : rp+kpend right above it (the previous
+// panel of its outer block and, for 128-row outer blocks, the whole previous outer block: kpend <= 192):
+//     W(r : r+nb, r : n) -= U(rp : rp+kpend, r : r+nb)^H * U(rp : rp+kpend, r : n)     (rankUpdate!, :51)
+// is applied first, in chunks of 64 rows, to the diagonal block by every CTA and to the slice by its owner.  The factor of the diagonal block
 // goes to a scratch copy (Ud), not into W: other CTAs of the same launch may still be reading the block.
 //   inverse: recursive doubling, X12 = -X11 U12 X22 for blocks of 1, 2, 4 .. 32 (12 barriers, all threads busy) instead of
 //   63 dependent back-substitution steps.
@@ -242,20 +243,28 @@ __device__ __forceinline__ int factor_block_regs(T (&s)[4][4], const int nb, T (
     const R rd = Fast<R>::rsqrt(piv);
     const R d = Fast<R>::sqrt_from_rsqrt(piv, rd);
     if (tid == 0) dinv[j] = rd;
+    // Entries strictly below the diagonal (c < i) are never read by anybody, so the rank-1 update only has to be
+    // masked by ROW (i > j): four selects per step instead of a predicate per entry.
     T ui[4], uc[4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a) ui[a] = cj(scale_real(rb[ty + 16 * a], rd));
+    for (int a = 0; a < 4; ++a) ui[a] = (ty + 16 * a > j) ? cj(scale_real(rb[ty + 16 * a], rd)) : Sc<T>::zero();
 #pragma unroll
     for (int b = 0; b < 4; ++b) uc[b] = scale_real(rb[tx + 16 * b], rd);
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const int i = ty + 16 * a;
+    for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const int c = tx + 16 * b;
-        if (i > j && c >= i) s[a][b] = s[a][b] - ui[a] * uc[b];                   // trailing upper triangle
-        else if (i == j && c >= j) s[a][b] = c == j ? Sc<T>::from_real(d) : uc[b];  // row j of the factor
-      }
+      for (int b = 0; b < 4; ++b) s[a][b] = s[a][b] - ui[a] * uc[b];
+    if (ty == (j & 15)) {   // row j of the factor: U(j, c) = W(j, c) / d for c > j, d on the diagonal
+      const int ja = j >> 4;
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+        if (a == ja) {
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const int c = tx + 16 * b;
+            s[a][b] = c == j ? Sc<T>::from_real(d) : uc[b];
+          }
+        }
     }
   }
   return 0;
@@ -280,25 +289,46 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(T* __restrict__ W, i64 
       const int i = ty + 16 * a, c = tx + 16 * b;
       s[a][b] = (i <= c && c < nb) ? W[(i64)(r + c) * ldw + r + i] : ((i == c && i >= nb) ? Sc<T>::one() : Sc<T>::zero());
     }
-  for (int e = tid; e < CB * CB; e += 256) {
-    const int k = e & (CB - 1), c = e >> 6;
-    sm.P[k][c] = (k < kpend && c < nb) ? W[(i64)(r + c) * ldw + rp + k] : Sc<T>::zero();
-  }
-  for (int e = tid; e < CB * SW; e += 256) {
-    const int k = e & (CB - 1), c = e >> 6;
-    const bool in = c < sw;
-    sm.Ys[k][c] = (in && k < nb) ? W[(i64)(c0 + c) * ldw + r + k] : Sc<T>::zero();
-    sm.Ps[k][c] = (in && k < kpend) ? W[(i64)(c0 + c) * ldw + rp + k] : Sc<T>::zero();
+  const int k_ = tid & (CB - 1), cq = tid >> 6;   // staging element e = tid + 256 q  ->  row k_, column cq + 4 q
+  {  // all global loads are issued before the first shared-memory store (one round trip, not one per element)
+    T vy[CB * SW / 256];
+#pragma unroll
+    for (int q = 0; q < CB * SW / 256; ++q) {
+      const int c = cq + 4 * q;
+      vy[q] = (c < sw && k_ < nb) ? W[(i64)(c0 + c) * ldw + r + k_] : Sc<T>::zero();
+    }
+#pragma unroll
+    for (int q = 0; q < CB * SW / 256; ++q) sm.Ys[k_][cq + 4 * q] = vy[q];
   }
   __syncthreads();
-  // ---- pending rank-kpend update: diagonal block (upper 16 x 16 sub-blocks only) and slice
+  // ---- pending rank-kpend update in chunks of 64 rows: diagonal block (upper 16 x 16 sub-blocks only) and slice
   T ys[4][2];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
     for (int b = 0; b < 2; ++b) ys[a][b] = sm.Ys[ty + 16 * a][tx + 16 * b];
-  if (kpend > 0) {
-    for (int k = 0; k < kpend; ++k) {
+  for (int kc = 0; kc < kpend; kc += CB) {
+    const int kn = min(CB, kpend - kc);
+    {
+      T vp[CB * CB / 256], vs[CB * SW / 256];
+#pragma unroll
+      for (int q = 0; q < CB * CB / 256; ++q) {
+        const int c = cq + 4 * q;
+        vp[q] = (k_ < kn && c < nb) ? W[(i64)(r + c) * ldw + rp + kc + k_] : Sc<T>::zero();
+      }
+#pragma unroll
+      for (int q = 0; q < CB * SW / 256; ++q) {
+        const int c = cq + 4 * q;
+        vs[q] = (c < sw && k_ < kn) ? W[(i64)(c0 + c) * ldw + rp + kc + k_] : Sc<T>::zero();
+      }
+      if (kc > 0) __syncthreads();   // the previous chunk has been consumed
+#pragma unroll
+      for (int q = 0; q < CB * CB / 256; ++q) sm.P[k_][cq + 4 * q] = vp[q];
+#pragma unroll
+      for (int q = 0; q < CB * SW / 256; ++q) sm.Ps[k_][cq + 4 * q] = vs[q];
+    }
+    __syncthreads();
+    for (int k = 0; k < kn; ++k) {
       T ui[4], uc[4], us[2];
 #pragma unroll
       for (int a = 0; a < 4; ++a) ui[a] = cj(sm.P[k][ty + 16 * a]);
@@ -337,24 +367,40 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(T* __restrict__ W, i64 
 #pragma unroll
     for (int b = 0; b < 2; ++b) sm.Ys[ty + 16 * a][tx + 16 * b] = ys[a][b];
   __syncthreads();
-  // ---- X = U_D^-1 by recursive doubling: X12 = -X11 (U12 X22); T = U12 X22 is parked at X[c][i] (strict lower part)
+  // ---- X = U_D^-1 by recursive doubling: X12 = -X11 (U12 X22) for blocks of b = 1, 2 .. 32; T = U12 X22 is parked in P
+  // (free after the pending update).  X stays exactly zero below its diagonal, so every dot runs over a whole block
+  // (fixed trip count b, no triangular bounds) and the loads of consecutive terms are independent.
   for (int b = 1; b < CB; b <<= 1) {
     const int elems = (CB / 2) * b;   // (CB / 2b) pairs x b x b
+    const int lb = 31 - __clz(b);     // log2 b
     for (int e = tid; e < elems; e += 256) {
-      const int p = e / (b * b), rem = e - p * b * b;
-      const int i = p * 2 * b + rem / b, c = p * 2 * b + b + rem % b;
-      T acc = Sc<T>::zero();
-      for (int l = p * 2 * b + b; l <= c; ++l) acc = fmad(sm.S[i][l], sm.X[l][c], acc);
-      sm.X[c][i] = acc;
+      const int p = e >> (2 * lb), rem = e & (b * b - 1);
+      const int base = p * 2 * b;
+      const int i = base + (rem >> lb), c = base + b + (rem & (b - 1));
+      T acc0 = Sc<T>::zero(), acc1 = Sc<T>::zero();
+      int l = base + b;
+#pragma unroll 4
+      for (; l + 1 < base + 2 * b; l += 2) {
+        acc0 = fmad(sm.S[i][l], sm.X[l][c], acc0);
+        acc1 = fmad(sm.S[i][l + 1], sm.X[l + 1][c], acc1);
+      }
+      if (l < base + 2 * b) acc0 = fmad(sm.S[i][l], sm.X[l][c], acc0);
+      sm.P[i][c] = acc0 + acc1;
     }
     __syncthreads();
     for (int e = tid; e < elems; e += 256) {
-      const int p = e / (b * b), rem = e - p * b * b;
-      const int i = p * 2 * b + rem / b, c = p * 2 * b + b + rem % b;
-      T acc = Sc<T>::zero();
-      for (int l = i; l < p * 2 * b + b; ++l) acc = fmad(sm.X[i][l], sm.X[c][l], acc);
-      // reads: X11 (upper, block 1) and T(l, c) parked at X[c][l] (strict lower); the write goes to the X12 block
-      sm.X[i][c] = -acc;
+      const int p = e >> (2 * lb), rem = e & (b * b - 1);
+      const int base = p * 2 * b;
+      const int i = base + (rem >> lb), c = base + b + (rem & (b - 1));
+      T acc0 = Sc<T>::zero(), acc1 = Sc<T>::zero();
+      int l = base;
+#pragma unroll 4
+      for (; l + 1 < base + b; l += 2) {
+        acc0 = fmad(sm.X[i][l], sm.P[l][c], acc0);
+        acc1 = fmad(sm.X[i][l + 1], sm.P[l + 1][c], acc1);
+      }
+      if (l < base + b) acc0 = fmad(sm.X[i][l], sm.P[l][c], acc0);
+      sm.X[i][c] = -(acc0 + acc1);   // the X12 block: nobody reads it at this level
     }
     __syncthreads();
   }
@@ -486,32 +532,84 @@ static int chol_right_looking(CholCtx<T>& cx, i64 n) {
   } else {
     const int smem = (int)sizeof(PanelSmem<T>);
     GLA_TRY(ensure_dyn_smem((const void*)chol_panel_kernel<T>, smem));
+    static const int dbg_skip = [] {   // timing experiments only: 1 = no trailing updates, 2 = no panel kernels
+      const char* e = getenv("GLA_CHOL_DEBUG_SKIP");
+      return e ? atoi(e) : 0;
+    }();
     auto panel = [&](i64 r, i64 nb, i64 rp, i64 kpend) -> int {
+      if (dbg_skip == 2) return 0;
       const i64 ncols = n - (r + nb);
       const unsigned grid = (unsigned)(ncols > 0 ? ceil_div(ncols, SW) : 1);
       chol_panel_kernel<T><<<grid, 256, smem, cx.st>>>(cx.W, cx.ldw, (int)n, (int)r, (int)nb, (int)rp, (int)kpend,
                                                        cx.Uinv + (r / CB) * CB * CB, cx.info);
       return check_cuda(cudaGetLastError(), __FILE__, __LINE__);
     };
-    for (i64 r0 = 0; r0 < n; r0 += 2 * CB) {
-      const i64 nbA = n - r0 < CB ? n - r0 : CB;
-      GLA_TRY(panel(r0, nbA, r0, 0));
-      i64 done = nbA;
-      if (n - r0 > CB) {
-        const i64 nbB = n - r0 - CB < CB ? n - r0 - CB : CB;
-        GLA_TRY(panel(r0 + CB, nbB, r0, CB));
-        done += nbB;
+    // Look-ahead: the sequential chain (panel kernels + the update of the NEXT outer block's 128 rows) runs on a cached
+    // high-priority stream `sc`; the bulk of every trailing update (rows beyond the next outer block) runs on the caller's
+    // stream concurrently with the next outer block's panel kernels.  GLA_CHOL_NO_OVERLAP=1: one stream.
+    static const bool no_overlap = getenv("GLA_CHOL_NO_OVERLAP") != nullptr;
+    const bool overlap = !no_overlap && n > 6 * CB;
+    cudaStream_t sc = cx.st;
+    AuxCtx* aux = nullptr;
+    if (overlap) {
+      GLA_TRY(aux_ctx(&aux));
+      sc = aux->hi;
+      GLA_CUDA(cudaEventRecord(aux->ev[0], cx.st));          // mirror ready
+      GLA_CUDA(cudaStreamWaitEvent(sc, aux->ev[0], 0));
+    }
+    const cudaStream_t caller = cx.st;
+    auto update = [&](i64 r0, i64 K, i64 c0, i64 mrows, cudaStream_t s) -> int {   // W(c0 : c0+mrows, c0 : n) -= U(r0 : r0+K, .)^H U(r0 : r0+K, .)
+      GemmTN<T> g;                                                                  // (rankUpdate!, :51), upper part only
+      g.At = cx.W + r0 + c0 * cx.ldw; g.ldat = cx.ldw;
+      g.B = g.At; g.ldb = cx.ldw;
+      g.C = cx.W + c0 + c0 * cx.ldw; g.ldc = cx.ldw;
+      g.M = mrows; g.N = n - c0; g.K = K;
+      g.alpha = -1; g.beta_one = 1; g.conj_a = 1; g.lower_only = 2;
+      return gemm_tn<T>(g, s);
+    };
+    // outer block: 128 rows while the panel chain is what bounds the run (n <= 4096), 256 beyond that, where the K = 128
+    // trailing updates would (each one reads and writes the whole trailing matrix once)
+    const i64 OB = n > 6144 ? 4 * CB : 2 * CB;
+    // (Folding the K = 128 update of the next outer block's rows into its two panel kernels as a longer pending update was
+    // measured slower: 5.58 ms against 4.81 ms at n = 4096 -- the in-kernel FMA update costs more than the tensor-pipe launch.)
+    bool bulk_pending = false;
+    for (i64 r0 = 0; r0 < n; r0 += OB) {
+      i64 done = 0;
+      cx.st = sc;
+      for (i64 p0 = r0; p0 < n && p0 < r0 + OB; p0 += 2 * CB) {   // pairs of panels; the second takes the first in-kernel
+        if (done > 0 && dbg_skip != 1)                             // rows of this pair <- the pairs before it in the block
+          GLA_TRY(update(r0, done, p0, n - p0 < 2 * CB ? n - p0 : 2 * CB, sc));
+        const i64 nbA = n - p0 < CB ? n - p0 : CB;
+        GLA_TRY(panel(p0, nbA, p0, 0));
+        done += nbA;
+        if (n - p0 > CB) {
+          const i64 nbB = n - p0 - CB < CB ? n - p0 - CB : CB;
+          GLA_TRY(panel(p0 + CB, nbB, p0, CB));
+          done += nbB;
+        }
       }
+      cx.st = caller;
       const i64 t0 = r0 + done, nt = n - t0;
-      if (nt > 0) {
-        GemmTN<T> g;                                                 // W22 -= U12^H U12     (rankUpdate!, :51)
-        g.At = cx.W + r0 + t0 * cx.ldw; g.ldat = cx.ldw;
-        g.B = g.At; g.ldb = cx.ldw;
-        g.C = cx.W + t0 + t0 * cx.ldw; g.ldc = cx.ldw;
-        g.M = nt; g.N = nt; g.K = done;
-        g.alpha = -1; g.beta_one = 1; g.conj_a = 1; g.lower_only = 2;
-        GLA_TRY(gemm_tn<T>(g, cx.st));
+      if (nt <= 0 || dbg_skip == 1) continue;
+      if (!overlap) {
+        GLA_TRY(update(r0, done, t0, nt, caller));
+        continue;
       }
+      const i64 mu = nt < OB ? nt : OB;                   // rows of the next outer block: needed by the chain right away
+      GLA_CUDA(cudaEventRecord(aux->ev[1], sc));          // panels of this outer block done
+      if (bulk_pending) GLA_CUDA(cudaStreamWaitEvent(sc, aux->ev[2], 0));   // those rows carry the previous bulk update
+      GLA_TRY(update(r0, done, t0, mu, sc));
+      if (nt > mu) {
+        GLA_CUDA(cudaStreamWaitEvent(caller, aux->ev[1], 0));
+        GLA_TRY(update(r0, done, t0 + mu, nt - mu, caller));
+        GLA_CUDA(cudaEventRecord(aux->ev[2], caller));
+        bulk_pending = true;
+      }
+    }
+    cx.st = caller;
+    if (overlap) {
+      GLA_CUDA(cudaEventRecord(aux->ev[3], sc));
+      GLA_CUDA(cudaStreamWaitEvent(caller, aux->ev[3], 0));
     }
     put_diag_blocks_kernel<T><<<(unsigned)ceil_div(n, CB), 256, 0, cx.st>>>(cx.W, cx.ldw, (int)n, cx.Uinv);
     return check_cuda(cudaGetLastError(), __FILE__, __LINE__);

@@ -163,6 +163,14 @@ inline int ceil_div(i64 a, i64 b) { return (int)((a + b - 1) / b); }
 inline i64 round_up(i64 a, i64 b) { return (a + b - 1) / b * b; }
 
 int sm_count();  // of the current device (cached)
+// High-priority side stream + four timing-free events for the look-ahead schedules (blocked QR, Cholesky), created once
+// per (host thread, device) and reused by every call: work is stream-ordered, so consecutive asynchronous calls of one
+// thread may share them.  Released when the thread exits.
+struct AuxCtx {
+  cudaStream_t hi = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+int aux_ctx(AuxCtx** out);
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel, size): the launch paths are host-bound for
 // small problems (hundreds of dependent launches), so the per-launch driver call is worth avoiding
 int ensure_dyn_smem(const void* func, int bytes);

@@ -50,6 +50,34 @@ int sm_count() {
   return cached[dev];
 }
 
+namespace {
+struct AuxCache {
+  std::map<int, AuxCtx> per_dev;
+  ~AuxCache() {
+    for (auto& kv : per_dev) {
+      for (auto& e : kv.second.ev)
+        if (e) cudaEventDestroy(e);
+      if (kv.second.hi) cudaStreamDestroy(kv.second.hi);
+    }
+  }
+};
+}  // namespace
+
+int aux_ctx(AuxCtx** out) {
+  static thread_local AuxCache cache;
+  int dev = 0;
+  GLA_CUDA(cudaGetDevice(&dev));
+  AuxCtx& a = cache.per_dev[dev];
+  if (!a.hi) {
+    int lo = 0, hi = 0;
+    GLA_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    GLA_CUDA(cudaStreamCreateWithPriority(&a.hi, cudaStreamNonBlocking, hi));
+    for (auto& e : a.ev) GLA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  *out = &a;
+  return 0;
+}
+
 int ensure_dyn_smem(const void* func, int bytes) {
   static std::mutex mu;
   static std::map<std::pair<int, const void*>, int> done;

@@ -925,20 +925,15 @@ static int apply_outer(QrWork<T>& w, int b, i64 mo, int kbig, T* A2, i64 lda, i6
 
 // ------------------------------------------------------------------------------- drivers
 namespace {
-struct AuxStream {  // high-priority side stream + the events of the look-ahead schedule
+struct AuxStream {  // high-priority side stream + the events of the look-ahead schedule (cached per thread and device)
   cudaStream_t s = nullptr;
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   int create() {
-    int lo = 0, hi = 0;
-    GLA_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    GLA_CUDA(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi));
-    for (auto& e : ev) GLA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    AuxCtx* a = nullptr;
+    GLA_TRY(aux_ctx(&a));
+    s = a->hi;
+    for (int i = 0; i < 3; ++i) ev[i] = a->ev[i];
     return 0;
-  }
-  ~AuxStream() {
-    for (auto& e : ev)
-      if (e) cudaEventDestroy(e);
-    if (s) cudaStreamDestroy(s);
   }
 };
 }  // namespace
