@@ -168,6 +168,9 @@ int larft_host(const T* F, i64 m, i64 n, i64 ldf, const T* tau, T* Tm, i64 ldt) 
   if (ldf < (m > 1 ? m : 1)) return -4;
   const i64 k = m < n ? m : n;
   if (k == 0) return 0;
+  if (!F) return -1;
+  if (!tau) return -5;
+  if (!Tm) return -6;
   if (ldt < k) return -7;
   Stream st;
   GLA_TRY(st.create());
@@ -188,10 +191,15 @@ template <class T>
 int ormqr_host(const T* F, i64 mF, i64 nF, i64 ldf, const T* tau, T* A, i64 mA, i64 nA, i64 lda, int adjoint) {
   if (mF < 0) return -2;
   if (nF < 0) return -3;
+  if (ldf < (mF > 1 ? mF : 1)) return -4;
   if (mA != mF) return -7;
   if (nA < 0) return -8;
+  if (lda < (mA > 1 ? mA : 1)) return -9;
   const i64 k = mF < nF ? mF : nF;
   if (k == 0 || nA == 0 || mA == 0) return 0;
+  if (!F) return -1;
+  if (!tau) return -5;
+  if (!A) return -6;
   Stream st;
   GLA_TRY(st.create());
   DevMatrix<T> dF, dA;
@@ -210,8 +218,12 @@ template <class T>
 int reflector_apply_right_host(T* A, i64 m, i64 n, i64 lda, const T* x, i64 lenx, const T* tau) {
   if (m < 0) return -2;
   if (n < 0) return -3;
-  if (lenx != n) return -5;  // DimensionMismatch, src/qr.jl:21-27
+  if (lda < (m > 1 ? m : 1)) return -4;
+  if (lenx != n) return -6;  // DimensionMismatch, src/qr.jl:21-27 (lenx is the 6th argument)
   if (m == 0 || n == 0) return 0;
+  if (!A) return -1;
+  if (!x) return -5;
+  if (!tau) return -7;
   Stream st;
   GLA_TRY(st.create());
   DevMatrix<T> dA;
@@ -369,6 +381,38 @@ int gla_sreflector_apply_right(float* A, int64_t m, int64_t n, int64_t lda, cons
 int gla_dreflector_apply_right(double* A, int64_t m, int64_t n, int64_t lda, const double* x, int64_t lenx, const double* tau) { return reflector_apply_right_host<double>(A, m, n, lda, x, lenx, tau); }
 int gla_zreflector_apply_right(void* A, int64_t m, int64_t n, int64_t lda, const void* x, int64_t lenx, const void* tau) { return reflector_apply_right_host<zd>(ZP(A), m, n, lda, ZCP(x), lenx, ZCP(tau)); }
 
+// ---- device-pointer twins of the T build, the block application and the right reflector application
+int gla_slarft_dev(const float* dF, int64_t m, int64_t n, int64_t ldf, const float* dtau, float* dT, int64_t ldt, void* stream) { return larft_dev<float>(dF, m, n, ldf, dtau, dT, ldt, STREAM(stream)); }
+int gla_dlarft_dev(const double* dF, int64_t m, int64_t n, int64_t ldf, const double* dtau, double* dT, int64_t ldt, void* stream) { return larft_dev<double>(dF, m, n, ldf, dtau, dT, ldt, STREAM(stream)); }
+int gla_zlarft_dev(const void* dF, int64_t m, int64_t n, int64_t ldf, const void* dtau, void* dT, int64_t ldt, void* stream) { return larft_dev<zd>(ZCP(dF), m, n, ldf, ZCP(dtau), ZP(dT), ldt, STREAM(stream)); }
+int gla_sormqr_blocked_dev(const float* dF, int64_t mF, int64_t nF, int64_t ldf, const float* dtau, float* dA, int64_t mA, int64_t nA, int64_t lda, int adjoint, void* stream) {
+  if (mA != mF) return -7;
+  return ormqr_blocked_dev<float>(dF, mF, nF, ldf, dtau, dA, mA, nA, lda, adjoint, STREAM(stream));
+}
+int gla_dormqr_blocked_dev(const double* dF, int64_t mF, int64_t nF, int64_t ldf, const double* dtau, double* dA, int64_t mA, int64_t nA, int64_t lda, int adjoint, void* stream) {
+  if (mA != mF) return -7;
+  return ormqr_blocked_dev<double>(dF, mF, nF, ldf, dtau, dA, mA, nA, lda, adjoint, STREAM(stream));
+}
+int gla_zormqr_blocked_dev(const void* dF, int64_t mF, int64_t nF, int64_t ldf, const void* dtau, void* dA, int64_t mA, int64_t nA, int64_t lda, int adjoint, void* stream) {
+  if (mA != mF) return -7;
+  return ormqr_blocked_dev<zd>(ZCP(dF), mF, nF, ldf, ZCP(dtau), ZP(dA), mA, nA, lda, adjoint, STREAM(stream));
+}
+int gla_sreflector_apply_right_dev(float* dA, int64_t m, int64_t n, int64_t lda, const float* dx, int64_t lenx, const float* tau, void* stream) {
+  if (lenx != n) return -6;
+  if (!tau) return -7;
+  return reflector_apply_right_dev<float>(dA, m, n, lda, dx, *tau, STREAM(stream));
+}
+int gla_dreflector_apply_right_dev(double* dA, int64_t m, int64_t n, int64_t lda, const double* dx, int64_t lenx, const double* tau, void* stream) {
+  if (lenx != n) return -6;
+  if (!tau) return -7;
+  return reflector_apply_right_dev<double>(dA, m, n, lda, dx, *tau, STREAM(stream));
+}
+int gla_zreflector_apply_right_dev(void* dA, int64_t m, int64_t n, int64_t lda, const void* dx, int64_t lenx, const void* tau, void* stream) {
+  if (lenx != n) return -6;
+  if (!tau) return -7;
+  return reflector_apply_right_dev<zd>(ZP(dA), m, n, lda, ZCP(dx), *ZCP(tau), STREAM(stream));
+}
+
 // ---- TSQR
 int gla_dtsqr_local_dev(const double* dA, int64_t m, int64_t n, int64_t lda, double* dR, int64_t ldr, void* stream) { return tsqr_local_dev(dA, m, n, lda, dR, ldr, STREAM(stream)); }
 int gla_dtsqr_combine_dev(const double* dRs, int64_t count, int64_t n, double* dR, int64_t ldr, void* stream) { return tsqr_combine_dev(dRs, count, n, dR, ldr, STREAM(stream)); }
@@ -394,6 +438,30 @@ int gla_zpotrf_recursive_L(void* A, int64_t n, int64_t lda, int64_t cutoff) { re
 int gla_spotrf_recursive_L_dev(float* dA, int64_t n, int64_t lda, int64_t cutoff, int* dinfo, void* stream) { return potrf_recursive_L_dev<float>(dA, n, lda, cutoff, dinfo, STREAM(stream)); }
 int gla_dpotrf_recursive_L_dev(double* dA, int64_t n, int64_t lda, int64_t cutoff, int* dinfo, void* stream) { return potrf_recursive_L_dev<double>(dA, n, lda, cutoff, dinfo, STREAM(stream)); }
 int gla_zpotrf_recursive_L_dev(void* dA, int64_t n, int64_t lda, int64_t cutoff, int* dinfo, void* stream) { return potrf_recursive_L_dev<zd>(ZP(dA), n, lda, cutoff, dinfo, STREAM(stream)); }
+
+// cholUnblocked!(A, Val{:L}) (src/cholesky.jl:3-15) and cholBlocked!(A, Val{:L}, blocksize) (src/cholesky.jl:17-35): the
+// lower Cholesky factor is unique, so both map onto the same device routine (the blocksize is a CPU tuning parameter)
+int gla_spotrf_unblocked_L(float* A, int64_t n, int64_t lda) { return potrf_host<float>(A, n, lda, 1); }
+int gla_dpotrf_unblocked_L(double* A, int64_t n, int64_t lda) { return potrf_host<double>(A, n, lda, 1); }
+int gla_zpotrf_unblocked_L(void* A, int64_t n, int64_t lda) { return potrf_host<zd>(ZP(A), n, lda, 1); }
+int gla_spotrf_blocked_L(float* A, int64_t n, int64_t lda, int64_t blocksize) { return blocksize < 1 ? -4 : potrf_host<float>(A, n, lda, 1); }
+int gla_dpotrf_blocked_L(double* A, int64_t n, int64_t lda, int64_t blocksize) { return blocksize < 1 ? -4 : potrf_host<double>(A, n, lda, 1); }
+int gla_zpotrf_blocked_L(void* A, int64_t n, int64_t lda, int64_t blocksize) { return blocksize < 1 ? -4 : potrf_host<zd>(ZP(A), n, lda, 1); }
+
+// ---- workspace query
+int64_t gla_workspace_query(int op, int elem_bytes, int64_t m, int64_t n) {
+  if (elem_bytes != 4 && elem_bytes != 8 && elem_bytes != 16) return -2;
+  if (m < 0) return -3;
+  if (n < 0) return -4;
+  const int64_t e = elem_bytes;
+  switch (op) {
+    case GLA_OP_GEQR_BLOCKED: return geqr_blocked_workspace_bytes(m, n, e);
+    case GLA_OP_POTRF_L: return (round_up(n, 16) * n + (n + 63) / 64 * 64 * 64) * e + 256;   // mirror + diagonal blocks
+    case GLA_OP_GEQR_BATCHED: return 0;
+    case GLA_OP_TSQR: return 2 * (int64_t)sm_count() * 2 * n * n * e;                          // two levels of per-CTA R factors
+    default: return -1;
+  }
+}
 
 // ---- Hermitian rank-k update
 int gla_ssyrk_lower(float* C, int64_t n, int64_t ldc, const float* A, int64_t k, int64_t lda, float alpha) { return herk_host<float>(C, n, ldc, A, k, lda, alpha); }

@@ -15,6 +15,7 @@ int geqr_batched_dev(T* dA, i64 m, i64 n, i64 batch, T* dtau, cudaStream_t st);
 // K1/K2/K3: blocked QR of one large matrix (qr_blocked.cu)
 template <class T>
 int geqr_blocked_dev(T* dA, i64 m, i64 n, i64 lda, T* dtau, i64 blocksize_hint, cudaStream_t st);
+i64 geqr_blocked_workspace_bytes(i64 m, i64 n, i64 elem_bytes);
 // compact-WY T of all k=min(m,n) reflectors; dT is k x k (ldt)
 template <class T>
 int larft_dev(const T* dF, i64 m, i64 n, i64 ldf, const T* dtau, T* dT, i64 ldt, cudaStream_t st);

@@ -652,7 +652,8 @@ struct QrWork {
   static constexpr int GP_SPLITS = 32;
 
   // nA0 / nA1: widest trailing block handled on path 0 / path 1 (0 = path unused); nbuf outer buffers
-  int alloc(i64 m, i64 nA0, i64 nA1, int nbuf, cudaStream_t stream) {
+  // total_only != nullptr: size computation only (gla_workspace_query), nothing is allocated
+  int alloc(i64 m, i64 nA0, i64 nA1, int nbuf, cudaStream_t stream, i64* total_only = nullptr) {
     st = stream;
     ldv = round_up(m, 2);
     auto al = [](i64 bytes) { return round_up(bytes, 256); };
@@ -681,6 +682,10 @@ struct QrWork {
     const i64 s_xz = al((i64)2 * GW_MAX * NR * 16);
     const i64 total = nbuf * (s_v + s_vt + s_tm + s_g) + s_gs + 2 * s_gp + s_wp[0] + s_wp[1] + s_z[0] + s_z[1] +
                       s_xd + s_xr + s_xw + s_xz + 256;
+    if (total_only) {
+      *total_only = total;
+      return 0;
+    }
     GLA_CUDA(cudaMallocAsync(&block, total, st));
     char* p = static_cast<char*>(block);
     for (int b = 0; b < 2; ++b) {
@@ -937,6 +942,24 @@ struct AuxStream {  // high-priority side stream + the events of the look-ahead 
   }
 };
 }  // namespace
+
+// device bytes geqr_blocked_dev takes from the stream-ordered pool for an m x n problem (gla_workspace_query)
+i64 geqr_blocked_workspace_bytes(i64 m, i64 n, i64 elem_bytes) {
+  if (m == 0 || n == 0) return 0;
+  const bool overlap = n > 2 * NBO && m > 2 * NBO;
+  i64 total = 0;
+  if (elem_bytes == 4) {
+    QrWork<float> w;
+    w.alloc(m, NBO, n > NBO ? n - NBO : 0, overlap ? 2 : 1, nullptr, &total);
+  } else if (elem_bytes == 8) {
+    QrWork<double> w;
+    w.alloc(m, NBO, n > NBO ? n - NBO : 0, overlap ? 2 : 1, nullptr, &total);
+  } else {
+    QrWork<zd> w;
+    w.alloc(m, NBO, n > NBO ? n - NBO : 0, overlap ? 2 : 1, nullptr, &total);
+  }
+  return total;
+}
 
 // Look-ahead schedule (one outer block ahead):
 //   chain(o)  on the side stream : panels + per-panel T + updates inside outer block o   (needs far A(o-1))

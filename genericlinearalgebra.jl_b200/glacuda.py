@@ -328,6 +328,63 @@ def cholRecursive_(A, uplo="L", cutoff: int = 1):
     return A
 
 
+def cholUnblocked_(A, uplo="L"):
+    """GenericLinearAlgebra.cholUnblocked!(A, Val{:L}) (src/cholesky.jl:3-15): the same unique lower factor, in place."""
+    if uplo not in ("L", ":L"):
+        raise ArgumentError("only Val{:L} has a method (src/cholesky.jl:3)")
+    lda = _colmajor(A, "cholUnblocked!")
+    if A.shape[0] != A.shape[1]:
+        raise DimensionMismatch(f"matrix is not square: dimensions are {A.shape}")
+    _check(_fn("potrf_unblocked_L", A.dtype)(_ptr(A), _I64(A.shape[0]), _I64(lda)), "potrf_unblocked_L")
+    return A
+
+
+def cholBlocked_(A, uplo="L", blocksize: int = 64):
+    """GenericLinearAlgebra.cholBlocked!(A, Val{:L}, blocksize) (src/cholesky.jl:17-35); blocksize is a hint."""
+    if uplo not in ("L", ":L"):
+        raise ArgumentError("only Val{:L} has a method (src/cholesky.jl:17)")
+    lda = _colmajor(A, "cholBlocked!")
+    if A.shape[0] != A.shape[1]:
+        raise DimensionMismatch(f"matrix is not square: dimensions are {A.shape}")
+    _check(_fn("potrf_blocked_L", A.dtype)(_ptr(A), _I64(A.shape[0]), _I64(lda), _I64(blocksize)), "potrf_blocked_L",
+           ArgumentError)
+    return A
+
+
+OP_GEQR_BLOCKED, OP_POTRF_L, OP_GEQR_BATCHED, OP_TSQR = 1, 2, 3, 4
+
+
+def workspace_query(op: int, dtype, m: int, n: int) -> int:
+    """Device bytes the `_dev` call of `op` takes from the library's stream-ordered pool (gla_workspace_query)."""
+    f = lib().gla_workspace_query
+    f.restype = C.c_int64
+    rc = int(f(C.c_int(op), C.c_int(np.dtype(dtype).itemsize), _I64(m), _I64(n)))
+    if rc < 0:
+        raise ArgumentError(f"workspace_query: argument {-rc} is illegal")
+    return rc
+
+
+def larft_dev(dF: int, m: int, n: int, ldf: int, dtau: int, dT: int, ldt: int, stream: int = 0, dtype=np.float64) -> None:
+    rc = _fn("larft_dev", dtype)(C.c_void_p(dF), _I64(m), _I64(n), _I64(ldf), C.c_void_p(dtau), C.c_void_p(dT), _I64(ldt),
+                                 C.c_void_p(stream))
+    _check(rc, "larft_dev")
+
+
+def ormqr_blocked_dev(dF: int, mF: int, nF: int, ldf: int, dtau: int, dA: int, mA: int, nA: int, lda: int, adjoint: bool,
+                      stream: int = 0, dtype=np.float64) -> None:
+    rc = _fn("ormqr_blocked_dev", dtype)(C.c_void_p(dF), _I64(mF), _I64(nF), _I64(ldf), C.c_void_p(dtau), C.c_void_p(dA),
+                                         _I64(mA), _I64(nA), _I64(lda), C.c_int(1 if adjoint else 0), C.c_void_p(stream))
+    _check(rc, "ormqr_blocked_dev")
+
+
+def reflector_apply_right_dev(dA: int, m: int, n: int, lda: int, dx: int, lenx: int, tau, stream: int = 0,
+                              dtype=np.float64) -> None:
+    t = np.array([tau], dtype=dtype)
+    rc = _fn("reflector_apply_right_dev", dtype)(C.c_void_p(dA), _I64(m), _I64(n), _I64(lda), C.c_void_p(dx), _I64(lenx),
+                                                 _ptr(t), C.c_void_p(stream))
+    _check(rc, "reflector_apply_right_dev")
+
+
 def chol_recursive_dev(dA: int, n: int, lda: int, dinfo: int, cutoff: int = 1, stream: int = 0,
                        dtype=np.float64) -> None:
     rc = _fn("potrf_recursive_L_dev", dtype)(C.c_void_p(dA), _I64(n), _I64(lda), _I64(cutoff), C.c_void_p(dinfo),

@@ -16,7 +16,8 @@ module GLACuda
 
 using LinearAlgebra
 import GenericLinearAlgebra
-import GenericLinearAlgebra: QR2, HouseholderBlock, qrBlocked!, qrUnblocked!, cholRecursive!, rankUpdate!
+import GenericLinearAlgebra: QR2, HouseholderBlock, qrBlocked!, qrUnblocked!, cholRecursive!, cholBlocked!, cholUnblocked!,
+    rankUpdate!
 
 const libgla = get(ENV, "GLA_CUDA_LIB", "libgla_cuda.so")
 const GLAFloat = Union{Float32,Float64,ComplexF64}
@@ -52,6 +53,8 @@ for T in (Float32, Float64, ComplexF64)
     p = prefix(T)
     geqr = Symbol("gla_", p, "geqr_blocked")
     potrf = Symbol("gla_", p, "potrf_recursive_L")
+    potrf_unb = Symbol("gla_", p, "potrf_unblocked_L")
+    potrf_blk = Symbol("gla_", p, "potrf_blocked_L")
     larft = Symbol("gla_", p, "larft")
     ormqr = Symbol("gla_", p, "ormqr_blocked")
     batched = Symbol("gla_", p, "geqr_batched")
@@ -143,6 +146,25 @@ for T in (Float32, Float64, ComplexF64)
                 (Ptr{$T}, Int64, Int64, Int64), A, n, max(1, stride(A, 2)), cutoff)
             chk(rc, "cholRecursive!")
             return LowerTriangular(A)
+        end
+
+        # ---- cholUnblocked!(A, Val{:L}) / cholBlocked!(A, Val{:L}, blocksize)   replace src/cholesky.jl:3-15, :17-35
+        # (the lower factor is unique: the same device routine; both return A like the reference)
+        function cholUnblocked!(A::Matrix{$T}, ::Type{Val{:L}})
+            n = LinearAlgebra.checksquare(A)
+            rc = GC.@preserve A ccall(
+                ($(QuoteNode(potrf_unb)), libgla), Cint,
+                (Ptr{$T}, Int64, Int64), A, n, max(1, stride(A, 2)))
+            chk(rc, "cholUnblocked!")
+            return A
+        end
+        function cholBlocked!(A::Matrix{$T}, ::Type{Val{:L}}, blocksize::Integer)
+            n = LinearAlgebra.checksquare(A)
+            rc = GC.@preserve A ccall(
+                ($(QuoteNode(potrf_blk)), libgla), Cint,
+                (Ptr{$T}, Int64, Int64, Int64), A, n, max(1, stride(A, 2)), blocksize)
+            chk(rc, "cholBlocked!")
+            return A
         end
 
         # ---- rankUpdate!(Hermitian(C,:L), A, α::Real)      replaces src/juliaBLAS.jl:89-112

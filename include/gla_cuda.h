@@ -82,6 +82,9 @@ GLA_API int gla_zgeqr_blocked_dev(void* dA, int64_t m, int64_t n, int64_t lda, v
 GLA_API int gla_slarft(const float* F, int64_t m, int64_t n, int64_t ldf, const float* tau, float* T, int64_t ldt);
 GLA_API int gla_dlarft(const double* F, int64_t m, int64_t n, int64_t ldf, const double* tau, double* T, int64_t ldt);
 GLA_API int gla_zlarft(const void* F, int64_t m, int64_t n, int64_t ldf, const void* tau, void* T, int64_t ldt);
+GLA_API int gla_slarft_dev(const float* dF, int64_t m, int64_t n, int64_t ldf, const float* dtau, float* dT, int64_t ldt, void* stream);
+GLA_API int gla_dlarft_dev(const double* dF, int64_t m, int64_t n, int64_t ldf, const double* dtau, double* dT, int64_t ldt, void* stream);
+GLA_API int gla_zlarft_dev(const void* dF, int64_t m, int64_t n, int64_t ldf, const void* dtau, void* dT, int64_t ldt, void* stream);
 
 /* ---- block reflector application ---------------------------------------------------
  * replaces lmul!(H, A, M) (adjoint = 0, A <- Q A, src/householder.jl:82-115) and
@@ -91,13 +94,19 @@ GLA_API int gla_zlarft(const void* F, int64_t m, int64_t n, int64_t ldf, const v
 GLA_API int gla_sormqr_blocked(const float* F, int64_t mF, int64_t nF, int64_t ldf, const float* tau, float* A, int64_t mA, int64_t nA, int64_t lda, int adjoint);
 GLA_API int gla_dormqr_blocked(const double* F, int64_t mF, int64_t nF, int64_t ldf, const double* tau, double* A, int64_t mA, int64_t nA, int64_t lda, int adjoint);
 GLA_API int gla_zormqr_blocked(const void* F, int64_t mF, int64_t nF, int64_t ldf, const void* tau, void* A, int64_t mA, int64_t nA, int64_t lda, int adjoint);
+GLA_API int gla_sormqr_blocked_dev(const float* dF, int64_t mF, int64_t nF, int64_t ldf, const float* dtau, float* dA, int64_t mA, int64_t nA, int64_t lda, int adjoint, void* stream);
+GLA_API int gla_dormqr_blocked_dev(const double* dF, int64_t mF, int64_t nF, int64_t ldf, const double* dtau, double* dA, int64_t mA, int64_t nA, int64_t lda, int adjoint, void* stream);
+GLA_API int gla_zormqr_blocked_dev(const void* dF, int64_t mF, int64_t nF, int64_t ldf, const void* dtau, void* dA, int64_t mA, int64_t nA, int64_t lda, int adjoint, void* stream);
 
 /* ---- right reflector application ---------------------------------------------------
  * replaces reflectorApply!(A, x, tau)   src/qr.jl:19-42   A <- A (I - tau v v^H), v = [1; x[2:]]
- * returns -5 when lenx != n (DimensionMismatch at src/qr.jl:21-27). tau passed by pointer. */
+ * returns -6 when lenx != n (DimensionMismatch at src/qr.jl:21-27). tau passed by (host) pointer. */
 GLA_API int gla_sreflector_apply_right(float* A, int64_t m, int64_t n, int64_t lda, const float* x, int64_t lenx, const float* tau);
 GLA_API int gla_dreflector_apply_right(double* A, int64_t m, int64_t n, int64_t lda, const double* x, int64_t lenx, const double* tau);
 GLA_API int gla_zreflector_apply_right(void* A, int64_t m, int64_t n, int64_t lda, const void* x, int64_t lenx, const void* tau);
+GLA_API int gla_sreflector_apply_right_dev(float* dA, int64_t m, int64_t n, int64_t lda, const float* dx, int64_t lenx, const float* tau, void* stream);
+GLA_API int gla_dreflector_apply_right_dev(double* dA, int64_t m, int64_t n, int64_t lda, const double* dx, int64_t lenx, const double* tau, void* stream);
+GLA_API int gla_zreflector_apply_right_dev(void* dA, int64_t m, int64_t n, int64_t lda, const void* dx, int64_t lenx, const void* tau, void* stream);
 
 /* ---- batched small QR --------------------------------------------------------------
  * `batch` independent qrBlocked! problems (src/qr.jl:113-146 per matrix); matrices are
@@ -144,6 +153,26 @@ GLA_API int gla_zpotrf_recursive_L(void* A, int64_t n, int64_t lda, int64_t cuto
 GLA_API int gla_spotrf_recursive_L_dev(float* dA, int64_t n, int64_t lda, int64_t cutoff, int* dinfo, void* stream);
 GLA_API int gla_dpotrf_recursive_L_dev(double* dA, int64_t n, int64_t lda, int64_t cutoff, int* dinfo, void* stream);
 GLA_API int gla_zpotrf_recursive_L_dev(void* dA, int64_t n, int64_t lda, int64_t cutoff, int* dinfo, void* stream);
+/* replace cholUnblocked!(A, Val{:L})   src/cholesky.jl:3-15   and   cholBlocked!(A, Val{:L}, blocksize)
+ * src/cholesky.jl:17-35.  The lower Cholesky factor is unique, so on the GPU they are the same computation as
+ * cholRecursive! (the reference's three variants differ in loop order only); `blocksize` >= 1 is a hint. */
+GLA_API int gla_spotrf_unblocked_L(float* A, int64_t n, int64_t lda);
+GLA_API int gla_dpotrf_unblocked_L(double* A, int64_t n, int64_t lda);
+GLA_API int gla_zpotrf_unblocked_L(void* A, int64_t n, int64_t lda);
+GLA_API int gla_spotrf_blocked_L(float* A, int64_t n, int64_t lda, int64_t blocksize);
+GLA_API int gla_dpotrf_blocked_L(double* A, int64_t n, int64_t lda, int64_t blocksize);
+GLA_API int gla_zpotrf_blocked_L(void* A, int64_t n, int64_t lda, int64_t blocksize);
+
+/* ---- workspace query ------------------------------------------------------------------
+ * the reference's FFI precedent asks LAPACK for its workspace before the call (src/lapack.jl:152-170,
+ * :514-553); here the library owns its temporaries (stream-ordered pool), and this reports how many
+ * device bytes the `_dev` call of `op` on an m x n problem (n x n for potrf, batch ignored) will take
+ * from the pool, so that a host can size its own allocations around it.  <0: illegal argument. */
+#define GLA_OP_GEQR_BLOCKED 1
+#define GLA_OP_POTRF_L 2
+#define GLA_OP_GEQR_BATCHED 3
+#define GLA_OP_TSQR 4
+GLA_API int64_t gla_workspace_query(int op, int elem_bytes, int64_t m, int64_t n);
 
 /* ---- Hermitian rank-k update, lower ---------------------------------------------------
  * replaces rankUpdate!(Hermitian(C,:L), A, alpha)   src/juliaBLAS.jl:89-112

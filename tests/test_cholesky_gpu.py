@@ -100,3 +100,32 @@ def test_rank_update_lower(gla, oracle, dtype, n, k):
         assert np.array_equal(np.triu(got, 1), np.triu(Cm, 1))
         full = Cm + alpha * (B @ B.conj().T)
         assert np.max(np.abs(np.tril(got) - np.tril(full))) <= TOL[dtype] * 10 * np.max(np.abs(full))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex128])
+def test_unblocked_and_blocked_entry_points(gla, oracle, dtype):
+    """cholUnblocked!(A, Val{:L}) (src/cholesky.jl:3-15) and cholBlocked!(A, Val{:L}, blocksize) (:17-35) against their
+    own restatements in the oracle; the strict upper triangle stays untouched, as in the reference."""
+    rng = np.random.default_rng(17)
+    for n, bs in ((50, 7), (130, 16), (257, 64)):
+        S = _spd(rng, n, dtype, shift=float(n))
+        for got, ref in ((gla.cholUnblocked_(S.copy(order="F")), oracle.chol_unblocked(S)),
+                         (gla.cholBlocked_(S.copy(order="F"), "L", bs), oracle.chol_blocked(S, bs))):
+            scale = np.max(np.abs(ref))
+            assert np.max(np.abs(np.tril(got) - np.tril(ref))) <= TOL[dtype] * scale * max(n, 10)
+            assert np.array_equal(np.triu(got, 1), np.triu(S, 1))
+    with pytest.raises(gla.ArgumentError):
+        gla.cholBlocked_(np.asfortranarray(np.eye(4)), "L", 0)
+
+
+def test_panel_path_matches_recursion_bitwise_shape(gla, oracle):
+    """Float64 above the look-ahead threshold of the right-looking driver (n > 384) and above its 256-row outer block
+    (n > 6144 is too slow for the oracle here, so 1000 and 2500): parity with the oracle at ragged sizes."""
+    rng = np.random.default_rng(5)
+    for n in (449, 1000, 2500):
+        X = rng.standard_normal((n, n))
+        S = np.asfortranarray(X.T @ X + n * np.eye(n))
+        got = gla.cholRecursive_(S.copy(order="F"))
+        ref = oracle.chol_recursive(S, 1, mt=True)
+        assert np.max(np.abs(np.tril(got) - np.tril(ref))) <= 1e-11 * np.max(np.abs(ref))
+        assert np.array_equal(np.triu(got, 1), np.triu(S, 1))

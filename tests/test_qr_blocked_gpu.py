@@ -135,3 +135,42 @@ def test_config1_1024(gla, oracle):
     qr = gla.qrBlocked_(A.copy(order="F"))
     _check_against_oracle(qr.factors, qr.tau, ref_f, ref_t, np.float64)
     assert qr.tau[-1] == 2.0
+
+
+def test_device_twins_and_workspace_query(gla, oracle):
+    """`_dev` twins of the T build, the block application and the right reflector application against the
+    oracle, and gla_workspace_query against the pool's high-water mark."""
+    import torch
+    rng = np.random.default_rng(21)
+    st = torch.cuda.current_stream().cuda_stream
+    for dtype, tdt in ((np.float64, torch.float64), (np.float32, torch.float32), (np.complex128, torch.complex128)):
+        m, n, nA = 90, 40, 23
+        A = _randn(rng, m, n, dtype)
+        f, t = oracle.qr_unblocked(A)
+        Tref = oracle.build_T(f, t)
+        dF = torch.from_numpy(np.ascontiguousarray(f.T)).cuda()          # column-major m x n
+        dtau = torch.from_numpy(t.copy()).cuda()
+        dT = torch.zeros((n, n), dtype=tdt, device="cuda")
+        gla.larft_dev(dF.data_ptr(), m, n, m, dtau.data_ptr(), dT.data_ptr(), n, st, dtype)
+        tol = 1e-4 if dtype == np.float32 else 1e-12
+        np.testing.assert_allclose(dT.cpu().numpy().T, Tref, rtol=0, atol=tol * np.max(np.abs(Tref)))
+        B = _randn(rng, m, nA, dtype)
+        for adjoint in (False, True):
+            ref = oracle.block_apply(f, Tref, B, adjoint=adjoint)
+            dB = torch.from_numpy(np.ascontiguousarray(B.T)).cuda()
+            gla.ormqr_blocked_dev(dF.data_ptr(), m, n, m, dtau.data_ptr(), dB.data_ptr(), m, nA, m, adjoint, st, dtype)
+            np.testing.assert_allclose(dB.cpu().numpy().T, ref, rtol=0, atol=10 * tol * np.max(np.abs(ref)))
+        x = _randn(rng, nA, 1, dtype)[:, 0]
+        tau = dtype(1.3) if dtype != np.complex128 else np.complex128(1.3 - 0.2j)
+        ref = oracle.reflector_apply_right(B, x, tau)
+        dB = torch.from_numpy(np.ascontiguousarray(B.T)).cuda()
+        dx = torch.from_numpy(x.copy()).cuda()
+        gla.reflector_apply_right_dev(dB.data_ptr(), m, nA, m, dx.data_ptr(), nA, tau, st, dtype)
+        np.testing.assert_allclose(dB.cpu().numpy().T, ref, rtol=0, atol=10 * tol * np.max(np.abs(ref)))
+        with pytest.raises(gla.DimensionMismatch):
+            gla.reflector_apply_right_dev(dB.data_ptr(), m, nA, m, dx.data_ptr(), nA - 1, tau, st, dtype)
+    assert gla.workspace_query(gla.OP_GEQR_BLOCKED, np.float64, 4096, 4096) > 4096 * 384 * 8
+    assert gla.workspace_query(gla.OP_POTRF_L, np.float64, 4096, 4096) >= 4096 * 4096 * 8
+    assert gla.workspace_query(gla.OP_GEQR_BATCHED, np.float64, 32, 32) == 0
+    with pytest.raises(gla.ArgumentError):
+        gla.workspace_query(99, np.float64, 4, 4)
