@@ -243,6 +243,172 @@ __global__ void __launch_bounds__(DmmaCfg<BM, BN, STAGES>::THREADS, 2)
   }
 }
 
+// ------------------------------------------------------------------------------- Float32 on the tensor pipe (3xTF32)
+// Same TMA / mbarrier ring as the Float64 kernel, K slabs of 32 floats (the 128 B swizzle span); the warps issue
+// mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 (SASS HMMA.1688.F32.TF32) on 32 x 32 warp tiles.  TF32 keeps 10
+// mantissa bits, so every operand is split IN REGISTERS into hi = rna_tf32(x) and lo = rna_tf32(x - hi) and a product is
+// accumulated as lo*hi + hi*lo + hi*hi (small terms first): Float32-level accuracy (the dropped lo*lo term is 2^-22
+// relative) at a third of the TF32 rate, with no extra pass over the operands in memory.  tcgen05 kind::tf32 would
+// read the fragments from shared memory directly and so would need the split tiles materialised there; see DESIGN.md.
+// Fragment addressing: tile row r holds 32 consecutive k as eight 16-byte chunks, chunk c at c ^ (r & 7).  MMA row g of
+// a 16-row block is tile row base + g (+8), so r & 7 = g and the eight rows a quarter-warp... the 32 lanes of one
+// LDS.32 (8 rows x 4 consecutive words of one chunk each) hit 32 distinct banks.
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return u;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <int BM, int BN, int STAGES>
+__global__ void __launch_bounds__(DmmaCfg<BM, BN, STAGES>::THREADS, 2)
+    gemm_tn_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                          float* __restrict__ C, i64 ldc, int M, int N, int K, int klen, i64 split_stride, float alpha,
+                          int beta_one, int lower_only) {
+  using Cfg = DmmaCfg<BM, BN, STAGES>;   // same tile bookkeeping: 128 B per tile row and stage
+  constexpr int WM = Cfg::WM, NCW = Cfg::NCW;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* sA = base;
+  unsigned char* sB = base + STAGES * BM * 128;
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  if (lower_only == 1 && n0 >= m0 + BM) return;
+  if (lower_only == 2 && m0 >= n0 + BN) return;
+  const int kbeg = blockIdx.z * klen;
+  const int kend = (kbeg + klen < K) ? kbeg + klen : K;
+  const int nk = (kend - kbeg + 31) >> 5;
+  const bool producer = threadIdx.x == 0;
+
+  if (producer) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], NCW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int it = 0; it < STAGES && it < nk; ++it) {
+      mbar_expect_tx(&full[it], Cfg::STAGE_BYTES);
+      tma_load_2d(sA + it * BM * 128, &tmA, kbeg + it * 32, m0, &full[it]);
+      tma_load_2d(sB + it * BN * 128, &tmB, kbeg + it * 32, n0, &full[it]);
+    }
+  }
+  const int wm = warp % WM, wn = warp / WM;
+  const int g = lane >> 2, t = lane & 3;
+  float acc[2][4][4];
+#pragma unroll
+  for (int P = 0; P < 2; ++P)
+#pragma unroll
+    for (int Q = 0; Q < 4; ++Q)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[P][Q][e] = 0.f;
+  __syncthreads();  // barrier inits visible to all consumers
+
+  const uint32_t sA_u32 = smem_u32(sA), sB_u32 = smem_u32(sB);
+  for (int it = 0; it < nk; ++it) {
+    const int s = it % STAGES;
+    if (producer && it >= 1 && it - 1 + STAGES < nk) {
+      const int ps = (it - 1) % STAGES;
+      mbar_wait(&empty[ps], ((it - 1) / STAGES) & 1);
+      mbar_expect_tx(&full[ps], Cfg::STAGE_BYTES);
+      tma_load_2d(sA + ps * BM * 128, &tmA, kbeg + (it - 1 + STAGES) * 32, m0, &full[ps]);
+      tma_load_2d(sB + ps * BN * 128, &tmB, kbeg + (it - 1 + STAGES) * 32, n0, &full[ps]);
+    }
+    __syncwarp();
+    mbar_wait(&full[s], (it / STAGES) & 1);
+    const uint32_t pa = sA_u32 + s * BM * 128 + (wm * 32 + g) * 128 + 4 * t;
+    const uint32_t pb = sB_u32 + s * BN * 128 + (wn * 32 + g) * 128 + 4 * t;
+    // The tensor pipe adds into its accumulator with truncation (a bias that grows linearly with the number of chained
+    // MMAs: 1.3e-4 on the Gram probe of a 16384^2 factorisation, K up to 16384, against 2.5e-6 for FFMA).  So the MMAs of
+    // ONE slab (12 per block) chain into a fresh accumulator, which is then added to the running sum with a rounded FADD.
+    float part[2][4][4];
+#pragma unroll
+    for (int P = 0; P < 2; ++P)
+#pragma unroll
+      for (int Q = 0; Q < 4; ++Q)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) part[P][Q][e] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {   // four k-steps of 8 inside the slab
+      const uint32_t c0 = (uint32_t)(((2 * j) ^ g) << 4), c1 = (uint32_t)(((2 * j + 1) ^ g) << 4);
+      uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+      for (int P = 0; P < 2; ++P) {
+        float v[4];
+        v[0] = lds_f32(pa + (16 * P) * 128 + c0);        // (row g,     k = t)
+        v[1] = lds_f32(pa + (16 * P + 8) * 128 + c0);    // (row g + 8, k = t)
+        v[2] = lds_f32(pa + (16 * P) * 128 + c1);        // (row g,     k = t + 4)
+        v[3] = lds_f32(pa + (16 * P + 8) * 128 + c1);    // (row g + 8, k = t + 4)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          ah[P][e] = tf32_rna(v[e]);
+          al[P][e] = tf32_rna(v[e] - __uint_as_float(ah[P][e]));
+        }
+      }
+#pragma unroll
+      for (int Q = 0; Q < 4; ++Q) {
+        float v[2];
+        v[0] = lds_f32(pb + (8 * Q) * 128 + c0);         // (k = t,     n = g)
+        v[1] = lds_f32(pb + (8 * Q) * 128 + c1);         // (k = t + 4, n = g)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          bh[Q][e] = tf32_rna(v[e]);
+          bl[Q][e] = tf32_rna(v[e] - __uint_as_float(bh[Q][e]));
+        }
+      }
+#pragma unroll
+      for (int P = 0; P < 2; ++P)
+#pragma unroll
+        for (int Q = 0; Q < 4; ++Q) {
+          mma_tf32(part[P][Q], al[P], bh[Q]);
+          mma_tf32(part[P][Q], ah[P], bl[Q]);
+          mma_tf32(part[P][Q], ah[P], bh[Q]);
+        }
+    }
+#pragma unroll
+    for (int P = 0; P < 2; ++P)
+#pragma unroll
+      for (int Q = 0; Q < 4; ++Q)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[P][Q][e] += part[P][Q][e];
+    release_fence();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
+
+  // ---- epilogue: lane owns (i, j), (i, j + 1), (i + 8, j), (i + 8, j + 1) of every 16 x 8 block
+  float* Cz = C + (i64)blockIdx.z * split_stride;
+#pragma unroll
+  for (int P = 0; P < 2; ++P)
+#pragma unroll
+    for (int Q = 0; Q < 4; ++Q)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = m0 + wm * 32 + 16 * P + g + 8 * (e >> 1);
+        const int j = n0 + wn * 32 + 8 * Q + 2 * t + (e & 1);
+        if (i >= M || j >= N) continue;
+        if (lower_only == 1 && i < j) continue;
+        if (lower_only == 2 && i > j) continue;
+        float* p = Cz + (i64)j * ldc + i;
+        const float v = alpha * acc[P][Q][e];
+        *p = beta_one ? __ldcg(p) + v : v;
+      }
+}
+
 // ------------------------------------------------------------------------------- ComplexF64 on the DMMA pipe
 // C(i,j) = sum_k op(At(k,i)) B(k,j) for interleaved complex operands, computed as TWO real contractions over the
 // 2K interleaved doubles of each operand row (the tile a TMA box delivers IS that real row):
@@ -507,20 +673,20 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-// K x R column-major f64 operand (K contiguous), box = 16 x rows
-int make_map(CUtensorMap* tm, const double* base, i64 K, i64 R, i64 ld, int box_rows) {
+// K x R column-major operand (K contiguous), box = one 128-byte swizzle span of K (16 doubles / 32 floats) x rows
+int make_map_t(CUtensorMap* tm, const void* base, i64 K, i64 R, i64 ld, int box_rows, int elem_bytes) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error(GLA_ERR_DRIVER, "cuTensorMapEncodeTiled entry point unavailable", __FILE__, __LINE__);
     return GLA_ERR_DRIVER;
   }
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)R};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
-  cuuint32_t box[2] = {16, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * elem_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(tm, elem_bytes == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char msg[128];
     snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled failed (CUresult %d, K=%lld R=%lld ld=%lld)", (int)r,
@@ -529,6 +695,30 @@ int make_map(CUtensorMap* tm, const double* base, i64 K, i64 R, i64 ld, int box_
     return GLA_ERR_DRIVER;
   }
   return 0;
+}
+int make_map(CUtensorMap* tm, const double* base, i64 K, i64 R, i64 ld, int box_rows) {
+  return make_map_t(tm, base, K, R, ld, box_rows, 8);
+}
+
+template <int BM, int BN, int STAGES>
+int launch_tf32x3(const GemmTN<float>& g, int klen, cudaStream_t st) {
+  using Cfg = DmmaCfg<BM, BN, STAGES>;
+  CUtensorMap tmA, tmB;
+  GLA_TRY(make_map_t(&tmA, g.At, g.K, g.M, g.ldat, BM, 4));
+  GLA_TRY(make_map_t(&tmB, g.B, g.K, g.N, g.ldb, BN, 4));
+  auto kern = gemm_tn_tf32x3_kernel<BM, BN, STAGES>;
+  GLA_TRY(ensure_dyn_smem((const void*)kern, (int)(Cfg::SMEM)));
+  dim3 grid((unsigned)ceil_div(g.M, BM), (unsigned)ceil_div(g.N, BN), (unsigned)g.nsplit);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmA, tmB, g.C, g.ldc, (int)g.M, (int)g.N, (int)g.K, klen, g.split_stride,
+                                              g.alpha, g.nsplit > 1 ? 0 : g.beta_one, g.lower_only);
+  GLA_CUDA(cudaGetLastError());
+  return 0;
+}
+
+bool tma_ok_f32(const GemmTN<float>& g) {
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return al(g.At) && al(g.B) && (g.ldat & 3) == 0 && (g.ldb & 3) == 0 && g.K >= 1 && g.M < (1ll << 31) &&
+         g.N < (1ll << 31) && g.K < (1ll << 31) && g.ldat * 4 < (1ll << 40) && g.ldb * 4 < (1ll << 40);
 }
 
 template <int BM, int BN, int STAGES>
@@ -619,7 +809,17 @@ int gemm_tn<double>(const GemmTN<double>& g, cudaStream_t st) {
 template <>
 int gemm_tn<float>(const GemmTN<float>& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return 0;
-  return launch_fma<float>(g, slice_len(g.K > 0 ? g.K : 1, g.nsplit), st);
+  i64 klen = ((g.K > 0 ? g.K : 1) + g.nsplit - 1) / g.nsplit;
+  klen = (klen + 31) / 32 * 32;   // K slabs of 32 floats: slices must not share a slab
+  static const bool force_fma = getenv("GLA_SGEMM_FMA") != nullptr;   // A/B switch
+  if (!force_fma && g.K > 0 && tma_ok_f32(g)) {
+    if (g.M <= 64) {
+      if ((i64)ceil_div(g.N, 128) * g.nsplit * 2 < sm_count()) return launch_tf32x3<64, 32, 4>(g, (int)klen, st);
+      return launch_tf32x3<64, 128, 4>(g, (int)klen, st);
+    }
+    return launch_tf32x3<128, 64, 4>(g, (int)klen, st);
+  }
+  return launch_fma<float>(g, (int)klen, st);
 }
 template <int BM, int BN, int STAGES>
 static int launch_zdmma(const GemmTN<zd>& g, int klen, cudaStream_t st) {

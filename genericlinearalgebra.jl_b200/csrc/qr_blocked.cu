@@ -655,7 +655,7 @@ struct QrWork {
   // total_only != nullptr: size computation only (gla_workspace_query), nothing is allocated
   int alloc(i64 m, i64 nA0, i64 nA1, int nbuf, cudaStream_t stream, i64* total_only = nullptr) {
     st = stream;
-    ldv = round_up(m, 2);
+    ldv = round_up(m, 4);   // 16-byte aligned columns for Float32 as well (TMA operands)
     auto al = [](i64 bytes) { return round_up(bytes, 256); };
     const i64 s_v = al(ldv * NBO * sizeof(T));
     const i64 s_vt = al((i64)NBO * m * sizeof(T));
