@@ -386,7 +386,28 @@ def main():
     e2e_value = world * batch * e2e_steps / el.item()
     h2d = batch * 8192
     d2h = batch * (8192 + 256)
-    del hA, ht
+    # the ceiling of that path on this box: raw pinned copies in both directions at once (PCIe is full duplex), all ranks
+    # together; e2e cannot exceed bytes / these rates whatever the kernel does
+    nb = min(1 << 31, batch * 8192)
+    dbuf_in = torch.empty(nb, dtype=torch.uint8, device=dev)
+    dbuf_out = torch.empty(nb, dtype=torch.uint8, device=dev)
+    hin = hA.view(torch.uint8).reshape(-1)[:nb]
+    hout = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            dbuf_in.copy_(hin, non_blocking=True)
+        with torch.cuda.stream(s2):
+            hout.copy_(dbuf_out, non_blocking=True)
+    torch.cuda.synchronize()
+    tc = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+    duplex_gbs = 3 * nb / tc.item() / 1e9            # per direction, per rank, with every rank copying
+    e2e_ceiling = world * batch / (max(h2d, d2h) / (duplex_gbs * 1e9))
+    del hA, ht, dbuf_in, dbuf_out, hout
     torch.cuda.empty_cache()
 
     other = {}
@@ -405,7 +426,9 @@ def main():
                    "l2": f"inputs larger than L2: every timed step factorises a fresh 8.6 GB slab ({nslab} slabs resident)",
                    "seed": 123},
         "e2e": {"value": e2e_value, "unit": "matrices/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "api": "gla_dgeqr_batched (host pointers, pinned)"},
+                "steps": e2e_steps, "api": "gla_dgeqr_batched (host pointers, pinned)",
+                "pcie_duplex_gbs_per_direction_per_gpu": duplex_gbs, "pcie_ceiling_matrices_per_s": e2e_ceiling,
+                "frac_of_pcie_ceiling": e2e_value / e2e_ceiling},
         "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak,
@@ -473,12 +496,17 @@ def other_configs(g, torch, dist, dev, rank, world, stream, cpu=False):
             return dict({"bound": "tensor", "achieved": tf, "unit": "TFLOP/s", "frac": tf / FP64_TENSOR_PEAK_TFLOPS}, **peak_note)
 
         def e2e_qr(n, dt, npdt):
+            """host-pointer gla_*geqr_blocked on a pinned matrix: H2D + factorisation + D2H, second call (workspace pool warm)"""
             hA = torch.empty((n, n), dtype=dt, pin_memory=True)
-            hA.copy_(torch.randn((n, n), device=dev, dtype=dt))
             htau = torch.empty(n, dtype=dt, pin_memory=True)
-            t0 = time.perf_counter()
-            g.qr_blocked_ptr(hA.data_ptr(), n, n, n, htau.data_ptr(), 0, npdt)
-            return (time.perf_counter() - t0) * 1e3
+            best = 1e30
+            for _ in range(2):
+                hA.copy_(torch.randn((n, n), device=dev, dtype=dt))
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                g.qr_blocked_ptr(hA.data_ptr(), n, n, n, htau.data_ptr(), 0, npdt)
+                best = min(best, (time.perf_counter() - t0) * 1e3)
+            return best
 
         # metric part 1: FP64 qrBlocked! n = 16384
         n = 16384
@@ -538,7 +566,8 @@ def other_configs(g, torch, dist, dev, rank, world, stream, cpu=False):
             dA.copy_(src)
             ms, _ = _time(torch, lambda: g.qr_blocked_dev(dA.data_ptr(), n, n, n, stau.data_ptr(), 0, stream, np.float32), reps=1)
             best = min(best, ms)
-        out["qr_f32_n16384"] = {"ms": best, "tflops": 4.0 / 3.0 * n ** 3 / (best * 1e-3) / 1e12, "unit": "TFLOP/s (Float32)"}
+        out["qr_f32_n16384"] = {"ms": best, "tflops": 4.0 / 3.0 * n ** 3 / (best * 1e-3) / 1e12, "unit": "TFLOP/s (Float32)",
+                                "contraction": "TMA-fed 3xTF32 mma.sync (HMMA.1688.F32.TF32) with per-slab accumulators"}
         if oracle is not None:
             out["qr_f32_n16384"]["oracle_leading_panel"] = _panel_check(np, torch, oracle, (dA, stau), src, 128, False)
         del src, dA, stau
@@ -553,7 +582,6 @@ def other_configs(g, torch, dist, dev, rank, world, stream, cpu=False):
             ms, _ = _time(torch, lambda: g.qr_blocked_dev(dA.data_ptr(), n, n, n, dtau.data_ptr(), 0, stream), reps=1)
             best = min(best, ms)
         tf = 4.0 / 3.0 * n ** 3 / (best * 1e-3) / 1e12
-        e2e_qr(n, torch.float64, np.float64)
         out["qr_f64_n1024"] = {"ms": best, "tflops": tf, "roofline": roof(tf), "e2e_ms": e2e_qr(n, torch.float64, np.float64)}
         # config 2: Cholesky n = 4096
         n = 4096
@@ -570,10 +598,13 @@ def other_configs(g, torch, dist, dev, rank, world, stream, cpu=False):
         L = torch.tril(dS.t())
         resid = ((L @ L.t() - S).norm() / S.norm()).item()
         hS = torch.empty((n, n), dtype=torch.float64, pin_memory=True)
-        hS.copy_(S)
-        t0 = time.perf_counter()
-        g.cholRecursive_(hS.numpy().T)     # a pinned host matrix through the host-pointer ABI (symmetric: layout is immaterial)
-        e2e = (time.perf_counter() - t0) * 1e3
+        e2e = 1e30
+        for _ in range(2):
+            hS.copy_(S)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            g.cholRecursive_(hS.numpy().T)     # a pinned host matrix through the host-pointer ABI (symmetric: layout is immaterial)
+            e2e = min(e2e, (time.perf_counter() - t0) * 1e3)
         out["chol_f64_n4096"] = {"ms": best, "tflops": tf, "info": int(info.item()), "residual": resid, "roofline": roof(tf),
                                  "e2e_ms": e2e}
         del X, S, dS, L, hS

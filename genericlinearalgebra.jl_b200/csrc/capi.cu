@@ -11,14 +11,15 @@ using namespace gla;
 
 namespace {
 
-struct DevBuf {
+struct DevBuf {   // device buffer from the library's stream-ordered pool, tied to the stream of the call
   void* p = nullptr;
+  cudaStream_t s = nullptr;
   ~DevBuf() {
-    if (p) cudaFree(p);
+    if (p) cudaFreeAsync(p, s);
   }
-  int alloc(size_t bytes) {
-    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
-    return check_cuda(e, __FILE__, __LINE__);
+  int alloc(size_t bytes, cudaStream_t st) {
+    s = st;
+    return pool_malloc(&p, bytes, st);
   }
   template <class T>
   T* as() {
@@ -88,14 +89,13 @@ int geqr_batched_host(T* A, i64 m, i64 n, i64 batch, T* tau) {
       if (p) cudaFreeAsync(p, s);
     }
   } dA[NS], dtau[NS];
-  (void)sm_count();
   const int ns_cap = want_ns < 1 ? 1 : (want_ns > NS ? NS : want_ns);
   int ns = (int)((batch + chunk - 1) / chunk < ns_cap ? (batch + chunk - 1) / chunk : ns_cap);
   for (int s = 0; s < ns; ++s) {
     GLA_TRY(st[s].create());
     dA[s].s = dtau[s].s = st[s].s;
-    GLA_CUDA(cudaMallocAsync(&dA[s].p, chunk * mat_bytes, st[s].s));
-    GLA_CUDA(cudaMallocAsync(&dtau[s].p, chunk * k * sizeof(T), st[s].s));
+    GLA_TRY(pool_malloc(reinterpret_cast<void**>(&dA[s].p), chunk * mat_bytes, st[s].s));
+    GLA_TRY(pool_malloc(reinterpret_cast<void**>(&dtau[s].p), chunk * k * sizeof(T), st[s].s));
   }
   i64 done = 0;
   int it = 0;
@@ -124,7 +124,7 @@ struct DevMatrix {
   T* p() { return buf.as<T>(); }
   int upload(const T* h, i64 ldh, i64 m, i64 n, cudaStream_t st) {
     ld = round_up(m > 0 ? m : 1, 16 / sizeof(T) > 2 ? 16 / sizeof(T) : 2);
-    GLA_TRY(buf.alloc((size_t)ld * (n > 0 ? n : 1) * sizeof(T)));
+    GLA_TRY(buf.alloc((size_t)ld * (n > 0 ? n : 1) * sizeof(T), st));
     return h2d_matrix<T>(p(), ld, h, ldh, m, n, st);
   }
   int download(T* h, i64 ldh, i64 m, i64 n, cudaStream_t st) { return d2h_matrix<T>(h, ldh, p(), ld, m, n, st); }
@@ -144,7 +144,7 @@ int geqr_blocked_host(T* A, i64 m, i64 n, i64 lda, T* tau, i64 hint) {
   DevMatrix<T> dA;
   DevBuf dtau;
   GLA_TRY(dA.upload(A, lda, m, n, st.s));
-  GLA_TRY(dtau.alloc(k * sizeof(T)));
+  GLA_TRY(dtau.alloc(k * sizeof(T), st.s));
   GLA_CUDA(cudaMemsetAsync(dtau.p, 0, k * sizeof(T), st.s));
   Event e0, e1;
   GLA_TRY(e0.create());
@@ -177,10 +177,10 @@ int larft_host(const T* F, i64 m, i64 n, i64 ldf, const T* tau, T* Tm, i64 ldt) 
   DevMatrix<T> dF, dT;
   DevBuf dtau;
   GLA_TRY(dF.upload(F, ldf, m, n, st.s));
-  GLA_TRY(dtau.alloc(k * sizeof(T)));
+  GLA_TRY(dtau.alloc(k * sizeof(T), st.s));
   GLA_CUDA(cudaMemcpyAsync(dtau.p, tau, k * sizeof(T), cudaMemcpyHostToDevice, st.s));
   dT.ld = round_up(k, 2);
-  GLA_TRY(dT.buf.alloc((size_t)dT.ld * k * sizeof(T)));
+  GLA_TRY(dT.buf.alloc((size_t)dT.ld * k * sizeof(T), st.s));
   GLA_TRY(larft_dev<T>(dF.p(), m, n, dF.ld, dtau.as<T>(), dT.p(), dT.ld, st.s));
   GLA_TRY(dT.download(Tm, ldt, k, k, st.s));
   GLA_CUDA(cudaStreamSynchronize(st.s));
@@ -206,7 +206,7 @@ int ormqr_host(const T* F, i64 mF, i64 nF, i64 ldf, const T* tau, T* A, i64 mA, 
   DevBuf dtau;
   GLA_TRY(dF.upload(F, ldf, mF, nF, st.s));
   GLA_TRY(dA.upload(A, lda, mA, nA, st.s));
-  GLA_TRY(dtau.alloc(k * sizeof(T)));
+  GLA_TRY(dtau.alloc(k * sizeof(T), st.s));
   GLA_CUDA(cudaMemcpyAsync(dtau.p, tau, k * sizeof(T), cudaMemcpyHostToDevice, st.s));
   GLA_TRY(ormqr_blocked_dev<T>(dF.p(), mF, nF, dF.ld, dtau.as<T>(), dA.p(), mA, nA, dA.ld, adjoint, st.s));
   GLA_TRY(dA.download(A, lda, mA, nA, st.s));
@@ -229,7 +229,7 @@ int reflector_apply_right_host(T* A, i64 m, i64 n, i64 lda, const T* x, i64 lenx
   DevMatrix<T> dA;
   DevBuf dx;
   GLA_TRY(dA.upload(A, lda, m, n, st.s));
-  GLA_TRY(dx.alloc(n * sizeof(T)));
+  GLA_TRY(dx.alloc(n * sizeof(T), st.s));
   GLA_CUDA(cudaMemcpyAsync(dx.p, x, n * sizeof(T), cudaMemcpyHostToDevice, st.s));
   GLA_TRY(reflector_apply_right_dev<T>(dA.p(), m, n, dA.ld, dx.as<T>(), *tau, st.s));
   GLA_TRY(dA.download(A, lda, m, n, st.s));
@@ -248,7 +248,7 @@ int potrf_host(T* A, i64 n, i64 lda, i64 cutoff) {
   DevMatrix<T> dA;
   DevBuf dinfo;
   GLA_TRY(dA.upload(A, lda, n, n, st.s));
-  GLA_TRY(dinfo.alloc(sizeof(int)));
+  GLA_TRY(dinfo.alloc(sizeof(int), st.s));
   Event e0, e1;
   GLA_TRY(e0.create());
   GLA_TRY(e1.create());
@@ -301,7 +301,7 @@ int tsqr_host(const double* A, i64 m, i64 n, i64 lda, double* R, i64 ldr) {
   DevMatrix<double> dA, dR;
   GLA_TRY(dA.upload(A, lda, m, n, st.s));
   dR.ld = n;
-  GLA_TRY(dR.buf.alloc((size_t)n * n * sizeof(double)));
+  GLA_TRY(dR.buf.alloc((size_t)n * n * sizeof(double), st.s));
   GLA_TRY(tsqr_local_dev(dA.p(), m, n, dA.ld, dR.p(), n, st.s));
   GLA_TRY(dR.download(R, ldr, n, n, st.s));
   GLA_CUDA(cudaStreamSynchronize(st.s));

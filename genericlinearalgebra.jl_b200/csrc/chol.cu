@@ -630,7 +630,7 @@ int potrf_recursive_L_dev(T* dA, i64 n, i64 lda, i64 /*cutoff*/, int* dinfo, cud
   const i64 nblk = (n + CB - 1) / CB;
   void* block = nullptr;
   const i64 wbytes = round_up(cx.ldw * n * sizeof(T), 256);
-  GLA_CUDA(cudaMallocAsync(&block, wbytes + nblk * CB * CB * sizeof(T), st));
+  GLA_TRY(pool_malloc(reinterpret_cast<void**>(&block), wbytes + nblk * CB * CB * sizeof(T), st));
   cx.W = static_cast<T*>(block);
   cx.Uinv = reinterpret_cast<T*>(static_cast<char*>(block) + wbytes);
   dim3 tb(32, 8), grid((unsigned)ceil_div(n, 32), (unsigned)ceil_div(n, 32));
@@ -657,7 +657,7 @@ int herk_lower_dev(T* dC, i64 n, i64 ldc, const T* dA, i64 k, i64 lda, typename 
   if (n == 0 || k == 0) return 0;
   const i64 ldp = round_up(k, 16);
   T* P = nullptr;
-  GLA_CUDA(cudaMallocAsync(&P, (size_t)ldp * n * sizeof(T), st));
+  GLA_TRY(pool_malloc(reinterpret_cast<void**>(&P), (size_t)ldp * n * sizeof(T), st));
   dim3 tb(32, 8), grid((unsigned)ceil_div(n, 32), (unsigned)ceil_div(k, 32));
   conj_transpose_kernel<T><<<grid, tb, 0, st>>>(dA, lda, (int)n, (int)k, P, ldp);
   int rc = check_cuda(cudaGetLastError(), __FILE__, __LINE__);

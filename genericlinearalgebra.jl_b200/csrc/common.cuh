@@ -163,6 +163,8 @@ inline int ceil_div(i64 a, i64 b) { return (int)((a + b - 1) / b); }
 inline i64 round_up(i64 a, i64 b) { return (a + b - 1) / b * b; }
 
 int sm_count();  // of the current device (cached)
+// stream-ordered allocation from the library-owned pool of the current device; release with cudaFreeAsync
+int pool_malloc(void** p, size_t bytes, cudaStream_t st);
 // High-priority side stream + four timing-free events for the look-ahead schedules (blocked QR, Cholesky), created once
 // per (host thread, device) and reused by every call: work is stream-ordered, so consecutive asynchronous calls of one
 // thread may share them.  Released when the thread exits.

@@ -38,16 +38,39 @@ int sm_count() {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
     cached[dev] = n;
     have[dev] = true;
-    // keep freed workspace in the stream-ordered pool instead of returning it to the driver at every
-    // synchronisation (the default release threshold of 0 makes each call pay a fresh cudaMalloc)
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      unsigned long long thr = ~0ull;
-      (void)cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-    }
     (void)cudaGetLastError();
   }
   return cached[dev];
+}
+
+// Library-owned stream-ordered memory pool (one per device): workspace freed with cudaFreeAsync stays in THIS pool
+// (release threshold = max) instead of going back to the driver at every synchronisation, and the process-wide default
+// pool -- shared with whatever else lives in the host process (Julia's CUDA.jl, torch) -- is left untouched.
+int pool_malloc(void** p, size_t bytes, cudaStream_t st) {
+  static std::mutex mu;
+  static cudaMemPool_t pools[64];
+  static bool have[64];
+  int dev = 0;
+  GLA_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return check_cuda(cudaMallocAsync(p, bytes ? bytes : 1, st), __FILE__, __LINE__);
+  cudaMemPool_t pool;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (!have[dev]) {
+      cudaMemPoolProps props;
+      memset(&props, 0, sizeof(props));
+      props.allocType = cudaMemAllocationTypePinned;
+      props.handleTypes = cudaMemHandleTypeNone;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = dev;
+      GLA_CUDA(cudaMemPoolCreate(&pools[dev], &props));
+      unsigned long long thr = ~0ull;
+      GLA_CUDA(cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &thr));
+      have[dev] = true;
+    }
+    pool = pools[dev];
+  }
+  return check_cuda(cudaMallocFromPoolAsync(p, bytes ? bytes : 1, pool, st), __FILE__, __LINE__);
 }
 
 namespace {

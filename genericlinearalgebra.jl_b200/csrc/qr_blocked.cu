@@ -686,7 +686,7 @@ struct QrWork {
       *total_only = total;
       return 0;
     }
-    GLA_CUDA(cudaMallocAsync(&block, total, st));
+    GLA_TRY(pool_malloc(reinterpret_cast<void**>(&block), total, st));
     char* p = static_cast<char*>(block);
     for (int b = 0; b < 2; ++b) {
       const int src = b < nbuf ? b : 0;
@@ -1128,8 +1128,8 @@ int larft_dev(const T* dF, i64 m, i64 n, i64 ldf, const T* dtau, T* dT, i64 ldt,
   const i64 ldv = round_up(m, 2);
   T* Vc = nullptr;
   T* X = nullptr;
-  GLA_CUDA(cudaMallocAsync(&Vc, (size_t)ldv * k * sizeof(T), st));
-  int rc = check_cuda(cudaMallocAsync(&X, (size_t)k * k * sizeof(T), st), __FILE__, __LINE__);
+  GLA_TRY(pool_malloc(reinterpret_cast<void**>(&Vc), (size_t)ldv * k * sizeof(T), st));
+  int rc = pool_malloc(reinterpret_cast<void**>(&X), (size_t)k * k * sizeof(T), st);
   if (!rc) {
     const unsigned grid = (unsigned)(ceil_div(m * k, 256) > 4096 ? 4096 : ceil_div(m * k, 256));
     clean_v_kernel<T><<<grid, 256, 0, st>>>(dF, ldf, m, k, Vc, ldv);

@@ -305,7 +305,7 @@ static int run_reduction(TsqrSrc src, i64 m, int n, double* dR, i64 ldr, cudaStr
       break;
     }
     const i64 tall = grid * n;
-    if (!buf[cur]) rc = check_cuda(cudaMallocAsync(&buf[cur], (size_t)sms * n * n * sizeof(double), st), __FILE__, __LINE__);
+    if (!buf[cur]) rc = pool_malloc(reinterpret_cast<void**>(&buf[cur]), (size_t)sms * n * n * sizeof(double), st);
     if (rc) break;
     rc = launch_stream(src, m, n, rows_per_cta, grid, buf[cur], tall, n, st);
     src = TsqrSrc{buf[cur], tall, tall, 0};

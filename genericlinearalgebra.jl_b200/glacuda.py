@@ -1,6 +1,6 @@
 """Host-side mirror of the reference's operator interface over the C ABI of libgla_cuda.so.
 
-This is what a Julia host does with `ccall` (see julia/GLACuda.jl and INTEGRATION.md), written in
+This is what a Julia host does with `ccall` (see julia/GLACuda/ and INTEGRATION.md), written in
 Python/ctypes because no Julia runtime exists in this image.  Names and argument meaning follow
 the reference (GenericLinearAlgebra.jl v0.4.0); a trailing `_` stands for Julia's `!`:
 
@@ -26,7 +26,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("GLA_CUDA_LIB") or os.path.join(_HERE, "lib", "libgla_cuda.so")   # same override as julia/GLACuda.jl
+LIB_PATH = os.environ.get("GLA_CUDA_LIB") or os.path.join(_HERE, "lib", "libgla_cuda.so")   # same override as julia/GLACuda/src/GLACuda.jl
 _LIB = None
 
 _I64 = C.c_int64

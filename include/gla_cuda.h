@@ -3,7 +3,7 @@
  *
  * Every entry point replaces one reference interface (citations are file:line into the
  * reference tree, GenericLinearAlgebra.jl v0.4.0).  A Julia host reaches them with `ccall`
- * (see INTEGRATION.md and genericlinearalgebra.jl_b200/julia/GLACuda.jl); the Python
+ * (see INTEGRATION.md and genericlinearalgebra.jl_b200/julia/GLACuda/); the Python
  * ctypes mirror used by tests/bench is genericlinearalgebra.jl_b200/glacuda.py.
  *
  * Conventions
