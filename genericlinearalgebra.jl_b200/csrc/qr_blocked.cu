@@ -442,6 +442,150 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) qr_panel_kernel(PanelArgs<T>
   }
 }
 
+// ------------------------------------------------------------------------------- K1c: cluster panel kernel
+// Panels of at most 8 x ROWS rows (3072 in Float64): ONE thread-block cluster, CTA r holds rows [r*ROWS, ...) of the
+// panel in shared memory (row-major, padded), and the per-column exchange goes through DISTRIBUTED SHARED MEMORY
+// instead of L2: every CTA writes its 2 x 64 partials (dots of the un-normalised pivot column with every column, and
+// its contribution to pivot row j) into the same slot of every CTA's exchange buffer, one barrier.cluster per column,
+// every CTA sums the slots in rank order (bitwise identical scalars everywhere, deterministic).  The L2 flag exchange of
+// qr_panel_kernel costs ~7000 cycles per column at m = 1024 (profiles/r02_ncu_qr_panel_n1024.txt: long_scoreboard on the
+// spinning loads + four CTA barriers); this one ~1500.  Plain right-looking steps (no 16-column sub-panels): at
+// <= 384 rows per CTA the rank-1 update of the whole slab is cheaper than the bookkeeping of the blocked form.
+// Semantics: qrUnblocked! (src/qr.jl:86-111) with stdlib reflector! / reflectorApply! (call sites :96, :102), then the
+// clean reflector block Vc (unit diagonal, zeros above) and its transpose VcT like qr_panel_kernel.
+constexpr int CL_MAX = 8;              // portable cluster size
+constexpr int CP_THREADS = 256;
+constexpr int CP_LD = NB + 1;          // padded row of the slab
+
+template <class T>
+struct ClusterPanelSmem {   // fixed part; the slab follows
+  T xbuf[2][CL_MAX][2 * NB];   // [parity][source rank][dots | pivot-row entries]
+  T part[4][NB];               // partial dots of the four row groups
+  T tot[2 * NB];               // reduced dots | pivot row
+};
+
+template <class T>
+__global__ void __launch_bounds__(CP_THREADS, 1) qr_panel_cluster_kernel(PanelArgs<T> a) {
+  using R = typename Sc<T>::real;
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ClusterPanelSmem<T>& sm = *reinterpret_cast<ClusterPanelSmem<T>*>(smem_raw);
+  T* S = reinterpret_cast<T*>(smem_raw + sizeof(ClusterPanelSmem<T>));   // S[i * CP_LD + c]
+  const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  const int tid = threadIdx.x;
+  const int c = tid & (NB - 1), rg = tid >> 6;   // column, row group (rows rg, rg + 4, ...)
+  const int r0 = rank * a.rows_per;
+  const int r1 = (r0 + a.rows_per < a.mk) ? r0 + a.rows_per : a.mk;
+  const int rows = r1 > r0 ? r1 - r0 : 0;
+  const int nb = a.nb;
+  const int kk = a.mk < nb ? a.mk : nb;
+
+  // ---- slab in: coalesced along the rows, L2-only loads (the far update of the other stream just rewrote the panel)
+  for (int e = tid; e < rows * nb; e += CP_THREADS) {
+    const int col = e / rows, i = e - col * rows;
+    S[i * CP_LD + col] = ldcg_t(a.A + (i64)col * a.lda + r0 + i);
+  }
+  __syncthreads();
+
+  T pend_ixi = Sc<T>::one();   // deferred finish of the previous pivot column (rows below the diagonal *= 1/xi, diagonal <- -nu)
+  R pend_nu = R(0);
+  bool pend = false;
+  auto finish = [&](int jc) {
+    if (!pend) return;
+    if (c == jc) {
+      int lo = jc + 1 - r0;
+      if (lo < 0) lo = 0;
+      for (int i = lo + rg; i < rows; i += 4) S[i * CP_LD + jc] = S[i * CP_LD + jc] * pend_ixi;
+      if (rg == 0 && jc >= r0 && jc < r1) S[(jc - r0) * CP_LD + jc] = Sc<T>::from_real(-pend_nu);
+    }
+  };
+
+  for (int j = 0; j < kk; ++j) {
+    if (j > 0) finish(j - 1);   // threads of column j-1 are idle from here on; nobody reads that column any more
+    const int par = j & 1;
+    int lo = j + 1 - r0;        // first local row strictly below the diagonal
+    if (lo < 0) lo = 0;
+    // ---- partial dots of the un-normalised pivot column with every column c >= j (c = j: tail norm^2)
+    T d = Sc<T>::zero();
+    if (c >= j && c < nb) {
+      T d1 = Sc<T>::zero(), d2 = Sc<T>::zero(), d3 = Sc<T>::zero();
+      int i = lo + rg;
+      for (; i + 12 < rows; i += 16) {   // four independent accumulators: the loads of a round are all in flight together
+        const T p0 = S[i * CP_LD + j], p1 = S[(i + 4) * CP_LD + j], p2 = S[(i + 8) * CP_LD + j], p3 = S[(i + 12) * CP_LD + j];
+        const T q0 = S[i * CP_LD + c], q1 = S[(i + 4) * CP_LD + c], q2 = S[(i + 8) * CP_LD + c], q3 = S[(i + 12) * CP_LD + c];
+        d = fmad(cj(p0), q0, d);
+        d1 = fmad(cj(p1), q1, d1);
+        d2 = fmad(cj(p2), q2, d2);
+        d3 = fmad(cj(p3), q3, d3);
+      }
+      for (; i < rows; i += 4) d = fmad(cj(S[i * CP_LD + j]), S[i * CP_LD + c], d);
+      d = (d + d1) + (d2 + d3);
+    }
+    sm.part[rg][c] = d;
+    __syncthreads();
+    if (tid < NB) {
+      const T dsum = (sm.part[0][c] + sm.part[1][c]) + (sm.part[2][c] + sm.part[3][c]);
+      const T rowj = (j >= r0 && j < r1 && c < nb) ? S[(j - r0) * CP_LD + c] : Sc<T>::zero();
+      for (int r = 0; r < CL; ++r) {   // same slot of every CTA's exchange buffer (distributed shared memory)
+        T* dst = cluster.map_shared_rank(&sm.xbuf[par][rank][0], r);
+        dst[c] = dsum;
+        dst[NB + c] = rowj;
+      }
+    }
+    cluster.sync();
+    if (tid < 2 * NB) {
+      T t = sm.xbuf[par][0][tid];
+      for (int r = 1; r < CL; ++r) t = t + sm.xbuf[par][r][tid];
+      sm.tot[tid] = t;
+    }
+    __syncthreads();
+    const T alpha = sm.tot[NB + j];
+    const R n2 = abs2(alpha) + re(sm.tot[j]);
+    ReflScalars<T> rs;
+    if constexpr (Sc<T>::is_complex) rs = reflector_scalars<T>(alpha, n2);
+    else rs = reflector_scalars_fast<T>(alpha, n2);
+    pend = rs.nonzero;
+    pend_ixi = rs.ixi;
+    pend_nu = rs.nu;
+    if (rank == 0 && tid == 0) a.tau[j] = rs.tau;
+    if (rs.nonzero && c > j && c < nb) {
+      // s = conj(tau) (a_jc + conj(1/xi) d_c);  a_jc -= s;  rows below -= x * (s / xi)
+      const T s = cj(rs.tau) * (sm.tot[NB + c] + cj(rs.ixi) * sm.tot[c]);
+      const T t = s * rs.ixi;
+      int i = lo + rg;
+      for (; i + 12 < rows; i += 16) {   // column c != column j: loads first, then the four stores
+        const T p0 = S[i * CP_LD + j], p1 = S[(i + 4) * CP_LD + j], p2 = S[(i + 8) * CP_LD + j], p3 = S[(i + 12) * CP_LD + j];
+        const T q0 = S[i * CP_LD + c], q1 = S[(i + 4) * CP_LD + c], q2 = S[(i + 8) * CP_LD + c], q3 = S[(i + 12) * CP_LD + c];
+        S[i * CP_LD + c] = q0 - p0 * t;
+        S[(i + 4) * CP_LD + c] = q1 - p1 * t;
+        S[(i + 8) * CP_LD + c] = q2 - p2 * t;
+        S[(i + 12) * CP_LD + c] = q3 - p3 * t;
+      }
+      for (; i < rows; i += 4) S[i * CP_LD + c] = S[i * CP_LD + c] - S[i * CP_LD + j] * t;
+      if (rg == 0 && j >= r0 && j < r1) S[(j - r0) * CP_LD + c] = S[(j - r0) * CP_LD + c] - s;
+    }
+    __syncthreads();
+  }
+  if (kk > 0) finish(kk - 1);
+  __syncthreads();
+
+  // ---- panel, clean reflectors and their transpose out
+  for (int e = tid; e < rows * nb; e += CP_THREADS) {
+    const int col = e / rows, i = e - col * rows;
+    const int gi = r0 + i;
+    const T v = S[i * CP_LD + col];
+    a.A[(i64)col * a.lda + gi] = v;
+    if (col < kk) a.Vc[(i64)col * a.ldvc + gi] = gi < col ? Sc<T>::zero() : (gi == col ? Sc<T>::one() : v);
+  }
+  for (int e = tid; e < rows * kk; e += CP_THREADS) {
+    const int i = e / kk, col = e - i * kk;
+    const int gi = r0 + i;
+    const T v = S[i * CP_LD + col];
+    a.VcT[(i64)gi * a.ldvct + col] = gi < col ? Sc<T>::zero() : (gi == col ? Sc<T>::one() : v);
+  }
+}
+
 // ------------------------------------------------------------------------------- clean V from factors
 // Vc (mk x kk, ldvc) and VcT (kk x mk, ldvct) from the factored panel F (unit lower trapezoid)
 template <class T>
@@ -752,6 +896,47 @@ static int launch_panel(T* A, i64 lda, i64 mk, int nb, T* tau, QrWork<T>& w, int
   a.xw = w.xw;
   a.xz = w.xz;
   a.epoch = ++w.epoch;
+  {  // panels that fit one thread-block cluster: exchange through distributed shared memory (qr_panel_cluster_kernel)
+    static const bool no_cluster = getenv("GLA_PANEL_NO_CLUSTER") != nullptr;
+    const i64 slab_cap = 226 * 1024 - (i64)sizeof(ClusterPanelSmem<T>);   // 227 KB per CTA minus the exchange buffers
+    const i64 rows_max = slab_cap / ((i64)CP_LD * sizeof(T)) / 4 * 4;
+    // measured (profiles/r02_qr_panel_cluster.txt): n = 1024 5.74 -> 4.30 ms, n = 2048 11.5 -> 10.4 ms, n = 4096 equal; beyond
+    // 256 rows per CTA the rank-1 update of the whole slab per column costs more than the sub-panel form of qr_panel_kernel
+    const i64 rows_use = rows_max < 256 ? rows_max : 256;
+    if (!no_cluster && mk <= CL_MAX * rows_use) {
+      int CL = (int)((mk + 63) / 64);
+      if (CL > CL_MAX) CL = CL_MAX;
+      if (CL < 1) CL = 1;
+      const i64 rows_per = round_up((mk + CL - 1) / CL, 4);
+      CL = (int)((mk + rows_per - 1) / rows_per);
+      a.rows_per = (int)rows_per;
+      a.resident = 1;
+      a.lds = CP_LD;
+      const size_t smem = sizeof(ClusterPanelSmem<T>) + (size_t)rows_per * CP_LD * sizeof(T);
+      auto kern = qr_panel_cluster_kernel<T>;
+      GLA_TRY(ensure_dyn_smem((const void*)kern, (int)(sizeof(ClusterPanelSmem<T>) + slab_cap)));
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3((unsigned)CL);
+      cfg.blockDim = dim3(CP_THREADS);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = (unsigned)CL;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      GLA_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+      if (j > 0) {
+        const int kk = (int)(mk < nb ? mk : nb);
+        zero_top_kernel<T><<<ceil_div((i64)j * NB * kk, 256), 256, 0, st>>>(w.V[w.cur], w.ldv, w.VT[w.cur], j * NB, kk);
+        GLA_CUDA(cudaGetLastError());
+      }
+      return 0;
+    }
+  }
   const i64 smem_cap = 176 * 1024;
   const i64 max_rows = (smem_cap / ((i64)nb * sizeof(T)) - 4) / 16 * 16;  // rows that fit one CTA
   const int sms = sm_count();

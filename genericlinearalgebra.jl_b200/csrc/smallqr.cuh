@@ -10,6 +10,7 @@
 //   scaled by 1/xi one step later (after the single __syncthreads of the step) by all threads.
 #pragma once
 #include "common.cuh"
+#include "fastmath.cuh"
 
 namespace gla {
 
@@ -58,6 +59,24 @@ __device__ __forceinline__ ReflScalars<T> reflector_scalars(T alpha, typename Sc
   T xi = alpha + Sc<T>::from_real(r.nu);
   r.tau = scale_real(xi, R(1) / r.nu);
   r.ixi = inv(xi);
+  return r;
+}
+
+// The same scalars from the MUFU seeds + FMA refinement of fastmath.cuh (no IEEE sqrt / division subroutine on the
+// per-column critical path of the panel kernels): sqrt correctly rounded in almost all cases, reciprocals to <= 1 ulp.
+template <class R>
+__device__ __forceinline__ ReflScalars<R> reflector_scalars_fast(R alpha, R n2) {
+  ReflScalars<R> r;
+  r.nonzero = n2 != R(0);
+  if (!r.nonzero || !(n2 >= SafeRange<R>::lo() && n2 <= SafeRange<R>::hi())) return reflector_scalars<R>(alpha, n2);
+  const R rs = Fast<R>::rsqrt(n2);
+  const R nrm = Fast<R>::sqrt_from_rsqrt(n2, rs);
+  r.nu = copysign(nrm, alpha);
+  const R xi = alpha + r.nu;
+  r.ixi = Fast<R>::rcp(xi);
+  r.tau = xi * copysign(rs, alpha);   // xi / nu
+  // one Newton correction of tau against nu (rs is 1/sqrt(n2) to ~1 ulp, nu is the rounded sqrt)
+  r.tau = fma(fma(-r.tau, r.nu, xi), copysign(rs, alpha), r.tau);
   return r;
 }
 
