@@ -215,6 +215,32 @@ int ormqr_host(const T* F, i64 mF, i64 nF, i64 ldf, const T* tau, T* A, i64 mA, 
 }
 
 template <class T>
+int orgqr_thin_host(const T* F, i64 m, i64 n, i64 ldf, const T* tau, T* Q, i64 ldq) {
+  if (m < 0) return -2;
+  if (n < 0) return -3;
+  if (ldf < (m > 1 ? m : 1)) return -4;
+  if (ldq < (m > 1 ? m : 1)) return -7;
+  const i64 k = m < n ? m : n;
+  if (k == 0) return 0;
+  if (!F) return -1;
+  if (!tau) return -5;
+  if (!Q) return -6;
+  Stream st;
+  GLA_TRY(st.create());
+  DevMatrix<T> dF, dQ;
+  DevBuf dtau;
+  GLA_TRY(dF.upload(F, ldf, m, n, st.s));
+  GLA_TRY(dtau.alloc(k * sizeof(T), st.s));
+  GLA_CUDA(cudaMemcpyAsync(dtau.p, tau, k * sizeof(T), cudaMemcpyHostToDevice, st.s));
+  dQ.ld = round_up(m, 16 / sizeof(T) > 2 ? 16 / sizeof(T) : 2);
+  GLA_TRY(dQ.buf.alloc((size_t)dQ.ld * k * sizeof(T), st.s));
+  GLA_TRY(orgqr_thin_dev<T>(dF.p(), m, n, dF.ld, dtau.as<T>(), dQ.p(), dQ.ld, st.s));
+  GLA_TRY(dQ.download(Q, ldq, m, k, st.s));
+  GLA_CUDA(cudaStreamSynchronize(st.s));
+  return 0;
+}
+
+template <class T>
 int reflector_apply_right_host(T* A, i64 m, i64 n, i64 lda, const T* x, i64 lenx, const T* tau) {
   if (m < 0) return -2;
   if (n < 0) return -3;
@@ -375,6 +401,14 @@ int gla_zlarft(const void* F, int64_t m, int64_t n, int64_t ldf, const void* tau
 int gla_sormqr_blocked(const float* F, int64_t mF, int64_t nF, int64_t ldf, const float* tau, float* A, int64_t mA, int64_t nA, int64_t lda, int adjoint) { return ormqr_host<float>(F, mF, nF, ldf, tau, A, mA, nA, lda, adjoint); }
 int gla_dormqr_blocked(const double* F, int64_t mF, int64_t nF, int64_t ldf, const double* tau, double* A, int64_t mA, int64_t nA, int64_t lda, int adjoint) { return ormqr_host<double>(F, mF, nF, ldf, tau, A, mA, nA, lda, adjoint); }
 int gla_zormqr_blocked(const void* F, int64_t mF, int64_t nF, int64_t ldf, const void* tau, void* A, int64_t mA, int64_t nA, int64_t lda, int adjoint) { return ormqr_host<zd>(ZCP(F), mF, nF, ldf, ZCP(tau), ZP(A), mA, nA, lda, adjoint); }
+
+// ---- thin Q
+int gla_sorgqr_thin(const float* F, int64_t m, int64_t n, int64_t ldf, const float* tau, float* Q, int64_t ldq) { return orgqr_thin_host<float>(F, m, n, ldf, tau, Q, ldq); }
+int gla_dorgqr_thin(const double* F, int64_t m, int64_t n, int64_t ldf, const double* tau, double* Q, int64_t ldq) { return orgqr_thin_host<double>(F, m, n, ldf, tau, Q, ldq); }
+int gla_zorgqr_thin(const void* F, int64_t m, int64_t n, int64_t ldf, const void* tau, void* Q, int64_t ldq) { return orgqr_thin_host<zd>(ZCP(F), m, n, ldf, ZCP(tau), ZP(Q), ldq); }
+int gla_sorgqr_thin_dev(const float* dF, int64_t m, int64_t n, int64_t ldf, const float* dtau, float* dQ, int64_t ldq, void* stream) { return orgqr_thin_dev<float>(dF, m, n, ldf, dtau, dQ, ldq, STREAM(stream)); }
+int gla_dorgqr_thin_dev(const double* dF, int64_t m, int64_t n, int64_t ldf, const double* dtau, double* dQ, int64_t ldq, void* stream) { return orgqr_thin_dev<double>(dF, m, n, ldf, dtau, dQ, ldq, STREAM(stream)); }
+int gla_zorgqr_thin_dev(const void* dF, int64_t m, int64_t n, int64_t ldf, const void* dtau, void* dQ, int64_t ldq, void* stream) { return orgqr_thin_dev<zd>(ZCP(dF), m, n, ldf, ZCP(dtau), ZP(dQ), ldq, STREAM(stream)); }
 
 // ---- right reflector application
 int gla_sreflector_apply_right(float* A, int64_t m, int64_t n, int64_t lda, const float* x, int64_t lenx, const float* tau) { return reflector_apply_right_host<float>(A, m, n, lda, x, lenx, tau); }

@@ -23,6 +23,9 @@ int larft_dev(const T* dF, i64 m, i64 n, i64 ldf, const T* dtau, T* dT, i64 ldt,
 template <class T>
 int ormqr_blocked_dev(const T* dF, i64 mF, i64 nF, i64 ldf, const T* dtau, T* dA, i64 mA, i64 nA,
                       i64 lda, int adjoint, cudaStream_t st);
+// thin Q = H_1 .. H_k [I_k; 0], m x k
+template <class T>
+int orgqr_thin_dev(const T* dF, i64 m, i64 n, i64 ldf, const T* dtau, T* dQ, i64 ldq, cudaStream_t st);
 template <class T>
 int reflector_apply_right_dev(T* dA, i64 m, i64 n, i64 lda, const T* dx, T tau, cudaStream_t st);
 

@@ -1251,30 +1251,137 @@ int geqr_blocked_dev(T* dA, i64 m, i64 n, i64 lda, T* dtau, i64 /*blocksize_hint
   return rc;
 }
 
+// TH (rows x rows, ld NB) = T^H for a rows x rows upper T (ld NB): the K-contiguous operand of Z = T Y
+template <class T>
+__global__ void conj_transpose_t_kernel(const T* __restrict__ Tm, T* __restrict__ TH, int rows) {
+  for (int e = threadIdx.x; e < rows * rows; e += blockDim.x) {
+    const int i = e / rows, l = e - i * rows;   // TH(l, i) = conj(T(i, l))
+    TH[(i64)i * NB + l] = cj(Tm[(i64)l * NB + i]);
+  }
+}
+
+// A2 <- (I - V T V^H) A2 for ONE outer block (non-adjoint twin of apply_outer): the panels act LAST TO FIRST,
+//     Y_j = W_j - sum_{i>j} G_ji Z_i ,   Z_j = T_j Y_j ,   A2 -= V Z          (lmul!(H, A, M), src/householder.jl:82-115)
+template <class T>
+static int apply_outer_fwd(QrWork<T>& w, int b, i64 mo, int kbig, T* A2, i64 lda, i64 nA, T* TH, cudaStream_t st) {
+  if (nA <= 0) return 0;
+  GemmTN<T> g1;
+  g1.At = w.V[b]; g1.ldat = w.ldv;
+  g1.B = A2; g1.ldb = lda;
+  g1.C = w.Wp[1]; g1.ldc = NBO;
+  g1.M = kbig; g1.N = nA; g1.K = mo;
+  g1.conj_a = 1;
+  g1.nsplit = wsplit_for(kbig, nA, mo);
+  g1.split_stride = (i64)NBO * nA;
+  if ((i64)g1.nsplit * NBO * nA > w.wp_elems[1]) g1.nsplit = (int)(w.wp_elems[1] / ((i64)NBO * nA));
+  if (g1.nsplit < 1) {
+    set_error(GLA_ERR_INTERNAL, "W workspace too small", __FILE__, __LINE__);
+    return GLA_ERR_INTERNAL;
+  }
+  GLA_TRY(gemm_tn<T>(g1, st));
+  if (g1.nsplit > 1) GLA_TRY(sum_splits<T>(w.Wp[1], NBO, w.Wp[1], NBO, g1.split_stride, g1.nsplit, kbig, nA, st));
+  const int nj = (kbig + NB - 1) / NB;
+  for (int j = nj - 1; j >= 0; --j) {
+    const int rows_j = (kbig - j * NB) < NB ? (kbig - j * NB) : NB;
+    conj_transpose_t_kernel<T><<<1, 256, 0, st>>>(w.Tm[b] + (i64)j * NB * NB, TH + (i64)j * NB * NB, rows_j);
+    GLA_CUDA(cudaGetLastError());
+    if (j < nj - 1) {
+      GemmTN<T> gy;   // conj(At(l, a)) = G(jNB + a, (j+1)NB + l): G is Hermitian, so At = G + (j+1)NB + jNB * ldg
+      gy.At = w.G[b] + (i64)(j + 1) * NB + (i64)j * NB * NBO; gy.ldat = NBO;
+      gy.B = w.Z[1] + (j + 1) * NB; gy.ldb = NBO;
+      gy.C = w.Wp[1] + j * NB; gy.ldc = NBO;
+      gy.M = rows_j; gy.N = nA; gy.K = kbig - (i64)(j + 1) * NB;
+      gy.alpha = -1; gy.beta_one = 1; gy.conj_a = 1;
+      GLA_TRY(gemm_tn<T>(gy, st));
+    }
+    GemmTN<T> gz;
+    gz.At = TH + (i64)j * NB * NB; gz.ldat = NB;
+    gz.B = w.Wp[1] + j * NB; gz.ldb = NBO;
+    gz.C = w.Z[1] + j * NB; gz.ldc = NBO;
+    gz.M = rows_j; gz.N = nA; gz.K = rows_j;
+    gz.conj_a = 1;
+    GLA_TRY(gemm_tn<T>(gz, st));
+  }
+  GemmTN<T> g2;
+  g2.At = w.VT[b]; g2.ldat = NBO;
+  g2.B = w.Z[1]; g2.ldb = NBO;
+  g2.C = A2; g2.ldc = lda;
+  g2.M = mo; g2.N = nA; g2.K = kbig;
+  g2.alpha = -1;
+  g2.beta_one = 1;
+  return gemm_tn<T>(g2, st);
+}
+
+// A <- Q A (adjoint = 0) or Q^H A (adjoint = 1), Q = H_1 .. H_k from (F, tau).  Outer blocks of NBO = 384 reflectors:
+// per block the clean V / V^T, the per-panel T_j and the Gram V^H V are rebuilt from the factors, then ONE K = 384 pass
+// over A (W = V^H A, the block recurrence on 64-row strips of W, A -= V Z) -- the same wide form as the far update of the
+// factorisation instead of one K = 64 pass per panel (16 B of A traffic per 128 flops: HBM bound).
 template <class T>
 int ormqr_blocked_dev(const T* dF, i64 mF, i64 nF, i64 ldf, const T* dtau, T* dA, i64 mA, i64 nA, i64 lda,
                       int adjoint, cudaStream_t st) {
   if (mF != mA) return -7;  // DimensionMismatch (src/householder.jl:87,129)
   if (mF < 0 || nF < 0 || nA < 0) return -2;
+  if (ldf < (mF > 1 ? mF : 1)) return -4;
+  if (lda < (mA > 1 ? mA : 1)) return -9;
   const i64 k = mF < nF ? mF : nF;
   if (k == 0 || nA == 0) return 0;
   QrWork<T> w;
-  GLA_TRY(w.alloc(mF, nA, 0, 1, st));
+  GLA_TRY(w.alloc(mF, 1, nA, 1, st));
+  T* TH = nullptr;
   int rc = 0;
-  const i64 npan = (k + NB - 1) / NB;
-  for (i64 ip = 0; ip < npan; ++ip) {
-    // Q^H A applies panels first to last, Q A last to first
-    const i64 k0 = (adjoint ? ip : npan - 1 - ip) * NB;
-    const i64 mk = mF - k0;
-    const int kk = (int)((k - k0) < NB ? (k - k0) : NB);
-    const unsigned grid = (unsigned)(ceil_div(mk * kk, 256) > 2048 ? 2048 : ceil_div(mk * kk, 256));
-    extract_v_kernel<T><<<grid, 256, 0, st>>>(dF + k0 + k0 * ldf, ldf, (int)mk, kk, w.V[0], w.ldv, w.VT[0], NBO);
-    if ((rc = check_cuda(cudaGetLastError(), __FILE__, __LINE__))) break;
-    if ((rc = build_T<T>(w, w.V[0], w.ldv, mk, kk, dtau + k0, w.Tm[0], st))) break;
-    if ((rc = apply_panel<T>(w, w.V[0], w.ldv, w.VT[0], NBO, w.Tm[0], mk, kk, dA + k0, lda, nA, adjoint, st))) break;
+  if (!adjoint) rc = pool_malloc(reinterpret_cast<void**>(&TH), (size_t)NBO * NB * sizeof(T), st);
+  const i64 nob = (k + NBO - 1) / NBO;
+  w.cur = 0;
+  for (i64 ib = 0; ib < nob && !rc; ++ib) {
+    // Q^H A applies the blocks first to last, Q A last to first
+    const i64 o0 = (adjoint ? ib : nob - 1 - ib) * NBO;
+    const int kbig = (int)((k - o0) < NBO ? (k - o0) : NBO);
+    const i64 mo = mF - o0;
+    for (int j = 0; j * NB < kbig && !rc; ++j) {
+      const i64 k0 = o0 + (i64)j * NB;
+      const i64 mk = mF - k0;
+      const int kk = (int)((k - k0) < NB ? (k - k0) : NB);
+      const unsigned grid = (unsigned)(ceil_div(mk * kk, 256) > 2048 ? 2048 : ceil_div(mk * kk, 256));
+      extract_v_kernel<T><<<grid, 256, 0, st>>>(dF + k0 + k0 * ldf, ldf, (int)mk, kk, w.Vj(j), w.ldv, w.VTj(j), NBO);
+      if ((rc = check_cuda(cudaGetLastError(), __FILE__, __LINE__))) break;
+      if (j > 0) {
+        zero_top_kernel<T><<<ceil_div((i64)j * NB * kk, 256), 256, 0, st>>>(w.V[0], w.ldv, w.VT[0], j * NB, kk);
+        if ((rc = check_cuda(cudaGetLastError(), __FILE__, __LINE__))) break;
+      }
+      rc = build_T<T>(w, w.Vj(j), w.ldv, mk, kk, dtau + k0, w.Tj(j), st);
+    }
+    if (rc) break;
+    if (kbig > NB) rc = gram<T>(w, 1, w.V[0], w.ldv, mo, kbig, w.G[0], NBO, st);
+    if (rc) break;
+    rc = adjoint ? apply_outer<T>(w, 0, mo, kbig, dA + o0, lda, nA, st)
+                 : apply_outer_fwd<T>(w, 0, mo, kbig, dA + o0, lda, nA, TH, st);
   }
+  if (TH) cudaFreeAsync(TH, st);
   w.release();
   return rc;
+}
+
+// thin Q (m x k, k = min(m, n)): Q = H_1 .. H_k [I_k; 0]                 (used to verify ||Q^H Q - I||)
+template <class T>
+__global__ void eye_kernel(T* __restrict__ Q, i64 ldq, i64 m, i64 k) {
+  const i64 total = m * k;
+  for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
+    const i64 j = e / m, i = e - j * m;
+    Q[j * ldq + i] = i == j ? Sc<T>::one() : Sc<T>::zero();
+  }
+}
+template <class T>
+int orgqr_thin_dev(const T* dF, i64 m, i64 n, i64 ldf, const T* dtau, T* dQ, i64 ldq, cudaStream_t st) {
+  if (m < 0) return -2;
+  if (n < 0) return -3;
+  if (ldf < (m > 1 ? m : 1)) return -4;
+  if (ldq < (m > 1 ? m : 1)) return -7;
+  const i64 k = m < n ? m : n;
+  if (k == 0) return 0;
+  const i64 total = m * k;
+  eye_kernel<T><<<(unsigned)(ceil_div(total, 256) > 4096 ? 4096 : ceil_div(total, 256)), 256, 0, st>>>(dQ, ldq, m, k);
+  GLA_CUDA(cudaGetLastError());
+  return ormqr_blocked_dev<T>(dF, m, n, ldf, dtau, dQ, m, k, ldq, 0, st);
 }
 
 // ------------------------------------------------------------------------------- full-width T (API parity)
@@ -1373,6 +1480,7 @@ int reflector_apply_right_dev(T* dA, i64 m, i64 n, i64 lda, const T* dx, T tau, 
 #define INST(T)                                                                                             \
   template int geqr_blocked_dev<T>(T*, i64, i64, i64, T*, i64, cudaStream_t);                               \
   template int ormqr_blocked_dev<T>(const T*, i64, i64, i64, const T*, T*, i64, i64, i64, int, cudaStream_t); \
+  template int orgqr_thin_dev<T>(const T*, i64, i64, i64, const T*, T*, i64, cudaStream_t);                        \
   template int larft_dev<T>(const T*, i64, i64, i64, const T*, T*, i64, cudaStream_t);                      \
   template int reflector_apply_right_dev<T>(T*, i64, i64, i64, const T*, T, cudaStream_t);
 INST(float)

@@ -156,6 +156,18 @@ class QR2:
     def __init__(self, factors, tau):
         self.factors, self.tau = factors, tau
 
+    def thinQ(self):
+        """Matrix of the first k = min(m, n) columns of Q = H_1 .. H_k (gla_?orgqr_thin): what
+        `F[Tuple{:QBlocked}] * Matrix(I, m, k)` gives in the reference (src/householder.jl:116-117)."""
+        lda = _colmajor(self.factors, "thinQ")
+        m, n = self.factors.shape
+        k = min(m, n)
+        Q = np.zeros((m, k), dtype=self.factors.dtype, order="F")
+        rc = _fn("orgqr_thin", Q.dtype)(_ptr(self.factors), _I64(m), _I64(n), _I64(lda), _ptr(self.tau), _ptr(Q),
+                                        _I64(max(m, 1)))
+        _check(rc, "orgqr_thin")
+        return Q
+
     @property
     def shape(self):
         return self.factors.shape

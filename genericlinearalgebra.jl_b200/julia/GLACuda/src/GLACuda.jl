@@ -86,6 +86,16 @@ for T in (Float32, Float64, ComplexF64)
             chk(rc, "ormqr_blocked!")
             return A
         end
+        # gla_?orgqr_thin: Q = H_1 .. H_k [I_k; 0]                            (HouseholderBlock * Matrix(I, m, k), src/householder.jl:116-117)
+        function orgqr_thin!(Q::Matrix{$T}, F::Matrix{$T}, tau::Vector{$T})
+            m, n = size(F)
+            size(Q) == (m, min(m, n)) || throw(DimensionMismatch("Q must be m x min(m, n)"))
+            rc = GC.@preserve F tau Q ccall(($(QuoteNode(Symbol("gla_", p, "orgqr_thin"))), libgla), Cint,
+                (Ptr{$T}, Int64, Int64, Int64, Ptr{$T}, Ptr{$T}, Int64),
+                F, m, n, max(1, stride(F, 2)), tau, Q, max(1, stride(Q, 2)))
+            chk(rc, "orgqr_thin!")
+            return Q
+        end
         # gla_?reflector_apply_right                                          (reflectorApply!(A, x, tau), src/qr.jl:19-42)
         function reflector_apply_right!(A::Matrix{$T}, x::Vector{$T}, tau::Number)
             m, n = size(A)

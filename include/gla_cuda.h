@@ -98,6 +98,16 @@ GLA_API int gla_sormqr_blocked_dev(const float* dF, int64_t mF, int64_t nF, int6
 GLA_API int gla_dormqr_blocked_dev(const double* dF, int64_t mF, int64_t nF, int64_t ldf, const double* dtau, double* dA, int64_t mA, int64_t nA, int64_t lda, int adjoint, void* stream);
 GLA_API int gla_zormqr_blocked_dev(const void* dF, int64_t mF, int64_t nF, int64_t ldf, const void* dtau, void* dA, int64_t mA, int64_t nA, int64_t lda, int adjoint, void* stream);
 
+/* ---- thin Q --------------------------------------------------------------------------
+ * Q (m x k, k = min(m,n), ldq >= m) = H_1 .. H_k [I_k; 0]: the product `HouseholderBlock * Matrix(I, m, k)` of the
+ * reference (src/householder.jl:116-117 with T from src/qr.jl:64-83), formed with 384-reflector-wide block applies. */
+GLA_API int gla_sorgqr_thin(const float* F, int64_t m, int64_t n, int64_t ldf, const float* tau, float* Q, int64_t ldq);
+GLA_API int gla_dorgqr_thin(const double* F, int64_t m, int64_t n, int64_t ldf, const double* tau, double* Q, int64_t ldq);
+GLA_API int gla_zorgqr_thin(const void* F, int64_t m, int64_t n, int64_t ldf, const void* tau, void* Q, int64_t ldq);
+GLA_API int gla_sorgqr_thin_dev(const float* dF, int64_t m, int64_t n, int64_t ldf, const float* dtau, float* dQ, int64_t ldq, void* stream);
+GLA_API int gla_dorgqr_thin_dev(const double* dF, int64_t m, int64_t n, int64_t ldf, const double* dtau, double* dQ, int64_t ldq, void* stream);
+GLA_API int gla_zorgqr_thin_dev(const void* dF, int64_t m, int64_t n, int64_t ldf, const void* dtau, void* dQ, int64_t ldq, void* stream);
+
 /* ---- right reflector application ---------------------------------------------------
  * replaces reflectorApply!(A, x, tau)   src/qr.jl:19-42   A <- A (I - tau v v^H), v = [1; x[2:]]
  * returns -6 when lenx != n (DimensionMismatch at src/qr.jl:21-27). tau passed by (host) pointer. */

@@ -174,3 +174,26 @@ def test_device_twins_and_workspace_query(gla, oracle):
     assert gla.workspace_query(gla.OP_GEQR_BATCHED, np.float64, 32, 32) == 0
     with pytest.raises(gla.ArgumentError):
         gla.workspace_query(99, np.float64, 4, 4)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.complex128])
+def test_wide_block_apply_and_thin_q(gla, oracle, dtype):
+    """lmul!(H, A, M) / lmul!(H', A, M) (src/householder.jl:82-157) across several 384-reflector outer blocks against the
+    oracle's block_apply with the full k x k T (src/qr.jl:64-83), and the thin Q: ||Q^H Q - I|| <= 10 n eps, Q R = A."""
+    rng = np.random.default_rng(77)
+    m, n, nA = 1300, 900, 37          # k = 900: three outer blocks (384 + 384 + 132), last panel ragged
+    A = _randn(rng, m, n, dtype)
+    qr = gla.qrBlocked_(A.copy(order="F"))
+    f, t = qr.factors, qr.tau
+    Tfull = oracle.build_T(f, t)
+    B = _randn(rng, m, nA, dtype)
+    tol = 2e-4 if dtype == np.float32 else 1e-11
+    H = qr.QBlocked
+    for adjoint in (False, True):
+        ref = oracle.block_apply(f, Tfull, B, adjoint=adjoint)
+        got = H.adjoint_lmul_(B.copy(order="F")) if adjoint else H.lmul_(B.copy(order="F"))
+        assert np.max(np.abs(got - ref)) <= tol * np.max(np.abs(ref))
+    Q = qr.thinQ()
+    eps = EPS[dtype]
+    assert np.linalg.norm(Q.conj().T @ Q - np.eye(n), 2) <= 10 * n * eps
+    assert np.linalg.norm(Q @ np.triu(f[:n]) - A) / np.linalg.norm(A) <= 10 * n * eps
