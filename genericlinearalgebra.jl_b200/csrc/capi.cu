@@ -299,6 +299,32 @@ int potrf_host(T* A, i64 n, i64 lda, i64 cutoff) {
 }
 
 template <class T>
+int ldlt_host(T* A, i64 n, i64 lda, int uplo, i64 blocksize) {
+  if (n < 0) return -2;
+  if (lda < (n > 1 ? n : 1)) return -3;
+  if (uplo != 'L' && uplo != 'U') return -4;
+  if (blocksize < 1) return -5;
+  if (n == 0) return 0;
+  if (!A) return -1;
+  Stream st;
+  GLA_TRY(st.create());
+  DevMatrix<T> dA;
+  DevBuf dinfo;
+  GLA_TRY(dA.upload(A, lda, n, n, st.s));
+  GLA_TRY(dinfo.alloc(sizeof(int), st.s));
+  GLA_TRY(ldlt_dev<T>(dA.p(), n, dA.ld, uplo == 'U', dinfo.as<int>(), st.s));
+  int info = 0;
+  GLA_CUDA(cudaMemcpyAsync(&info, dinfo.p, sizeof(int), cudaMemcpyDeviceToHost, st.s));
+  GLA_TRY(dA.download(A, lda, n, n, st.s));
+  GLA_CUDA(cudaStreamSynchronize(st.s));
+  if (info != 0) {
+    g_last_info = info;
+    return GLA_ERR_SINGULAR;
+  }
+  return 0;
+}
+
+template <class T>
 int herk_host(T* Cm, i64 n, i64 ldc, const T* A, i64 k, i64 lda, typename Sc<T>::real alpha) {
   if (n < 0) return -2;
   if (ldc < (n > 1 ? n : 1)) return -3;
@@ -481,6 +507,18 @@ int gla_zpotrf_unblocked_L(void* A, int64_t n, int64_t lda) { return potrf_host<
 int gla_spotrf_blocked_L(float* A, int64_t n, int64_t lda, int64_t blocksize) { return blocksize < 1 ? -4 : potrf_host<float>(A, n, lda, 1); }
 int gla_dpotrf_blocked_L(double* A, int64_t n, int64_t lda, int64_t blocksize) { return blocksize < 1 ? -4 : potrf_host<double>(A, n, lda, 1); }
 int gla_zpotrf_blocked_L(void* A, int64_t n, int64_t lda, int64_t blocksize) { return blocksize < 1 ? -4 : potrf_host<zd>(ZP(A), n, lda, 1); }
+
+// ---- LDL^H without pivoting (real element types; ComplexF64 / Quaternion stay on the reference path)
+int gla_sldlt(float* A, int64_t n, int64_t lda, int uplo, int64_t blocksize) { return ldlt_host<float>(A, n, lda, uplo, blocksize); }
+int gla_dldlt(double* A, int64_t n, int64_t lda, int uplo, int64_t blocksize) { return ldlt_host<double>(A, n, lda, uplo, blocksize); }
+int gla_sldlt_dev(float* dA, int64_t n, int64_t lda, int uplo, int* dinfo, void* stream) {
+  if (uplo != 'L' && uplo != 'U') return -4;
+  return ldlt_dev<float>(dA, n, lda, uplo == 'U', dinfo, STREAM(stream));
+}
+int gla_dldlt_dev(double* dA, int64_t n, int64_t lda, int uplo, int* dinfo, void* stream) {
+  if (uplo != 'L' && uplo != 'U') return -4;
+  return ldlt_dev<double>(dA, n, lda, uplo == 'U', dinfo, STREAM(stream));
+}
 
 // ---- workspace query
 int64_t gla_workspace_query(int op, int elem_bytes, int64_t m, int64_t n) {

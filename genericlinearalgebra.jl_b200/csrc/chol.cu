@@ -221,7 +221,9 @@ struct PanelSmem {
 
 // upper Cholesky of the block held in registers: thread (ty, tx) of a 16 x 16 grid owns the cyclic 4 x 4 sub-grid
 // S(ty + 16a, tx + 16b).  Returns 0 or (index of the non-positive pivot) + 1 (uniform over the CTA).
-template <class T>
+// LDL = true: the unit upper factor of W = U^H D U instead (ldlt!, src/ldlt.jl: no square roots, D real and of either sign
+// on the diagonal, U(j, c) = W(j, c) / d_j, trailing block -= conj(W(j, i)) W(j, c) / d_j); dinv[j] = 1 / d_j.
+template <class T, bool LDL = false>
 __device__ __forceinline__ int factor_block_regs(T (&s)[4][4], const int nb, T (*rowbuf)[CB], typename Sc<T>::real* dinv) {
   using R = typename Sc<T>::real;
   const int tid = threadIdx.x;
@@ -239,15 +241,16 @@ __device__ __forceinline__ int factor_block_regs(T (&s)[4][4], const int nb, T (
     }
     __syncthreads();
     const R piv = re(rb[j]);
-    if (!(piv > R(0))) return j + 1;  // uniform: every thread reads the same pivot
-    const R rd = Fast<R>::rsqrt(piv);
-    const R d = Fast<R>::sqrt_from_rsqrt(piv, rd);
+    if (LDL ? !(piv != R(0)) : !(piv > R(0))) return j + 1;  // uniform: every thread reads the same pivot
+    const R rd = LDL ? Fast<R>::rcp(piv) : Fast<R>::rsqrt(piv);
+    const R d = LDL ? piv : Fast<R>::sqrt_from_rsqrt(piv, rd);
     if (tid == 0) dinv[j] = rd;
     // Entries strictly below the diagonal (c < i) are never read by anybody, so the rank-1 update only has to be
     // masked by ROW (i > j): four selects per step instead of a predicate per entry.
     T ui[4], uc[4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a) ui[a] = (ty + 16 * a > j) ? cj(scale_real(rb[ty + 16 * a], rd)) : Sc<T>::zero();
+    for (int a = 0; a < 4; ++a)
+      ui[a] = (ty + 16 * a > j) ? cj(LDL ? rb[ty + 16 * a] : scale_real(rb[ty + 16 * a], rd)) : Sc<T>::zero();
 #pragma unroll
     for (int b = 0; b < 4; ++b) uc[b] = scale_real(rb[tx + 16 * b], rd);
 #pragma unroll
@@ -270,9 +273,13 @@ __device__ __forceinline__ int factor_block_regs(T (&s)[4][4], const int nb, T (
   return 0;
 }
 
-template <class T>
+// LDL = true: W = U^H D U.  Yw (same shape as W) receives Y = D U for the row panel, the left operand of the trailing
+// updates (W22 -= Y12^H U12); the pending update scales the rows of the pending operand by their d (read from the diagonal
+// of the pending panel's factor block Udp).
+template <class T, bool LDL = false>
 __global__ void __launch_bounds__(256) chol_panel_kernel(T* __restrict__ W, i64 ldw, int n, int r, int nb, int rp, int kpend,
-                                                         T* __restrict__ Ud, int* __restrict__ info) {
+                                                         T* __restrict__ Ud, int* __restrict__ info,
+                                                         T* __restrict__ Yw = nullptr, const T* __restrict__ Udp = nullptr) {
   using R = typename Sc<T>::real;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PanelSmem<T>& sm = *reinterpret_cast<PanelSmem<T>*>(smem_raw);
@@ -330,8 +337,9 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(T* __restrict__ W, i64 
     __syncthreads();
     for (int k = 0; k < kn; ++k) {
       T ui[4], uc[4], us[2];
+      const R dk = LDL ? re(Udp[(i64)(kc + k) * CB + kc + k]) : R(1);   // LDL: (D U)^H U, d of the pending row
 #pragma unroll
-      for (int a = 0; a < 4; ++a) ui[a] = cj(sm.P[k][ty + 16 * a]);
+      for (int a = 0; a < 4; ++a) ui[a] = cj(LDL ? scale_real(sm.P[k][ty + 16 * a], dk) : sm.P[k][ty + 16 * a]);
 #pragma unroll
       for (int b = 0; b < 4; ++b) uc[b] = sm.P[k][tx + 16 * b];
 #pragma unroll
@@ -347,7 +355,7 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(T* __restrict__ W, i64 
     }
   }
   // ---- factorisation of the diagonal block (registers), redundantly in every CTA
-  const int bad = factor_block_regs<T>(s, nb, sm.rowbuf, sm.dinv);
+  const int bad = factor_block_regs<T, LDL>(s, nb, sm.rowbuf, sm.dinv);
   if (bad) {
     if (blockIdx.x == 0 && tid == 0) atomicCAS(info, 0, r + bad);
     return;
@@ -359,7 +367,7 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(T* __restrict__ W, i64 
     for (int b = 0; b < 4; ++b) {
       const int i = ty + 16 * a, c = tx + 16 * b;
       sm.S[i][c] = s[a][b];
-      sm.X[i][c] = (i == c) ? Sc<T>::from_real(i < nb ? sm.dinv[i] : R(1)) : Sc<T>::zero();
+      sm.X[i][c] = (i == c) ? Sc<T>::from_real((!LDL && i < nb) ? sm.dinv[i] : R(1)) : Sc<T>::zero();   // LDL: unit factor
       if (blockIdx.x == 0 && i <= c && c < nb) Ud[(i64)c * CB + i] = s[a][b];
     }
 #pragma unroll
@@ -428,7 +436,14 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(T* __restrict__ W, i64 
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
         const int i = ty + 16 * a;
-        if (c < sw && i < nb) W[(i64)(c0 + c) * ldw + r + i] = acc[a][b];
+        if (c < sw && i < nb) {
+          if (LDL) {   // acc = (D U)(i, c): keep it for the trailing updates, store U = D^-1 acc
+            Yw[(i64)(c0 + c) * ldw + r + i] = acc[a][b];
+            W[(i64)(c0 + c) * ldw + r + i] = scale_real(acc[a][b], sm.dinv[i]);
+          } else {
+            W[(i64)(c0 + c) * ldw + r + i] = acc[a][b];
+          }
+        }
       }
     }
   }
@@ -454,6 +469,7 @@ struct CholCtx {
   T* Uinv;   // one CB x CB inverse per diagonal block
   int* info;
   cudaStream_t st;
+  T* Y = nullptr;   // LDL only: D U, same shape as W
 };
 
 static i64 split_point(i64 n) {
@@ -525,13 +541,13 @@ static bool use_panel_path() {
   return !Sc<T>::is_complex && !off;   // ComplexF64: the panel kernel's tiles do not fit in shared memory
 }
 
-template <class T>
+template <class T, bool LDL = false>
 static int chol_right_looking(CholCtx<T>& cx, i64 n) {
   if constexpr (Sc<T>::is_complex) {
     return GLA_ERR_INTERNAL;
   } else {
     const int smem = (int)sizeof(PanelSmem<T>);
-    GLA_TRY(ensure_dyn_smem((const void*)chol_panel_kernel<T>, smem));
+    GLA_TRY(ensure_dyn_smem((const void*)chol_panel_kernel<T, LDL>, smem));
     static const int dbg_skip = [] {   // timing experiments only: 1 = no trailing updates, 2 = no panel kernels
       const char* e = getenv("GLA_CHOL_DEBUG_SKIP");
       return e ? atoi(e) : 0;
@@ -540,8 +556,9 @@ static int chol_right_looking(CholCtx<T>& cx, i64 n) {
       if (dbg_skip == 2) return 0;
       const i64 ncols = n - (r + nb);
       const unsigned grid = (unsigned)(ncols > 0 ? ceil_div(ncols, SW) : 1);
-      chol_panel_kernel<T><<<grid, 256, smem, cx.st>>>(cx.W, cx.ldw, (int)n, (int)r, (int)nb, (int)rp, (int)kpend,
-                                                       cx.Uinv + (r / CB) * CB * CB, cx.info);
+      chol_panel_kernel<T, LDL><<<grid, 256, smem, cx.st>>>(cx.W, cx.ldw, (int)n, (int)r, (int)nb, (int)rp, (int)kpend,
+                                                            cx.Uinv + (r / CB) * CB * CB, cx.info, cx.Y,
+                                                            cx.Uinv + (rp / CB) * CB * CB);
       return check_cuda(cudaGetLastError(), __FILE__, __LINE__);
     };
     // Look-ahead: the sequential chain (panel kernels + the update of the NEXT outer block's 128 rows) runs on a cached
@@ -560,8 +577,8 @@ static int chol_right_looking(CholCtx<T>& cx, i64 n) {
     const cudaStream_t caller = cx.st;
     auto update = [&](i64 r0, i64 K, i64 c0, i64 mrows, cudaStream_t s) -> int {   // W(c0 : c0+mrows, c0 : n) -= U(r0 : r0+K, .)^H U(r0 : r0+K, .)
       GemmTN<T> g;                                                                  // (rankUpdate!, :51), upper part only
-      g.At = cx.W + r0 + c0 * cx.ldw; g.ldat = cx.ldw;
-      g.B = g.At; g.ldb = cx.ldw;
+      g.At = (LDL ? cx.Y : cx.W) + r0 + c0 * cx.ldw; g.ldat = cx.ldw;   // LDL: (D U)^H U
+      g.B = cx.W + r0 + c0 * cx.ldw; g.ldb = cx.ldw;
       g.C = cx.W + c0 + c0 * cx.ldw; g.ldc = cx.ldw;
       g.M = mrows; g.N = n - c0; g.K = K;
       g.alpha = -1; g.beta_one = 1; g.conj_a = 1; g.lower_only = 2;
@@ -648,6 +665,68 @@ int potrf_recursive_L_dev(T* dA, i64 n, i64 lda, i64 /*cutoff*/, int* dinfo, cud
   return rc;
 }
 
+// W(i,j) = A(i,j) for i <= j (upper triangle as it is; strict lower zeroed) and back: the 'U' variant of ldlt!
+template <class T>
+__global__ void upper_in_kernel(const T* __restrict__ A, i64 lda, T* __restrict__ W, i64 ldw, int n) {
+  const i64 total = (i64)n * n;
+  for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
+    const int j = (int)(e / n), i = (int)(e - (i64)j * n);
+    W[(i64)j * ldw + i] = i <= j ? A[(i64)j * lda + i] : Sc<T>::zero();
+  }
+}
+template <class T>
+__global__ void upper_out_kernel(T* __restrict__ A, i64 lda, const T* __restrict__ W, i64 ldw, int n) {
+  const i64 total = (i64)n * n;
+  for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
+    const int j = (int)(e / n), i = (int)(e - (i64)j * n);
+    if (i <= j) A[(i64)j * lda + i] = W[(i64)j * ldw + i];
+  }
+}
+
+// ldlt!(Hermitian(A, uplo), blocksize) without pivoting (src/ldlt.jl:80-162): in place, D on the diagonal, the unit
+// factor in the strict `uplo` triangle, the other triangle untouched.  Real element types on the fused panel kernel
+// (the mirror holds the unit UPPER factor of W = U^H D U; 'L': W = tril(A)^H, 'U': W = triu(A)).  A zero pivot stops
+// the factorisation: *dinfo = its 1-based index (the reference would divide by it).
+template <class T>
+int ldlt_dev(T* dA, i64 n, i64 lda, int upper, int* dinfo, cudaStream_t st) {
+  if (n < 0) return -2;
+  if (lda < (n > 1 ? n : 1)) return -3;
+  if (n == 0) return 0;
+  if (!dA) return -1;
+  if (!dinfo) return -5;
+  if constexpr (Sc<T>::is_complex) {
+    return -1;   // no ComplexF64 method: stays on the reference path
+  } else {
+    CholCtx<T> cx;
+    cx.ldw = round_up(n, 16);
+    cx.st = st;
+    cx.info = dinfo;
+    const i64 nblk = (n + CB - 1) / CB;
+    void* block = nullptr;
+    const i64 wbytes = round_up(cx.ldw * n * sizeof(T), 256);
+    GLA_TRY(pool_malloc(&block, 2 * wbytes + nblk * CB * CB * sizeof(T), st));
+    cx.W = static_cast<T*>(block);
+    cx.Y = reinterpret_cast<T*>(static_cast<char*>(block) + wbytes);
+    cx.Uinv = reinterpret_cast<T*>(static_cast<char*>(block) + 2 * wbytes);
+    dim3 tb(32, 8), grid((unsigned)ceil_div(n, 32), (unsigned)ceil_div(n, 32));
+    const unsigned g1 = (unsigned)(ceil_div((i64)n * n, 256) > 4096 ? 4096 : ceil_div((i64)n * n, 256));
+    int rc = check_cuda(cudaMemsetAsync(dinfo, 0, sizeof(int), st), __FILE__, __LINE__);
+    if (!rc) {
+      if (upper) upper_in_kernel<T><<<g1, 256, 0, st>>>(dA, lda, cx.W, cx.ldw, (int)n);
+      else mirror_in_kernel<T><<<grid, tb, 0, st>>>(dA, lda, cx.W, cx.ldw, (int)n);
+      rc = check_cuda(cudaGetLastError(), __FILE__, __LINE__);
+    }
+    if (!rc) rc = chol_right_looking<T, true>(cx, n);
+    if (!rc) {
+      if (upper) upper_out_kernel<T><<<g1, 256, 0, st>>>(dA, lda, cx.W, cx.ldw, (int)n);
+      else mirror_out_kernel<T><<<grid, tb, 0, st>>>(dA, lda, cx.W, cx.ldw, (int)n);
+      rc = check_cuda(cudaGetLastError(), __FILE__, __LINE__);
+    }
+    cudaFreeAsync(block, st);
+    return rc;
+  }
+}
+
 // C(lower) += alpha * A A^H,  A n x k (lda)      rankUpdate!(Hermitian(C,:L), A, alpha)
 template <class T>
 int herk_lower_dev(T* dC, i64 n, i64 ldc, const T* dA, i64 k, i64 lda, typename Sc<T>::real alpha,
@@ -676,7 +755,8 @@ int herk_lower_dev(T* dC, i64 n, i64 ldc, const T* dA, i64 k, i64 lda, typename 
 
 #define INST(T)                                                                  \
   template int potrf_recursive_L_dev<T>(T*, i64, i64, i64, int*, cudaStream_t);  \
-  template int herk_lower_dev<T>(T*, i64, i64, const T*, i64, i64, typename Sc<T>::real, cudaStream_t);
+  template int herk_lower_dev<T>(T*, i64, i64, const T*, i64, i64, typename Sc<T>::real, cudaStream_t); \
+  template int ldlt_dev<T>(T*, i64, i64, int, int*, cudaStream_t);
 INST(float)
 INST(double)
 INST(zd)

@@ -42,6 +42,9 @@ int tsqr_allreduce_dev(void* comm, int nranks, const double* dRloc, i64 n, doubl
 // K6: Cholesky (chol.cu)
 template <class T>
 int potrf_recursive_L_dev(T* dA, i64 n, i64 lda, i64 cutoff, int* dinfo, cudaStream_t st);
+// ldlt!(Hermitian(A, uplo)) without pivoting (src/ldlt.jl:80-162); real element types
+template <class T>
+int ldlt_dev(T* dA, i64 n, i64 lda, int upper, int* dinfo, cudaStream_t st);
 template <class T>
 int herk_lower_dev(T* dC, i64 n, i64 ldc, const T* dA, i64 k, i64 lda, typename Sc<T>::real alpha,
                    cudaStream_t st);

@@ -42,10 +42,15 @@ class ArgumentError(ValueError):
 
 
 GLA_ERR_NOT_POSDEF = 900
+GLA_ERR_SINGULAR = 901
 
 
 class DomainError(ArithmeticError):
     """Julia's DomainError (sqrt of a negative pivot inside cholRecursive!)."""
+
+
+class ZeroPivotError(ArithmeticError):
+    """ldlt!: a zero pivot (the reference divides by it and carries Inf/NaN on)."""
 
 
 class GLACudaError(RuntimeError):
@@ -77,6 +82,9 @@ def _check(rc, what, neg=DimensionMismatch):
     if rc == GLA_ERR_NOT_POSDEF:
         k = int(lib().gla_last_info())
         raise DomainError(f"{what}: leading minor {k} is not positive definite (sqrt of a non-positive pivot)", k)
+    if rc == GLA_ERR_SINGULAR:
+        k = int(lib().gla_last_info())
+        raise ZeroPivotError(f"{what}: pivot {k} is zero", k)
     raise GLACudaError(f"{what}: unexpected return code {rc}")
 
 
@@ -360,6 +368,23 @@ def cholBlocked_(A, uplo="L", blocksize: int = 64):
         raise DimensionMismatch(f"matrix is not square: dimensions are {A.shape}")
     _check(_fn("potrf_blocked_L", A.dtype)(_ptr(A), _I64(A.shape[0]), _I64(lda), _I64(blocksize)), "potrf_blocked_L",
            ArgumentError)
+    return A
+
+
+def ldlt_(A, uplo="L", blocksize=None):
+    """LinearAlgebra.ldlt!(Hermitian(A, uplo), blocksize) of the reference (src/ldlt.jl:155-162), without pivoting:
+    in place, D on the diagonal, the unit factor in the strict `uplo` triangle.  Float32 / Float64."""
+    lda = _colmajor(A, "ldlt!")
+    if A.shape[0] != A.shape[1]:
+        raise DimensionMismatch(f"matrix is not square: dimensions are {A.shape}")
+    if A.dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
+        raise TypeError("ldlt!: only Float32/Float64 have a GPU method; other element types stay on the reference path")
+    u = uplo[-1]
+    if u not in ("L", "U"):
+        raise ArgumentError("uplo must be :L or :U")
+    bs = max(1, 128 // A.dtype.itemsize) if blocksize is None else int(blocksize)
+    rc = _fn("ldlt", A.dtype)(_ptr(A), _I64(A.shape[0]), _I64(lda), C.c_int(ord(u)), _I64(bs))
+    _check(rc, "ldlt", ArgumentError)
     return A
 
 

@@ -152,6 +152,19 @@ for T in (Float32, Float64, ComplexF64)
     end
 end
 
+# gla_{s,d}ldlt: LDL^H without pivoting, in place                      (ldlt!, src/ldlt.jl:155-162; real types only)
+const GLA_ERR_SINGULAR = Cint(901)
+for (T, sym) in ((Float32, :gla_sldlt), (Float64, :gla_dldlt))
+    @eval function ldlt_inplace!(A::Matrix{$T}, uplo::Char, blocksize::Integer)
+        n = LinearAlgebra.checksquare(A)
+        rc = GC.@preserve A ccall(($(QuoteNode(sym)), libgla), Cint,
+            (Ptr{$T}, Int64, Int64, Cint, Int64), A, n, max(1, stride(A, 2)), Cint(uplo), blocksize)
+        rc == GLA_ERR_SINGULAR && throw(SingularException(Int(last_info())))
+        chk(rc, "ldlt_inplace!")
+        return A
+    end
+end
+
 # R factor of a tall-skinny Float64 matrix by a TSQR tree (BASELINE configs[3]); row signs: DESIGN.md
 function tsqrR(A::Matrix{Float64})
     m, n = size(A)

@@ -50,6 +50,7 @@ extern "C" {
 #endif
 
 #define GLA_ERR_NOT_POSDEF 900
+#define GLA_ERR_SINGULAR 901   /* ldlt: zero pivot, 1-based index in gla_last_info() */
 #define GLA_ERR_CUDA 1000
 #define GLA_ERR_NCCL 2000
 
@@ -172,6 +173,17 @@ GLA_API int gla_zpotrf_unblocked_L(void* A, int64_t n, int64_t lda);
 GLA_API int gla_spotrf_blocked_L(float* A, int64_t n, int64_t lda, int64_t blocksize);
 GLA_API int gla_dpotrf_blocked_L(double* A, int64_t n, int64_t lda, int64_t blocksize);
 GLA_API int gla_zpotrf_blocked_L(void* A, int64_t n, int64_t lda, int64_t blocksize);
+
+/* ---- LDL^H without pivoting -----------------------------------------------------------
+ * replaces ldlt!(A::Hermitian, blocksize)   src/ldlt.jl:155-162  ->  _ldlt_lower_blocked! (:80-103) for uplo = 'L',
+ * _ldlt_upper_blocked! (:122-146) for uplo = 'U'.  In place: D on the diagonal, the unit factor in the strict `uplo`
+ * triangle, the other triangle untouched; `blocksize` >= 1 is a hint (the reference's default is 128 / sizeof(T)).
+ * Float32 / Float64 only (ComplexF64, Quaternion, Rational stay on the reference path).  A zero pivot returns
+ * GLA_ERR_SINGULAR with its index in gla_last_info() (the reference divides by it). */
+GLA_API int gla_sldlt(float* A, int64_t n, int64_t lda, int uplo, int64_t blocksize);
+GLA_API int gla_dldlt(double* A, int64_t n, int64_t lda, int uplo, int64_t blocksize);
+GLA_API int gla_sldlt_dev(float* dA, int64_t n, int64_t lda, int uplo, int* dinfo, void* stream);
+GLA_API int gla_dldlt_dev(double* dA, int64_t n, int64_t lda, int uplo, int* dinfo, void* stream);
 
 /* ---- workspace query ------------------------------------------------------------------
  * the reference's FFI precedent asks LAPACK for its workspace before the call (src/lapack.jl:152-170,

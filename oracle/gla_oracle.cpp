@@ -364,6 +364,100 @@ int chol_recursive(T* A, i64 n, i64 lda, i64 cutoff, i64 off, int mt) {
   return chol_recursive(A22, n - n2, lda, cutoff, off + n2, mt);
 }
 
+// ---------------------------------------------------------------------------------
+// LDL^H without pivoting                             src/ldlt.jl
+//   _ldlt_lower!  :17-35   delta = A[1,1]; l = a/delta; A_-(lower) -= l*delta*l';  recurse
+//   _ldlt_upper!  :50-64   delta = A[1,1]; u^T = a^T/delta; A_-(upper) -= conj(u)*delta*u^T; recurse
+//   _ldlt_lower_blocked! :80-103, _ldlt_upper_blocked! :122-146  (rdiv!/ldiv! with the unit triangle, then with D,
+//   then the k-innermost rank update with workspace = d .* conj(row))
+// Only the named triangle is read or written; the diagonal holds D, the strict triangle the unit factor.
+// ---------------------------------------------------------------------------------
+template <class T>
+void ldlt_lower_unblocked(T* A, i64 n, i64 lda) {
+  for (i64 k = 0; k + 1 <= n; ++k) {
+    T* a = A + k + k * lda;
+    const i64 m = n - k;
+    const T delta = a[0];
+    for (i64 i = 1; i < m; ++i) a[i] = a[i] / delta;
+    for (i64 j = 1; j < m; ++j) {
+      const T ljd = a[j] * delta;
+      for (i64 i = j; i < m; ++i) a[i + j * lda] -= a[i] * cj(ljd);
+    }
+    if (m <= 2 && k + 2 >= n) { /* the reference recurses only while n > 2: a trailing 1x1 block is left as is */ }
+  }
+}
+template <class T>
+void ldlt_upper_unblocked(T* A, i64 n, i64 lda) {
+  for (i64 k = 0; k + 1 <= n; ++k) {
+    T* a = A + k + k * lda;
+    const i64 m = n - k;
+    const T delta = a[0];
+    for (i64 j = 1; j < m; ++j) {
+      const T dl = a[j * lda];
+      a[j * lda] = dl / delta;
+      for (i64 i = 1; i <= j; ++i) a[i + j * lda] -= cj(a[i * lda]) * dl;
+    }
+  }
+}
+template <class T>
+void ldlt_lower_blocked(T* A, i64 n, i64 lda, i64 bs) {
+  std::vector<T> ws((size_t)bs);
+  for (i64 k = 0; k < n; k += bs) {
+    T* A11 = A + k + k * lda;
+    const i64 m = n - k;
+    if (bs >= m) {
+      ldlt_lower_unblocked(A11, m, lda);
+      return;
+    }
+    ldlt_lower_unblocked(A11, bs, lda);
+    T* A21 = A11 + bs;
+    const i64 r = m - bs;
+    // rdiv!(A21, UnitLowerTriangular(A11)'):  x_j = x_j - sum_{l<j} x_l conj(L[j,l])
+    for (i64 j = 0; j < bs; ++j)
+      for (i64 l = 0; l < j; ++l) {
+        const T c = cj(A11[j + l * lda]);
+        for (i64 i = 0; i < r; ++i) A21[i + j * lda] -= A21[i + l * lda] * c;
+      }
+    for (i64 j = 0; j < bs; ++j) {
+      const T d = A11[j + j * lda];
+      for (i64 i = 0; i < r; ++i) A21[i + j * lda] = A21[i + j * lda] / d;
+    }
+    T* A22 = A11 + bs + bs * lda;
+    for (i64 j = 0; j < r; ++j) {
+      for (i64 q = 0; q < bs; ++q) ws[q] = A11[q + q * lda] * cj(A21[j + q * lda]);
+      for (i64 i = j; i < r; ++i)
+        for (i64 q = 0; q < bs; ++q) A22[i + j * lda] -= A21[i + q * lda] * ws[q];
+    }
+  }
+}
+template <class T>
+void ldlt_upper_blocked(T* A, i64 n, i64 lda, i64 bs) {
+  std::vector<T> ws((size_t)bs);
+  for (i64 k = 0; k < n; k += bs) {
+    T* A11 = A + k + k * lda;
+    const i64 m = n - k;
+    if (bs >= m) {
+      ldlt_upper_unblocked(A11, m, lda);
+      return;
+    }
+    ldlt_upper_unblocked(A11, bs, lda);
+    T* U12 = A11 + bs * lda;
+    const i64 r = m - bs;
+    // ldiv!(UnitUpperTriangular(A11)', U12):  row i: x_i = x_i - sum_{l<i} conj(U[l,i]) x_l
+    for (i64 c = 0; c < r; ++c)
+      for (i64 i = 0; i < bs; ++i)
+        for (i64 l = 0; l < i; ++l) U12[i + c * lda] -= cj(A11[l + i * lda]) * U12[l + c * lda];
+    for (i64 c = 0; c < r; ++c)
+      for (i64 i = 0; i < bs; ++i) U12[i + c * lda] = U12[i + c * lda] / A11[i + i * lda];
+    T* A22 = A11 + bs + bs * lda;
+    for (i64 j = 0; j < r; ++j) {
+      for (i64 q = 0; q < bs; ++q) ws[q] = A11[q + q * lda] * U12[q + j * lda];
+      for (i64 i = 0; i <= j; ++i)
+        for (i64 q = 0; q < bs; ++q) A22[i + j * lda] -= cj(U12[q + i * lda]) * ws[q];
+    }
+  }
+}
+
 }  // namespace
 
 #define ORACLE_API extern "C" __attribute__((visibility("default")))
@@ -415,6 +509,10 @@ int chol_recursive(T* A, i64 n, i64 lda, i64 cutoff, i64 off, int mt) {
   }                                                                                                \
   ORACLE_API int oracle_##P##chol_recursive(T* A, i64 n, i64 lda, i64 cutoff, int mt) {            \
     return chol_recursive<T>(A, n, lda, cutoff, 0, mt);                                            \
+  }                                                                                                \
+  ORACLE_API void oracle_##P##ldlt(T* A, i64 n, i64 lda, i64 bs, int upper) {                      \
+    if (upper) ldlt_upper_blocked<T>(A, n, lda, bs);                                               \
+    else ldlt_lower_blocked<T>(A, n, lda, bs);                                                     \
   }
 
 DEFINE_TYPE(s, float, float)

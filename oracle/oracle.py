@@ -213,3 +213,16 @@ def chol_blocked(A, blocksize):
 def chol_recursive(A, cutoff=1, mt=False):
     """cholRecursive!(A, Val{:L}, cutoff).  src/cholesky.jl:37-55 (strict upper untouched)."""
     return _chol("chol_recursive", A, _I64(cutoff), C.c_int(1 if mt else 0))
+
+
+def ldlt(A, uplo="L", blocksize=None):
+    """ldlt!(Hermitian(A, uplo), blocksize) (src/ldlt.jl:155-162 -> _ldlt_lower_blocked! / _ldlt_upper_blocked!):
+    in place, D on the diagonal, the unit factor in the strict `uplo` triangle; the other triangle is untouched.
+    Default blocksize = max(1, 128 / sizeof(T)) as in the reference."""
+    A = _f(A)
+    n = A.shape[0]
+    if A.shape[1] != n:
+        raise ValueError("DimensionMismatch: matrix is not square")
+    bs = max(1, 128 // A.dtype.itemsize) if blocksize is None else int(blocksize)
+    _fn("ldlt", A)(_p(A), _I64(n), _I64(n), _I64(bs), C.c_int(1 if uplo in ("U", ":U") else 0))
+    return A

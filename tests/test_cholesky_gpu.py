@@ -129,3 +129,55 @@ def test_panel_path_matches_recursion_bitwise_shape(gla, oracle):
         ref = oracle.chol_recursive(S, 1, mt=True)
         assert np.max(np.abs(np.tril(got) - np.tril(ref))) <= 1e-11 * np.max(np.abs(ref))
         assert np.array_equal(np.triu(got, 1), np.triu(S, 1))
+
+
+def _hermitian_dd(rng, n, dtype, indefinite):
+    """Diagonally dominant symmetric test matrix (all leading minors well conditioned, so LDL^T without pivoting is
+    stable); with `indefinite` the diagonal alternates in sign."""
+    X = rng.standard_normal((n, n))
+    H = (X + X.T) / 2
+    d = np.abs(H).sum(axis=1) + 1.0
+    if indefinite:
+        d = d * np.where(np.arange(n) % 3 == 1, -1.0, 1.0)
+    H[np.arange(n), np.arange(n)] = d
+    return np.asfortranarray(H.astype(dtype))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("uplo", ["L", "U"])
+@pytest.mark.parametrize("n", [1, 2, 5, 50, 64, 65, 130, 500, 1000])
+def test_ldlt_vs_oracle(gla, oracle, dtype, uplo, n):
+    """ldlt!(Hermitian(A, uplo)) (src/ldlt.jl:80-162; grid of test/ldlt.jl: n in 5, 50, 500, both triangles) against the
+    oracle's restatement, the factorisation identity L D L' = A (U' D U = A), and the untouched other triangle."""
+    rng = np.random.default_rng(n + (7 if uplo == "U" else 0))
+    for indefinite in (False, True):
+        H = _hermitian_dd(rng, n, dtype, indefinite)
+        ref = oracle.ldlt(H, uplo)
+        got = gla.ldlt_(H.copy(order="F"), uplo)
+        tol = (3e-5 if dtype == np.float32 else 1e-12) * max(n, 10)
+        tri = np.tril if uplo == "L" else np.triu
+        assert np.max(np.abs(tri(got) - tri(ref))) <= tol * np.max(np.abs(tri(ref)))
+        other = (np.triu(got, 1), np.triu(H, 1)) if uplo == "L" else (np.tril(got, -1), np.tril(H, -1))
+        assert np.array_equal(*other)
+        d = np.diag(got).astype(np.float64)
+        if indefinite and n >= 5:
+            assert d.min() < 0 < d.max()
+        F = tri(got, -1 if uplo == "L" else 1).astype(np.float64) + np.eye(n)
+        R = F @ np.diag(d) @ F.T if uplo == "L" else F.T @ np.diag(d) @ F
+        Hs = np.tril(H) + np.tril(H, -1).T if uplo == "L" else np.triu(H) + np.triu(H, 1).T
+        assert np.max(np.abs(R - Hs)) <= tol * np.max(np.abs(Hs))
+
+
+def test_ldlt_zero_pivot_and_errors(gla):
+    A = np.asfortranarray(np.eye(70) * 3.0)
+    A[10, 10] = 0.0
+    with pytest.raises(gla.ZeroPivotError) as ei:
+        gla.ldlt_(A)
+    assert ei.value.args[1] == 11
+    with pytest.raises(gla.DimensionMismatch):
+        gla.ldlt_(np.zeros((3, 4), order="F"))
+    with pytest.raises(TypeError):
+        gla.ldlt_(np.asfortranarray(np.eye(3, dtype=np.complex128)))
+    # the doc example of the reference (src/ldlt.jl docstring): [1 1; 1 -1] -> L = [1 0; 1 1], D = (1, -2)
+    got = gla.ldlt_(np.asfortranarray(np.array([[1.0, 1.0], [1.0, -1.0]])), "U")
+    assert np.array_equal(got, np.array([[1.0, 1.0], [1.0, -2.0]]))

@@ -129,3 +129,32 @@ def test_error_paths(oracle):
         oracle.reflector_apply_right(np.zeros((5, 5)), np.zeros(4), 1.0)       # test/qr.jl:29-33
     with pytest.raises(ValueError):
         oracle.block_apply(np.zeros((5, 2)), np.zeros((2, 2)), np.zeros((4, 3)))
+
+
+def test_ldlt_restatement(oracle):
+    """ldlt!(Hermitian(A, uplo)) (src/ldlt.jl:80-162): the factorisation identity for both triangles and several block
+    sizes, the docstring example of the reference, and the untouched other triangle."""
+    rng = np.random.default_rng(9)
+    for dtype in (np.float64, np.complex128):
+        for n in (1, 2, 5, 50, 130):
+            X = rng.standard_normal((n, n))
+            if dtype == np.complex128:
+                X = X + 1j * rng.standard_normal((n, n))
+            P = (X @ X.conj().T + n * np.eye(n)).astype(dtype)      # Hermitian positive definite: no pivoting needed
+            for uplo in ("L", "U"):
+                for bs in (1, 7, 16, 200):
+                    F = oracle.ldlt(P, uplo, bs)
+                    d = np.diag(F)
+                    if uplo == "L":
+                        L = np.tril(F, -1) + np.eye(n)
+                        R = L @ np.diag(d) @ L.conj().T
+                        assert np.array_equal(np.triu(F, 1), np.triu(P, 1))
+                    else:
+                        U = np.triu(F, 1) + np.eye(n)
+                        R = U.conj().T @ np.diag(d) @ U
+                        assert np.array_equal(np.tril(F, -1), np.tril(P, -1))
+                    assert np.max(np.abs(R - P)) <= 1e-12 * n * np.max(np.abs(P))
+    got = oracle.ldlt(np.array([[1.0, 1.0], [1.0, -1.0]]), "U")
+    assert np.array_equal(got, np.array([[1.0, 1.0], [1.0, -2.0]]))
+    got = oracle.ldlt(np.array([[1.0, 1.0], [1.0, 1.0]]), "L")
+    assert np.array_equal(got, np.array([[1.0, 1.0], [1.0, 0.0]]))
