@@ -5,7 +5,7 @@
 // the reference omits at :72)  ->  trailing update A2 <- (I - V T^H V^H) A2 (src/householder.jl:119-157).
 //
 // GPU structure: panels of NB = 64 columns, grouped six at a time into outer blocks of NBO = 384 whose
-// reflectors hit the far trailing matrix in one K = 256 pass (wy_fixup_kernel).  Per panel:
+// reflectors hit the far trailing matrix in one K = 384 pass (apply_outer).  Per panel:
 //   qr_panel_kernel   cooperative, P CTAs each holding a row slab of the panel in shared memory;
 //                     ONE grid-wide reduction per column: every CTA publishes the partial dots
 //                     d_c = sum_{i>j} conj(a_ij) a_ic of the un-normalised pivot column with every
@@ -657,125 +657,14 @@ __global__ void __launch_bounds__(256) larft_finish_kernel(const T* __restrict__
   }
 }
 
-// W2(kk x nA, ld NB) = op(T) * sum_z Wp[z]   op = T^H (adjoint apply, Q^H A) or T (Q A)
-template <class T>
-__global__ void __launch_bounds__(256) apply_t_kernel(const T* __restrict__ Wp, i64 wstride, int nsplit, int kk,
-                                                      i64 nA, const T* __restrict__ Tm, i64 ldt, int adjoint,
-                                                      T* __restrict__ W2) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  typedef T RowT[NB + 1];
-  typedef T RowW[32 + 1];
-  RowT* sT = reinterpret_cast<RowT*>(smem_raw);       // sT[i][l] = op(T)(i,l)
-  RowW* sW = reinterpret_cast<RowW*>(sT + NB);        // sW[l][jj]
-  const int tid = threadIdx.x;
-  for (int e = tid; e < kk * kk; e += blockDim.x) {
-    const int l = e / kk, i = e - l * kk;  // element (i,l) of op(T)
-    T v;
-    if (adjoint) v = (l <= i) ? cj(ldcg_t(Tm + (i64)i * ldt + l)) : Sc<T>::zero();  // T^H(i,l) = conj(T(l,i))
-    else v = (i <= l) ? ldcg_t(Tm + (i64)l * ldt + i) : Sc<T>::zero();
-    sT[i][l] = v;
-  }
-  const i64 j0 = (i64)blockIdx.x * 32;
-  for (int e = tid; e < kk * 32; e += blockDim.x) {
-    const int jj = e / kk, l = e - jj * kk;
-    T w = Sc<T>::zero();
-    if (j0 + jj < nA) {
-      w = ldcg_t(Wp + (j0 + jj) * NB + l);
-      for (int z = 1; z < nsplit; ++z) w = w + ldcg_t(Wp + (i64)z * wstride + (j0 + jj) * NB + l);
-    }
-    sW[l][jj] = w;
-  }
-  __syncthreads();
-  for (int e = tid; e < kk * 32; e += blockDim.x) {
-    const int jj = e / kk, i = e - jj * kk;
-    if (j0 + jj >= nA) continue;
-    T s = Sc<T>::zero();
-    const int lbeg = adjoint ? 0 : i, lend = adjoint ? i + 1 : kk;
-    for (int l = lbeg; l < lend; ++l) s = fmad(sT[i][l], sW[l][jj], s);
-    W2[(j0 + jj) * NB + i] = s;
-  }
-}
-
-// ------------------------------------------------------------------------------- outer-block fix-up
+// ------------------------------------------------------------------------------- outer-block recurrence
 // Two-level blocking: NBO/NB consecutive panels form one OUTER block whose reflectors are applied to the
 // far trailing matrix in a single pass with K = NBO (K = NB would make that pass HBM-bound: 16 B of C
 // traffic per 2*NB flops).  With V = [V_0 .. V_{nj-1}], W = V^H A2 and G = V^H V, the product
 // Q_{nj-1}^H ... Q_0^H A2 = A2 - V Z follows from the block recurrence
 //     Y_j = W_j - sum_{i<j} G_ji Z_i ,   Z_j = T_j^H Y_j ,
-// which needs only the per-panel T_j (never the NBO x NBO T).  One CTA handles 32 columns of W.
-template <class T>
-__global__ void __launch_bounds__(256)
-    wy_fixup_kernel(const T* __restrict__ Wp, i64 wstride, int nsplit, int kbig, i64 nA, const T* __restrict__ G,
-                    i64 ldg, const T* __restrict__ Tm, int ldw, T* __restrict__ Z) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  typedef T RowW[32 + 1];
-  typedef T RowM[NB + 1];
-  RowW* sW = reinterpret_cast<RowW*>(smem_raw);          // sW[l][jj], l < kbig
-  RowM* sM = reinterpret_cast<RowM*>(sW + kbig);         // 64 x 64 operand block
-  const int tid = threadIdx.x;
-  const int jj = tid & 31, rq = tid >> 5;                 // column within the 32, row phase (8 phases)
-  const i64 col = (i64)blockIdx.x * 32 + jj;
-  for (int l = rq; l < kbig; l += 8) {
-    T w = Sc<T>::zero();
-    if (col < nA) {
-      w = ldcg_t(Wp + col * ldw + l);
-      for (int z = 1; z < nsplit; ++z) w = w + ldcg_t(Wp + (i64)z * wstride + col * ldw + l);
-    }
-    sW[l][jj] = w;
-  }
-  const int nj = (kbig + NB - 1) / NB;
-  for (int j = 0; j < nj; ++j) {
-    const int rows_j = (kbig - j * NB) < NB ? (kbig - j * NB) : NB;
-    for (int i = 0; i < j; ++i) {
-      __syncthreads();
-      for (int e = tid; e < rows_j * NB; e += 256) {       // sM[r][l] = G(jNB + r, iNB + l)
-        const int l = e / rows_j, r = e - l * rows_j;
-        sM[r][l] = ldcg_t(G + (i64)(i * NB + l) * ldg + j * NB + r);
-      }
-      __syncthreads();
-      // register tile: 8 rows (rq, rq+8, ...) per thread share every load of W (9 LDS per 8 FMA instead of 16)
-      T acc[NB / 8];
-#pragma unroll
-      for (int u = 0; u < NB / 8; ++u) acc[u] = Sc<T>::zero();
-#pragma unroll 4
-      for (int l = 0; l < NB; ++l) {
-        const T wv = sW[i * NB + l][jj];
-#pragma unroll
-        for (int u = 0; u < NB / 8; ++u) acc[u] = fmad(sM[rq + 8 * u][l], wv, acc[u]);
-      }
-#pragma unroll
-      for (int u = 0; u < NB / 8; ++u) {
-        const int r = rq + 8 * u;                          // only this thread touches (jNB+r, jj)
-        if (r < rows_j) sW[j * NB + r][jj] = sW[j * NB + r][jj] - acc[u];
-      }
-    }
-    __syncthreads();
-    const T* Tj = Tm + (i64)j * NB * NB;
-    for (int e = tid; e < rows_j * rows_j; e += 256) {     // sM[r][l] = conj(T_j(l, r)), l <= r
-      const int r = e / rows_j, l = e - r * rows_j;
-      sM[r][l] = l <= r ? cj(ldcg_t(Tj + (i64)r * NB + l)) : Sc<T>::zero();
-    }
-    __syncthreads();
-    T out[NB / 8];
-#pragma unroll
-    for (int u = 0; u < NB / 8; ++u) out[u] = Sc<T>::zero();
-    for (int l = 0; l < rows_j; ++l) {                     // sM is zero right of the diagonal; the row guard is
-      const T wv = sW[j * NB + l][jj];                     // warp-uniform (rq is), so dead rows are skipped
-#pragma unroll
-      for (int u = 0; u < NB / 8; ++u)
-        if (rq + 8 * u >= l) out[u] = fmad(sM[rq + 8 * u][l], wv, out[u]);
-    }
-    __syncthreads();
-#pragma unroll
-    for (int u = 0; u < NB / 8; ++u) {
-      const int r = rq + 8 * u;
-      if (r < rows_j) sW[j * NB + r][jj] = out[u];
-    }
-  }
-  __syncthreads();
-  if (col < nA)
-    for (int l = rq; l < kbig; l += 8) Z[col * ldw + l] = sW[l][jj];
-}
+// which needs only the per-panel T_j (never the NBO x NBO T); apply_outer runs it as TN contractions on the tensor
+// pipe (a scalar one-CTA-per-32-columns kernel did the same in round 1: 280 ms against 262 ms at n = 16384).
 
 // ------------------------------------------------------------------------------- workspace
 constexpr int NBO = 384;  // outer block: K of the far trailing contractions (measured at n=16384: 256 -> 258.8 ms, 384 -> 254.0 ms, 512 -> 258.3 ms)
@@ -1033,11 +922,15 @@ static int apply_panel(QrWork<T>& w, const T* Vc, i64 ldvc, const T* VcT, i64 ld
     return GLA_ERR_INTERNAL;
   }
   GLA_TRY(gemm_tn<T>(g1, st));
-  static const bool fixup_kernel = getenv("GLA_QR_FIXUP_KERNEL") != nullptr;   // A/B switch: scalar T-apply kernel
-  if (adjoint && !fixup_kernel) {
-    // Z = T_j^H (sum of the split-K slices of W): T_j (column-major, zeros below the diagonal) is the K-contiguous
-    // operand of the TN contraction as it stands
-    if (g1.nsplit > 1) GLA_TRY(sum_splits<T>(w.Wp[0], NB, w.Wp[0], NB, g1.split_stride, g1.nsplit, kk, nA, st));
+  if (!adjoint) {
+    set_error(GLA_ERR_INTERNAL, "apply_panel is the adjoint (factorisation) form only; Q A goes through apply_outer_fwd", __FILE__,
+              __LINE__);
+    return GLA_ERR_INTERNAL;
+  }
+  // Z = T_j^H (sum of the split-K slices of W): T_j (column-major, zeros below the diagonal) is the K-contiguous
+  // operand of the TN contraction as it stands
+  if (g1.nsplit > 1) GLA_TRY(sum_splits<T>(w.Wp[0], NB, w.Wp[0], NB, g1.split_stride, g1.nsplit, kk, nA, st));
+  {
     GemmTN<T> gz;
     gz.At = Tj; gz.ldat = NB;
     gz.B = w.Wp[0]; gz.ldb = NB;
@@ -1045,12 +938,6 @@ static int apply_panel(QrWork<T>& w, const T* Vc, i64 ldvc, const T* VcT, i64 ld
     gz.M = kk; gz.N = nA; gz.K = kk;
     gz.conj_a = 1;
     GLA_TRY(gemm_tn<T>(gz, st));
-  } else {
-    const int smem_t = (NB * (NB + 1) + NB * 33) * (int)sizeof(T);
-    GLA_TRY(ensure_dyn_smem((const void*)apply_t_kernel<T>, (int)(smem_t)));
-    apply_t_kernel<T><<<(unsigned)ceil_div(nA, 32), 256, smem_t, st>>>(w.Wp[0], g1.split_stride, g1.nsplit, kk, nA, Tj,
-                                                                        NB, adjoint, w.Z[0]);
-    GLA_CUDA(cudaGetLastError());
   }
   GemmTN<T> g2;
   g2.At = VcT; g2.ldat = ldvct;
@@ -1081,14 +968,7 @@ static int apply_outer(QrWork<T>& w, int b, i64 mo, int kbig, T* A2, i64 lda, i6
     return GLA_ERR_INTERNAL;
   }
   GLA_TRY(gemm_tn<T>(g1, st));
-  static const bool fixup_kernel = getenv("GLA_QR_FIXUP_KERNEL") != nullptr;   // A/B switch: scalar fix-up kernel
-  if (fixup_kernel) {
-    const int smem = (kbig * 33 + NB * (NB + 1)) * (int)sizeof(T);
-    GLA_TRY(ensure_dyn_smem((const void*)wy_fixup_kernel<T>, (int)(smem)));
-    wy_fixup_kernel<T><<<(unsigned)ceil_div(nA, 32), 256, smem, st>>>(w.Wp[1], g1.split_stride, g1.nsplit, kbig, nA,
-                                                                       w.G[b], NBO, w.Tm[b], NBO, w.Z[1]);
-    GLA_CUDA(cudaGetLastError());
-  } else {
+  {
     // the block recurrence  Y_j = W_j - sum_{i<j} G_ji Z_i,  Z_j = T_j^H Y_j  as TN contractions on the tensor pipe:
     //   G_ji = conj(G(iNB.., jNB..))^T is the K-contiguous operand G + jNB*ldg (G is Hermitian), T_j^H likewise T_j
     if (g1.nsplit > 1)   // fixed-order sum of the split-K slices, in place into slice 0
