@@ -486,7 +486,9 @@ __global__ void __launch_bounds__(CP_THREADS, 1) qr_panel_cluster_kernel(PanelAr
     const int col = e / rows, i = e - col * rows;
     S[i * CP_LD + col] = ldcg_t(a.A + (i64)col * a.lda + r0 + i);
   }
-  __syncthreads();
+  // every CTA of the cluster must be running before anybody writes into its shared memory (compute-sanitizer:
+  // "address located in a block that might not have entered yet"); the barrier also orders the slab loads
+  cluster.sync();
 
   T pend_ixi = Sc<T>::one();   // deferred finish of the previous pivot column (rows below the diagonal *= 1/xi, diagonal <- -nu)
   R pend_nu = R(0);
