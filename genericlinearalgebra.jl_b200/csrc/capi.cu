@@ -324,6 +324,72 @@ int ldlt_host(T* A, i64 n, i64 lda, int uplo, i64 blocksize) {
   return 0;
 }
 
+// ------------------------------------------------------------------ two-sided reductions, host pointers
+template <class T>
+int bidiagonalize_host(T* A, i64 m, i64 n, i64 lda, T* taul, T* taur) {
+  if (m < 0) return -2;
+  if (n < 0) return -3;
+  if (lda < (m > 1 ? m : 1)) return -4;
+  if (m == 0 || n == 0) return 0;
+  if (!A) return -1;
+  const i64 nl = m >= n ? n : m - 1, nr = m >= n ? n - 1 : m;
+  if (nl > 0 && !taul) return -5;
+  if (nr > 0 && !taur) return -6;
+  Stream st;
+  GLA_TRY(st.create());
+  DevMatrix<T> dA;
+  DevBuf dt;
+  GLA_TRY(dA.upload(A, lda, m, n, st.s));
+  GLA_TRY(dt.alloc((size_t)(nl + nr + 2) * sizeof(T), st.s));
+  GLA_CUDA(cudaMemsetAsync(dt.p, 0, (size_t)(nl + nr + 2) * sizeof(T), st.s));
+  T* dl = dt.as<T>();
+  T* dr = dl + nl + 1;
+  Event e0, e1;
+  GLA_TRY(e0.create());
+  GLA_TRY(e1.create());
+  GLA_CUDA(cudaEventRecord(e0.e, st.s));
+  GLA_TRY(bidiagonalize_dev<T>(dA.p(), m, n, dA.ld, dl, dr, st.s));
+  GLA_CUDA(cudaEventRecord(e1.e, st.s));
+  GLA_TRY(dA.download(A, lda, m, n, st.s));
+  if (nl > 0) GLA_CUDA(cudaMemcpyAsync(taul, dl, nl * sizeof(T), cudaMemcpyDeviceToHost, st.s));
+  if (nr > 0) GLA_CUDA(cudaMemcpyAsync(taur, dr, nr * sizeof(T), cudaMemcpyDeviceToHost, st.s));
+  GLA_CUDA(cudaStreamSynchronize(st.s));
+  float ms = 0;
+  GLA_CUDA(cudaEventElapsedTime(&ms, e0.e, e1.e));
+  g_last_ms = ms;
+  return 0;
+}
+
+template <class T>
+int square_reduction_host(T* A, i64 n, i64 lda, T* tau, int which, int upper) {   // which: 0 hessenberg, 1 symtri
+  if (n < 0) return -2;
+  if (lda < (n > 1 ? n : 1)) return -3;
+  if (n == 0) return 0;
+  if (!A) return -1;
+  if (n > 1 && !tau) return which == 0 ? -4 : -5;
+  Stream st;
+  GLA_TRY(st.create());
+  DevMatrix<T> dA;
+  DevBuf dt;
+  GLA_TRY(dA.upload(A, lda, n, n, st.s));
+  GLA_TRY(dt.alloc((size_t)n * sizeof(T), st.s));
+  GLA_CUDA(cudaMemsetAsync(dt.p, 0, (size_t)n * sizeof(T), st.s));
+  Event e0, e1;
+  GLA_TRY(e0.create());
+  GLA_TRY(e1.create());
+  GLA_CUDA(cudaEventRecord(e0.e, st.s));
+  if (which == 0) GLA_TRY(hessenberg_dev<T>(dA.p(), n, dA.ld, dt.as<T>(), st.s));
+  else GLA_TRY(symtri_dev<T>(dA.p(), n, dA.ld, upper, dt.as<T>(), st.s));
+  GLA_CUDA(cudaEventRecord(e1.e, st.s));
+  GLA_TRY(dA.download(A, lda, n, n, st.s));
+  if (n > 1) GLA_CUDA(cudaMemcpyAsync(tau, dt.p, (n - 1) * sizeof(T), cudaMemcpyDeviceToHost, st.s));
+  GLA_CUDA(cudaStreamSynchronize(st.s));
+  float ms = 0;
+  GLA_CUDA(cudaEventElapsedTime(&ms, e0.e, e1.e));
+  g_last_ms = ms;
+  return 0;
+}
+
 template <class T>
 int herk_host(T* Cm, i64 n, i64 ldc, const T* A, i64 k, i64 lda, typename Sc<T>::real alpha) {
   if (n < 0) return -2;
@@ -519,6 +585,32 @@ int gla_dldlt_dev(double* dA, int64_t n, int64_t lda, int uplo, int* dinfo, void
   if (uplo != 'L' && uplo != 'U') return -4;
   return ldlt_dev<double>(dA, n, lda, uplo == 'U', dinfo, STREAM(stream));
 }
+
+// ---- two-sided reductions
+#define GLA_TWOSIDED(P, T, CT)                                                                                        \
+  int gla_##P##bidiagonalize(CT* A, int64_t m, int64_t n, int64_t lda, CT* taul, CT* taur) {                          \
+    return bidiagonalize_host<T>((T*)A, m, n, lda, (T*)taul, (T*)taur);                                               \
+  }                                                                                                                   \
+  int gla_##P##bidiagonalize_dev(CT* dA, int64_t m, int64_t n, int64_t lda, CT* dtaul, CT* dtaur, void* stream) {     \
+    return bidiagonalize_dev<T>((T*)dA, m, n, lda, (T*)dtaul, (T*)dtaur, STREAM(stream));                             \
+  }                                                                                                                   \
+  int gla_##P##hessenberg(CT* A, int64_t n, int64_t lda, CT* tau) {                                                   \
+    return square_reduction_host<T>((T*)A, n, lda, (T*)tau, 0, 0);                                                    \
+  }                                                                                                                   \
+  int gla_##P##hessenberg_dev(CT* dA, int64_t n, int64_t lda, CT* dtau, void* stream) {                               \
+    return hessenberg_dev<T>((T*)dA, n, lda, (T*)dtau, STREAM(stream));                                               \
+  }                                                                                                                   \
+  int gla_##P##symtri(CT* A, int64_t n, int64_t lda, int uplo, CT* tau) {                                             \
+    if (uplo != 'L' && uplo != 'U') return -4;                                                                        \
+    return square_reduction_host<T>((T*)A, n, lda, (T*)tau, 1, uplo == 'U');                                          \
+  }                                                                                                                   \
+  int gla_##P##symtri_dev(CT* dA, int64_t n, int64_t lda, int uplo, CT* dtau, void* stream) {                         \
+    if (uplo != 'L' && uplo != 'U') return -4;                                                                        \
+    return symtri_dev<T>((T*)dA, n, lda, uplo == 'U', (T*)dtau, STREAM(stream));                                      \
+  }
+GLA_TWOSIDED(s, float, float)
+GLA_TWOSIDED(d, double, double)
+GLA_TWOSIDED(z, zd, void)
 
 // ---- workspace query
 int64_t gla_workspace_query(int op, int elem_bytes, int64_t m, int64_t n) {

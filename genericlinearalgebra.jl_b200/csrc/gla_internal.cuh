@@ -49,4 +49,15 @@ template <class T>
 int herk_lower_dev(T* dC, i64 n, i64 ldc, const T* dA, i64 k, i64 lda, typename Sc<T>::real alpha,
                    cudaStream_t st);
 
+// ---- two-sided reductions (twosided.cu), asynchronous on `st`
+// bidiagonalize!(A) (src/svd.jl:328-381): taul / taur get n / n-1 entries for m >= n, m-1 / m for m < n
+template <class T>
+int bidiagonalize_dev(T* dA, i64 m, i64 n, i64 lda, T* dtaul, T* dtaur, cudaStream_t st);
+// _hessenberg!(A) (src/eigenGeneral.jl:18-31): tau has n-1 entries
+template <class T>
+int hessenberg_dev(T* dA, i64 n, i64 lda, T* dtau, cudaStream_t st);
+// symtriLower! / symtriUpper! (src/eigenSelfAdjoint.jl:450-564): tau has n-1 entries
+template <class T>
+int symtri_dev(T* dA, i64 n, i64 lda, int upper, T* dtau, cudaStream_t st);
+
 }  // namespace gla

@@ -445,3 +445,98 @@ def rankUpdate_(Cm, A, alpha=-1.0):
     rc = fn(Cm.ctypes.data, Cm.shape[0], ldc, A2.ctypes.data, A2.shape[1], lda, float(alpha))
     _check(rc, name)
     return Cm
+
+
+# ---------------------------------------------------------------------------------------------- two-sided reductions
+class BidiagonalFactorization:
+    """Mirror of the reference's BidiagonalFactorization (src/svd.jl:321-326): `bidiagonal` = (dv, ev, uplo),
+    `reflectors` = the in-place array, `taul`, `taur`."""
+
+    def __init__(self, dv, ev, uplo, reflectors, taul, taur):
+        self.dv, self.ev, self.uplo = dv, ev, uplo
+        self.reflectors, self.taul, self.taur = reflectors, taul, taur
+
+    @property
+    def bidiagonal(self):
+        k = self.dv.size
+        B = np.diag(self.dv)
+        if k > 1:
+            B = B + np.diag(self.ev, 1 if self.uplo == "U" else -1)
+        return B
+
+
+def bidiagonalize_(A) -> BidiagonalFactorization:
+    """bidiagonalize!(A) (src/svd.jl:328-381) on the GPU: upper bidiagonal for m >= n, lower for m < n."""
+    lda = _colmajor(A, "bidiagonalize!")
+    m, n = A.shape
+    nl, nr = (n, max(n - 1, 0)) if m >= n else (max(m - 1, 0), m)
+    taul = np.zeros(max(nl, 1), dtype=A.dtype)
+    taur = np.zeros(max(nr, 1), dtype=A.dtype)
+    rc = _fn("bidiagonalize", A.dtype)(_ptr(A), _I64(m), _I64(n), _I64(lda), _ptr(taul), _ptr(taur))
+    _check(rc, "bidiagonalize")
+    k = min(m, n)
+    off = 1 if m >= n else -1
+    dv = np.real(np.diagonal(A)[:k]).copy()
+    ev = np.real(np.diagonal(A, off)).copy()[:(nr if m >= n else nl)]
+    return BidiagonalFactorization(dv, ev, "U" if m >= n else "L", A, taul[:nl], taur[:nr])
+
+
+def hessenberg_(A):
+    """_hessenberg!(A) (src/eigenGeneral.jl:18-31) on the GPU: returns (factors, tau); H = triu(factors, -1)."""
+    lda = _colmajor(A, "hessenberg!")
+    n = A.shape[0]
+    if A.shape[1] != n:
+        raise DimensionMismatch(f"matrix is not square: dimensions are {A.shape}")   # checksquare, :19
+    tau = np.zeros(max(n - 1, 1), dtype=A.dtype)
+    rc = _fn("hessenberg", A.dtype)(_ptr(A), _I64(n), _I64(lda), _ptr(tau))
+    _check(rc, "hessenberg")
+    return A, tau[:max(n - 1, 0)]
+
+
+class SymmetricTridiagonalFactorization:
+    """Mirror of the reference's SymmetricTridiagonalFactorization (src/eigenSelfAdjoint.jl): `reflectors` =
+    (uplo, factors, tau) as in EigenQ, `diagonals` = (dv, ev)."""
+
+    def __init__(self, uplo, factors, tau, dv, ev):
+        self.uplo, self.factors, self.tau, self.dv, self.ev = uplo, factors, tau, dv, ev
+
+    @property
+    def diagonals(self):
+        T = np.diag(self.dv)
+        if self.dv.size > 1:
+            T = T + np.diag(self.ev, 1) + np.diag(self.ev, -1)
+        return T
+
+
+def symtri_(A, uplo="L") -> SymmetricTridiagonalFactorization:
+    """symtri!(Hermitian(A, uplo)) (src/eigenSelfAdjoint.jl:446-564) on the GPU; only the `uplo` triangle is touched."""
+    lda = _colmajor(A, "symtri!")
+    n = A.shape[0]
+    if A.shape[1] != n:
+        raise DimensionMismatch(f"matrix is not square: dimensions are {A.shape}")
+    u = uplo[-1]
+    if u not in ("L", "U"):
+        raise ArgumentError("uplo must be :L or :U")
+    tau = np.zeros(max(n - 1, 1), dtype=A.dtype)
+    rc = _fn("symtri", A.dtype)(_ptr(A), _I64(n), _I64(lda), C.c_int(ord(u)), _ptr(tau))
+    _check(rc, "symtri")
+    dv = np.real(np.diagonal(A)).copy()
+    ev = np.real(np.diagonal(A, 1 if u == "U" else -1)).copy()
+    return SymmetricTridiagonalFactorization(u, A, tau[:max(n - 1, 0)], dv, ev)
+
+
+def bidiagonalize_dev(dA: int, m: int, n: int, lda: int, dtaul: int, dtaur: int, stream: int = 0, dtype=np.float64) -> None:
+    rc = _fn("bidiagonalize_dev", dtype)(C.c_void_p(dA), _I64(m), _I64(n), _I64(lda), C.c_void_p(dtaul), C.c_void_p(dtaur),
+                                         C.c_void_p(stream))
+    _check(rc, "bidiagonalize_dev")
+
+
+def hessenberg_dev(dA: int, n: int, lda: int, dtau: int, stream: int = 0, dtype=np.float64) -> None:
+    rc = _fn("hessenberg_dev", dtype)(C.c_void_p(dA), _I64(n), _I64(lda), C.c_void_p(dtau), C.c_void_p(stream))
+    _check(rc, "hessenberg_dev")
+
+
+def symtri_dev(dA: int, n: int, lda: int, uplo: str, dtau: int, stream: int = 0, dtype=np.float64) -> None:
+    rc = _fn("symtri_dev", dtype)(C.c_void_p(dA), _I64(n), _I64(lda), C.c_int(ord(uplo[-1])), C.c_void_p(dtau),
+                                  C.c_void_p(stream))
+    _check(rc, "symtri_dev")

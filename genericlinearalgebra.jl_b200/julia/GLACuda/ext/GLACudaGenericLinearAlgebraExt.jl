@@ -87,4 +87,34 @@ for T in (Float32, Float64)
     end
 end
 
+# ---- two-sided reductions (SURVEY 8 f3): the step after QR in svd / eigen of the reference
+for T in (Float32, Float64, ComplexF64)
+    @eval begin
+        # bidiagonalize!(A)                                   replaces src/svd.jl:328-381
+        function GenericLinearAlgebra.bidiagonalize!(A::Matrix{$T})
+            m, n = size(A)
+            _, taul, taur = GLACuda.bidiagonalize_inplace!(A)
+            bd = m >= n ? Bidiagonal(real(diag(A)), real(diag(A, 1)), :U) : Bidiagonal(real(diag(A)), real(diag(A, -1)), :L)
+            return GenericLinearAlgebra.BidiagonalFactorization{eltype(bd),typeof(bd.dv),typeof(A),typeof(taul)}(
+                bd, A, taul, taur)
+        end
+        # _hessenberg!(A)                                     replaces src/eigenGeneral.jl:18-31
+        function GenericLinearAlgebra._hessenberg!(A::Matrix{$T})
+            _, tau = GLACuda.hessenberg_inplace!(A)
+            return Hessenberg(A, tau)
+        end
+        # symtriLower!(AS, tau, u) / symtriUpper!(AS, tau, u) replace src/eigenSelfAdjoint.jl:450-564 (`u` is scratch: ignored)
+        function GenericLinearAlgebra.symtriLower!(AS::Matrix{$T}, tau::Vector{$T} = zeros($T, size(AS, 1) - 1), u = nothing)
+            GLACuda.symtri_inplace!(AS, 'L', tau)
+            return GenericLinearAlgebra.SymmetricTridiagonalFactorization(
+                GenericLinearAlgebra.EigenQ('L', AS, tau), SymTridiagonal(real(diag(AS)), real(diag(AS, -1))))
+        end
+        function GenericLinearAlgebra.symtriUpper!(AS::Matrix{$T}, tau::Vector{$T} = zeros($T, size(AS, 1) - 1), u = nothing)
+            GLACuda.symtri_inplace!(AS, 'U', tau)
+            return GenericLinearAlgebra.SymmetricTridiagonalFactorization(
+                GenericLinearAlgebra.EigenQ('U', AS, tau), SymTridiagonal(real(diag(AS)), real(diag(AS, 1))))
+        end
+    end
+end
+
 end # module

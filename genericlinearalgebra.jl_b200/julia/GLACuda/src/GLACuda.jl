@@ -152,6 +152,39 @@ for T in (Float32, Float64, ComplexF64)
     end
 end
 
+# gla_?bidiagonalize / gla_?hessenberg / gla_?symtri: the two-sided reductions, in place
+#   (bidiagonalize!, src/svd.jl:328-381; _hessenberg!, src/eigenGeneral.jl:18-31; symtriLower!/symtriUpper!,
+#    src/eigenSelfAdjoint.jl:450-564)
+for (T, p) in ((Float32, "s"), (Float64, "d"), (ComplexF64, "z"))
+    @eval begin
+        function bidiagonalize_inplace!(A::Matrix{$T})
+            m, n = size(A)
+            nl, nr = m >= n ? (n, max(n - 1, 0)) : (max(m - 1, 0), m)
+            taul, taur = zeros($T, nl), zeros($T, nr)
+            rc = GC.@preserve A taul taur ccall(($(QuoteNode(Symbol("gla_", p, "bidiagonalize"))), libgla), Cint,
+                (Ptr{$T}, Int64, Int64, Int64, Ptr{$T}, Ptr{$T}), A, m, n, max(1, stride(A, 2)), taul, taur)
+            chk(rc, "bidiagonalize_inplace!")
+            return A, taul, taur
+        end
+        function hessenberg_inplace!(A::Matrix{$T})
+            n = LinearAlgebra.checksquare(A)
+            tau = zeros($T, max(n - 1, 0))
+            rc = GC.@preserve A tau ccall(($(QuoteNode(Symbol("gla_", p, "hessenberg"))), libgla), Cint,
+                (Ptr{$T}, Int64, Int64, Ptr{$T}), A, n, max(1, stride(A, 2)), tau)
+            chk(rc, "hessenberg_inplace!")
+            return A, tau
+        end
+        function symtri_inplace!(A::Matrix{$T}, uplo::Char, tau::Vector{$T} = zeros($T, max(size(A, 1) - 1, 0)))
+            n = LinearAlgebra.checksquare(A)
+            length(tau) >= n - 1 || throw(DimensionMismatch("tau is too short"))
+            rc = GC.@preserve A tau ccall(($(QuoteNode(Symbol("gla_", p, "symtri"))), libgla), Cint,
+                (Ptr{$T}, Int64, Int64, Cint, Ptr{$T}), A, n, max(1, stride(A, 2)), Cint(uplo), tau)
+            chk(rc, "symtri_inplace!")
+            return A, tau
+        end
+    end
+end
+
 # gla_{s,d}ldlt: LDL^H without pivoting, in place                      (ldlt!, src/ldlt.jl:155-162; real types only)
 const GLA_ERR_SINGULAR = Cint(901)
 for (T, sym) in ((Float32, :gla_sldlt), (Float64, :gla_dldlt))

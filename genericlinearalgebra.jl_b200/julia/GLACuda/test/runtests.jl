@@ -49,3 +49,22 @@ end
     C = Matrix(Hermitian(randn(5, 5) + 5I)); B = randn(5, 2)
     @test tril(rankUpdate!(Hermitian(copy(C), :L), B, 0.5).data) ≈ tril(C + 0.5 * B * B')
 end
+
+@testset "two-sided reductions (test/svd.jl:100-112, test/eigengeneral.jl:239-249, test/eigenselfadjoint.jl:61-68)" begin
+    A = randn(8, 8)
+    @test svdvals(Matrix(GenericLinearAlgebra.bidiagonalize!(copy(A)).bidiagonal)) ≈ svdvals(A)
+    BF = GenericLinearAlgebra.bidiagonalize!(copy(A))
+    @test (BF.rightQ' * Matrix(I, size(A)...)) * BF.rightQ ≈ I
+    n = 10
+    A = randn(n, n)
+    LHF = GenericLinearAlgebra._hessenberg!(copy(A))
+    @test tril(LHF.Q' * A * LHF.Q, -2) ≈ zeros(n, n) atol = 1e-14
+    for uplo in (:L, :U)
+        S = Hermitian(A + A', uplo)
+        Tf = GenericLinearAlgebra.symtri!(copy(S))
+        Q = Array(Tf.reflectors)
+        @test Q'Q ≈ I
+        @test Q' * S * Q ≈ Tf.diagonals
+    end
+    @test GenericLinearAlgebra.bidiagonalize!(big.(A)) isa GenericLinearAlgebra.BidiagonalFactorization   # BigFloat: reference path
+end

@@ -185,6 +185,38 @@ GLA_API int gla_dldlt(double* A, int64_t n, int64_t lda, int uplo, int64_t block
 GLA_API int gla_sldlt_dev(float* dA, int64_t n, int64_t lda, int uplo, int* dinfo, void* stream);
 GLA_API int gla_dldlt_dev(double* dA, int64_t n, int64_t lda, int uplo, int* dinfo, void* stream);
 
+/* ---- two-sided Householder reductions (the step after QR in the reference's SVD / eigen pipelines) ----------
+ * gla_?bidiagonalize   replaces bidiagonalize!(A)                      src/svd.jl:328-381
+ *     in place: m >= n -> upper bidiagonal (d = real(diag(A)), e = real(diag(A, 1))), left reflectors below the
+ *     diagonal (taul: n entries), right reflectors right of the superdiagonal (taur: n-1 entries, row i holds
+ *     reflector!(conj(row))); m < n -> lower bidiagonal, taur: m entries, taul: m-1 entries.
+ * gla_?hessenberg      replaces _hessenberg!(A) / hessenberg!(A)       src/eigenGeneral.jl:18-31
+ *     in place: upper Hessenberg part + reflectors below the first subdiagonal, tau: n-1 entries.
+ * gla_?symtri          replaces symtri!(Hermitian(A, uplo)) = symtriLower! / symtriUpper!
+ *                                                                      src/eigenSelfAdjoint.jl:446-564
+ *     in place: only the `uplo` ('L' / 'U') triangle is read and written; diagonal and first off-diagonal hold
+ *     the real tridiagonal, reflectors beyond; tau: n-1 entries (real element types stop one step earlier: tau[n-2] = 0).
+ * Return values: 0, -k (k-th argument illegal), >= 1000 CUDA error.  Each reduction is ONE persistent kernel launched
+ * cooperatively (all SMs of the device); the `_dev` twins are asynchronous on `stream`. */
+GLA_API int gla_sbidiagonalize(float* A, int64_t m, int64_t n, int64_t lda, float* taul, float* taur);
+GLA_API int gla_sbidiagonalize_dev(float* dA, int64_t m, int64_t n, int64_t lda, float* dtaul, float* dtaur, void* stream);
+GLA_API int gla_shessenberg(float* A, int64_t n, int64_t lda, float* tau);
+GLA_API int gla_shessenberg_dev(float* dA, int64_t n, int64_t lda, float* dtau, void* stream);
+GLA_API int gla_ssymtri(float* A, int64_t n, int64_t lda, int uplo, float* tau);
+GLA_API int gla_ssymtri_dev(float* dA, int64_t n, int64_t lda, int uplo, float* dtau, void* stream);
+GLA_API int gla_dbidiagonalize(double* A, int64_t m, int64_t n, int64_t lda, double* taul, double* taur);
+GLA_API int gla_dbidiagonalize_dev(double* dA, int64_t m, int64_t n, int64_t lda, double* dtaul, double* dtaur, void* stream);
+GLA_API int gla_dhessenberg(double* A, int64_t n, int64_t lda, double* tau);
+GLA_API int gla_dhessenberg_dev(double* dA, int64_t n, int64_t lda, double* dtau, void* stream);
+GLA_API int gla_dsymtri(double* A, int64_t n, int64_t lda, int uplo, double* tau);
+GLA_API int gla_dsymtri_dev(double* dA, int64_t n, int64_t lda, int uplo, double* dtau, void* stream);
+GLA_API int gla_zbidiagonalize(void* A, int64_t m, int64_t n, int64_t lda, void* taul, void* taur);
+GLA_API int gla_zbidiagonalize_dev(void* dA, int64_t m, int64_t n, int64_t lda, void* dtaul, void* dtaur, void* stream);
+GLA_API int gla_zhessenberg(void* A, int64_t n, int64_t lda, void* tau);
+GLA_API int gla_zhessenberg_dev(void* dA, int64_t n, int64_t lda, void* dtau, void* stream);
+GLA_API int gla_zsymtri(void* A, int64_t n, int64_t lda, int uplo, void* tau);
+GLA_API int gla_zsymtri_dev(void* dA, int64_t n, int64_t lda, int uplo, void* dtau, void* stream);
+
 /* ---- workspace query ------------------------------------------------------------------
  * the reference's FFI precedent asks LAPACK for its workspace before the call (src/lapack.jl:152-170,
  * :514-553); here the library owns its temporaries (stream-ordered pool), and this reports how many

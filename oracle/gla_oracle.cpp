@@ -32,8 +32,8 @@ namespace {
 using i64 = int64_t;
 using zd = std::complex<double>;
 
-template <class T> struct Num { using real = T; };
-template <> struct Num<zd> { using real = double; };
+template <class T> struct Num { using real = T; static constexpr bool is_complex = false; };
+template <> struct Num<zd> { using real = double; static constexpr bool is_complex = true; };
 
 inline float cj(float x) { return x; }
 inline double cj(double x) { return x; }
@@ -460,6 +460,184 @@ void ldlt_upper_blocked(T* A, i64 n, i64 lda, i64 bs) {
 
 }  // namespace
 
+// =================================================================================
+// Two-sided Householder reductions.  The apply loops carry an OpenMP `for` over independent columns /
+// rows (bitwise the serial result) so that the CPU baseline timed beside the GPU uses the host's cores.
+// =================================================================================
+template <class T>
+void apply_left_mt(const T* x, T tau, T* A, i64 m, i64 n, i64 lda) {   // stdlib reflectorApply!(x, tau, A)
+#pragma omp parallel for schedule(static) if (m * n > 16384)
+  for (i64 j = 0; j < n; ++j) {
+    T* a = A + j * lda;
+    T s = a[0];
+    for (i64 i = 1; i < m; ++i) s += cj(x[i]) * a[i];
+    s = cj(tau) * s;
+    a[0] -= s;
+    for (i64 i = 1; i < m; ++i) a[i] -= x[i] * s;
+  }
+}
+template <class T>
+void apply_right_mt(T* A, i64 m, i64 n, i64 lda, const T* x, T tau) {  // reflectorApply!(A, x, tau), src/qr.jl:19-42
+#pragma omp parallel for schedule(static) if (m * n > 16384)
+  for (i64 i = 0; i < m; ++i) {
+    T s = A[i];
+    for (i64 j = 1; j < n; ++j) s += A[i + j * lda] * x[j];
+    s = s * tau;
+    A[i] -= s;
+    for (i64 j = 1; j < n; ++j) A[i + j * lda] -= s * cj(x[j]);
+  }
+}
+
+// reflector! on a strided view (a row of a column-major matrix), optionally conj!(x) first (src/svd.jl:341-343)
+template <class T>
+T reflector_strided(T* x, i64 n, i64 inc, bool conj_first, std::vector<T>& tmp) {
+  tmp.resize((size_t)n);
+  for (i64 i = 0; i < n; ++i) tmp[i] = conj_first ? cj(x[i * inc]) : x[i * inc];
+  T tau = reflector(tmp.data(), n);
+  for (i64 i = 0; i < n; ++i) x[i * inc] = tmp[i];
+  return tau;
+}
+
+// ---------------------------------------------------------------------------------
+// bidiagonalize!(A)                                  src/svd.jl:328-381
+// m >= n: upper bidiagonal, taul has n entries, taur n-1;  m < n: lower bidiagonal, taur has m entries, taul m-1
+// ---------------------------------------------------------------------------------
+template <class T>
+void bidiagonalize(T* A, i64 m, i64 n, i64 lda, T* taul, T* taur) {
+  std::vector<T> row;
+  if (m >= n) {
+    for (i64 i = 0; i < n; ++i) {                                         // :334-346
+      T* x = A + i + i * lda;
+      T t = reflector(x, m - i);
+      taul[i] = t;
+      apply_left_mt(x, t, x + lda, m - i, n - i - 1, lda);
+      if (i < n - 1) {
+        T* r = A + i + (i + 1) * lda;
+        T tr = reflector_strided(r, n - i - 1, lda, true, row);
+        taur[i] = tr;
+        apply_right_mt(A + (i + 1) + (i + 1) * lda, m - i - 1, n - i - 1, lda, row.data(), tr);
+      }
+    }
+  } else {
+    for (i64 i = 0; i < m; ++i) {                                         // :358-371
+      T* r = A + i + i * lda;
+      T tr = reflector_strided(r, n - i, lda, true, row);
+      taur[i] = tr;
+      apply_right_mt(A + (i + 1) + i * lda, m - i - 1, n - i, lda, row.data(), tr);
+      if (i < m - 1) {
+        T* x = A + (i + 1) + i * lda;
+        T t = reflector(x, m - i - 1);
+        taul[i] = t;
+        apply_left_mt(x, t, x + lda, m - i - 1, n - i - 1, lda);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// _hessenberg!(A)                                    src/eigenGeneral.jl:18-31
+//   lmul!(H', A[i+1:n, i+1:n])  (src/householder.jl:61-79),  rmul!(A[:, i+1:n], H)  (src/householder.jl:43-59)
+// ---------------------------------------------------------------------------------
+template <class T>
+void hessenberg(T* A, i64 n, i64 lda, T* tau) {
+  std::vector<T> xw((size_t)(n > 0 ? n : 1));
+  for (i64 i = 0; i + 1 < n; ++i) {
+    T* xi = A + (i + 1) + i * lda;
+    const i64 len = n - i - 1;
+    T t = reflector(xi, len);
+    tau[i] = t;
+    apply_left_mt(xi, t, A + (i + 1) + (i + 1) * lda, len, len, lda);     // va = tau'(A[1,j] + v.Aj); column -= va [1; v]
+    // rmul!: x = A1 v + a1;  a1 -= tau x;  A1 += x (-tau) v_j'
+    T* a1 = A + (i + 1) * lda;
+    T* A1 = a1 + lda;
+#pragma omp parallel for schedule(static) if (n * len > 16384)
+    for (i64 r = 0; r < n; ++r) {
+      T s = T(0);
+      for (i64 j = 0; j + 1 < len; ++j) s += A1[r + j * lda] * xi[j + 1];
+      s += a1[r];
+      xw[r] = s;
+      a1[r] -= t * s;
+      for (i64 j = 0; j + 1 < len; ++j) A1[r + j * lda] += s * (-t) * cj(xi[j + 1]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// symtriLower!(AS, tau, u) / symtriUpper!             src/eigenSelfAdjoint.jl:450-503 / :505-564
+// ---------------------------------------------------------------------------------
+template <class T>
+void symtri_lower(T* A, i64 n, i64 lda, T* tau) {
+  using R = typename Num<T>::real;
+  for (i64 i = 0; i < n; ++i) A[i + i * lda] = T(re(A[i + i * lda]));     // :458-460
+  const i64 steps = n - 2 + (Num<T>::is_complex ? 1 : 0);
+  std::vector<T> u((size_t)(n > 0 ? n : 1));
+  for (i64 k = 0; k < steps; ++k) {
+    T* x = A + (k + 1) + k * lda;
+    const i64 L = n - k - 1;
+    T t = reflector(x, L);
+    tau[k] = t;
+    const T tmp = x[0];
+    x[0] = T(1);
+    T* At = A + (k + 1) + (k + 1) * lda;
+    // u = tau * Hermitian(At, :L) * x
+#pragma omp parallel for schedule(static) if (L * L > 16384)
+    for (i64 i = 0; i < L; ++i) {
+      T s = T(0);
+      for (i64 j = 0; j < i; ++j) s += At[i + j * lda] * x[j];
+      s += T(re(At[i + i * lda])) * x[i];
+      for (i64 j = i + 1; j < L; ++j) s += cj(At[j + i * lda]) * x[j];
+      u[i] = t * s;
+    }
+    T dot = T(0);
+    for (i64 i = 0; i < L; ++i) dot += cj(x[i]) * u[i];
+    const R xi = re(cj(t) * dot);                                          // :479
+#pragma omp parallel for schedule(static) if (L * L > 16384)
+    for (i64 j = 0; j < L; ++j) {                                          // :483-490
+      const T xj = x[j], uj = u[j];
+      const T xixj = T(xi) * xj;
+      for (i64 i = j; i < L; ++i) At[i + j * lda] += x[i] * cj(xixj) - x[i] * cj(uj) - u[i] * cj(xj);
+    }
+    x[0] = tmp;
+  }
+}
+
+template <class T>
+void symtri_upper(T* A, i64 n, i64 lda, T* tau) {
+  using R = typename Num<T>::real;
+  for (i64 i = 0; i < n; ++i) A[i + i * lda] = T(re(A[i + i * lda]));
+  const i64 steps = n - 2 + (Num<T>::is_complex ? 1 : 0);
+  std::vector<T> u((size_t)(n > 0 ? n : 1)), rev((size_t)(n > 0 ? n : 1));
+  for (i64 k = 0; k < steps; ++k) {
+    const i64 L = n - k - 1;              // x = A[0:L, L]
+    T* x = A + L * lda;
+    for (i64 i = 0; i < L; ++i) rev[i] = x[L - 1 - i];                    // the reversed view :524-526
+    T t = reflector(rev.data(), L);
+    for (i64 i = 0; i < L; ++i) x[L - 1 - i] = rev[i];
+    tau[k] = t;
+    const T tmp = x[L - 1];
+    x[L - 1] = T(1);
+    // u = tau * Hermitian(A[0:L, 0:L], :U) * x
+#pragma omp parallel for schedule(static) if (L * L > 16384)
+    for (i64 i = 0; i < L; ++i) {
+      T s = T(0);
+      for (i64 j = 0; j < i; ++j) s += cj(A[j + i * lda]) * x[j];
+      s += T(re(A[i + i * lda])) * x[i];
+      for (i64 j = i + 1; j < L; ++j) s += A[i + j * lda] * x[j];
+      u[i] = t * s;
+    }
+    T dot = T(0);
+    for (i64 i = 0; i < L; ++i) dot += cj(x[i]) * u[i];
+    const R xi = re(cj(t) * dot);
+#pragma omp parallel for schedule(static) if (L * L > 16384)
+    for (i64 j = 0; j < L; ++j) {                                          // :545-552
+      const T xj = x[j], uj = u[j];
+      const T xixj = T(xi) * xj;
+      for (i64 i = 0; i <= j; ++i) A[i + j * lda] += x[i] * cj(xixj) - x[i] * cj(uj) - u[i] * cj(xj);
+    }
+    x[L - 1] = tmp;
+  }
+}
+
 #define ORACLE_API extern "C" __attribute__((visibility("default")))
 
 #define DEFINE_TYPE(P, T, R)                                                                       \
@@ -510,6 +688,14 @@ void ldlt_upper_blocked(T* A, i64 n, i64 lda, i64 bs) {
   ORACLE_API int oracle_##P##chol_recursive(T* A, i64 n, i64 lda, i64 cutoff, int mt) {            \
     return chol_recursive<T>(A, n, lda, cutoff, 0, mt);                                            \
   }                                                                                                \
+  ORACLE_API void oracle_##P##bidiagonalize(T* A, i64 m, i64 n, i64 lda, T* taul, T* taur) {      \
+    bidiagonalize<T>(A, m, n, lda, taul, taur);                                                    \
+  }                                                                                                \
+  ORACLE_API void oracle_##P##hessenberg(T* A, i64 n, i64 lda, T* tau) { hessenberg<T>(A, n, lda, tau); } \
+  ORACLE_API void oracle_##P##symtri(T* A, i64 n, i64 lda, T* tau, int upper) {                    \
+    if (upper) symtri_upper<T>(A, n, lda, tau);                                                    \
+    else symtri_lower<T>(A, n, lda, tau);                                                          \
+  }                                                                                                \
   ORACLE_API void oracle_##P##ldlt(T* A, i64 n, i64 lda, i64 bs, int upper) {                      \
     if (upper) ldlt_upper_blocked<T>(A, n, lda, bs);                                               \
     else ldlt_lower_blocked<T>(A, n, lda, bs);                                                     \
@@ -519,7 +705,7 @@ DEFINE_TYPE(s, float, float)
 DEFINE_TYPE(d, double, double)
 DEFINE_TYPE(z, zd, double)
 
-ORACLE_API int oracle_version() { return 2; }
+ORACLE_API int oracle_version() { return 3; }
 // OpenMP team size actually in effect (bench.py reports it; torchrun exports OMP_NUM_THREADS=1, which bench.py overrides)
 ORACLE_API int oracle_max_threads() { return omp_get_max_threads(); }
 ORACLE_API void oracle_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }

@@ -226,3 +226,42 @@ def ldlt(A, uplo="L", blocksize=None):
     bs = max(1, 128 // A.dtype.itemsize) if blocksize is None else int(blocksize)
     _fn("ldlt", A)(_p(A), _I64(n), _I64(n), _I64(bs), C.c_int(1 if uplo in ("U", ":U") else 0))
     return A
+
+
+def bidiagonalize(A):
+    """bidiagonalize!(A) (src/svd.jl:328-381).  Returns (factors, taul, taur, dv, ev, uplo): the reflectors in place,
+    the bidiagonal as real(diag(A)) and real(diag(A, +-1)), uplo 'U' for m >= n and 'L' for m < n."""
+    A = _f(A)
+    m, n = A.shape
+    k = min(m, n)
+    nl, nr = (n, max(n - 1, 0)) if m >= n else (max(m - 1, 0), m)
+    taul = np.zeros(max(nl, 1), dtype=A.dtype)
+    taur = np.zeros(max(nr, 1), dtype=A.dtype)
+    _fn("bidiagonalize", A)(_p(A), _I64(m), _I64(n), _I64(max(m, 1)), _p(taul), _p(taur))
+    off = 1 if m >= n else -1
+    ev = np.real(np.diagonal(A, off)).copy()[:(nr if m >= n else nl)]
+    return A, taul[:nl], taur[:nr], np.real(np.diagonal(A)[:k]).copy(), ev, ("U" if m >= n else "L")
+
+
+def hessenberg(A):
+    """_hessenberg!(A) (src/eigenGeneral.jl:18-31): reflectors below the first subdiagonal, tau of length n-1."""
+    A = _f(A)
+    n = A.shape[0]
+    if A.shape[1] != n:
+        raise ValueError("DimensionMismatch: matrix is not square")
+    tau = np.zeros(max(n - 1, 1), dtype=A.dtype)
+    _fn("hessenberg", A)(_p(A), _I64(n), _I64(max(n, 1)), _p(tau))
+    return A, tau[:max(n - 1, 0)]
+
+
+def symtri(A, uplo="L"):
+    """symtri!(Hermitian(A, uplo)) (src/eigenSelfAdjoint.jl:446-564): returns (factors, tau, dv, ev); tau has n-1
+    entries (the last one stays 0 for real element types, which stop one step earlier)."""
+    A = _f(A)
+    n = A.shape[0]
+    if A.shape[1] != n:
+        raise ValueError("DimensionMismatch: matrix is not square")
+    up = uplo in ("U", ":U")
+    tau = np.zeros(max(n - 1, 1), dtype=A.dtype)
+    _fn("symtri", A)(_p(A), _I64(n), _I64(max(n, 1)), _p(tau), C.c_int(1 if up else 0))
+    return A, tau[:max(n - 1, 0)], np.real(np.diagonal(A)).copy(), np.real(np.diagonal(A, 1 if up else -1)).copy()
