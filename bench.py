@@ -209,6 +209,16 @@ def cpu_other_configs():
     t = best(lambda: oracle.qr_blocked(A, 12), 1)
     out["qr_f64_n16384"] = {"ms": t * 512 * 1e3, "tflops": 4.0 / 3.0 * n ** 3 / t / 1e12, "cores": team, "kind": "port",
                             "sample": "oracle qr_blocked at n=2048; ms EXTRAPOLATED x512 ((4/3)n^3)"}
+    # f3 rows: the two-sided reductions at n = 2048 (full config)
+    t_b = best(lambda: oracle.bidiagonalize(A.copy(order="F")), 1)
+    t_h = best(lambda: oracle.hessenberg(A.copy(order="F")), 1)
+    S2 = np.asfortranarray(A + A.T)
+    t_s = best(lambda: oracle.symtri(S2.copy(order="F"), "L"), 1)
+    out["twosided_f64_n2048"] = {"bidiagonalize_ms": t_b * 1e3, "hessenberg_ms": t_h * 1e3, "symtri_ms": t_s * 1e3,
+                                 "cores": team, "kind": "port",
+                                 "sample": "full config: oracle bidiagonalize / hessenberg / symtri(:L) at n=2048 (OpenMP over the "
+                                           "independent columns / rows of each reflector application)"}
+    del S2
     Z = np.asfortranarray(A + 1j * rng.standard_normal((n, n)))
     t = best(lambda: oracle.qr_blocked(Z, 12), 1)
     out["qr_c128_n16384"] = {"ms": t * 512 * 1e3, "tflops_real": 4.0 * 4.0 / 3.0 * n ** 3 / t / 1e12, "cores": team,
@@ -608,6 +618,40 @@ def other_configs(g, torch, dist, dev, rank, world, stream, cpu=False):
         out["chol_f64_n4096"] = {"ms": best, "tflops": tf, "info": int(info.item()), "residual": resid, "roofline": roof(tf),
                                  "e2e_ms": e2e}
         del X, S, dS, L, hS
+        torch.cuda.empty_cache()
+        # f3 rows: two-sided reductions n = 2048 (BLAS-2: every step streams the trailing matrix; L2 resident at this size)
+        n = 2048
+        src = torch.randn((n, n), device=dev, dtype=torch.float64)
+        sym = src + src.t()
+        dW = torch.empty_like(src)
+        t1 = torch.zeros(n, device=dev, dtype=torch.float64)
+        t2 = torch.zeros(n, device=dev, dtype=torch.float64)
+        ts = {}
+        for name, base, call, passes in (
+                ("bidiagonalize", src, lambda: g.bidiagonalize_dev(dW.data_ptr(), n, n, n, t1.data_ptr(), t2.data_ptr(), stream), 6.0),
+                ("hessenberg", src, lambda: g.hessenberg_dev(dW.data_ptr(), n, n, t1.data_ptr(), stream), 7.5),
+                ("symtri", sym, lambda: g.symtri_dev(dW.data_ptr(), n, n, "L", t1.data_ptr(), stream), 2.0)):
+            best = 1e30
+            for _ in range(3):
+                dW.copy_(base)
+                ms, _ = _time(torch, call, reps=1)
+                best = min(best, ms)
+            # algorithmic traffic: passes x 8 B x sum over the steps of the trailing size (n^3/3 elements; hessenberg's right
+            # application runs over all n rows: n^3/2), see DESIGN.md
+            ts[name + "_ms"] = best
+            ts[name + "_stream_gbps"] = passes * 8.0 * n ** 3 / 3.0 / (best * 1e-3) / 1e9
+        out["twosided_f64_n2048"] = dict(ts, note="GB/s = algorithmic trailing-matrix traffic of the unblocked reductions / time "
+                                         "(reads for the dots + read-modify-write of the updates); the matrix (32 MiB) is L2 resident")
+        if oracle is not None:
+            dW.copy_(src)
+            g.bidiagonalize_dev(dW.data_ptr(), n, n, n, t1.data_ptr(), t2.data_ptr(), stream)
+            torch.cuda.synchronize()
+            F, tl, tr, dv, ev, _ = oracle.bidiagonalize(np.asfortranarray(src.cpu().numpy().T))
+            got = dW.cpu().numpy().T
+            out["twosided_f64_n2048"]["oracle_bidiagonal_max_abs_err"] = float(max(np.max(np.abs(np.diagonal(got) - dv)),
+                                                                                   np.max(np.abs(np.diagonal(got, 1) - ev))))
+            out["twosided_f64_n2048"]["oracle_factors_max_abs_err"] = float(np.max(np.abs(got - F)))
+        del src, sym, dW
         torch.cuda.empty_cache()
     # config 4: TSQR 8,388,608 x 64, row-sharded; the 64x64 R factors are exchanged by ONE ncclAllGather issued
     # inside the library (gla_dtsqr_allreduce_dev on a library-owned communicator) and reduced on every rank

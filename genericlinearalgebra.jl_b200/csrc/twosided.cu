@@ -162,42 +162,105 @@ __device__ void cta_writeback(T* x, i64 len, i64 inc, const T* v, const Refl<T>&
   }
 }
 
+// ------------------------------------------------------------------ memory-level parallelism
+// Every phase is a latency chain on L2 (~0.7 us per dependent round trip, 16 warps per SM): each lane keeps TS_U
+// independent loads in flight, and a column is shared by `wpc` warps as soon as there are fewer columns than warps.
+template <class T>
+struct TsU {
+  static constexpr int value = sizeof(T) == 16 ? 4 : 8;
+};
+
+// warps per column (power of two <= TS_WARPS): all warps of the grid stay busy, >= 64 rows per warp
+__device__ __forceinline__ int warps_per_column(i64 rows, i64 cols) {
+  const i64 nwarps = (i64)gridDim.x * TS_WARPS;
+  int wpc = 1;
+  while (wpc < TS_WARPS && cols * wpc * 2 <= nwarps && rows >= 128 * (i64)wpc) wpc <<= 1;
+  return wpc;
+}
+
+// sum over the `wpc` warps that share a column (fixed order); every thread of the CTA must call
+template <class T>
+__device__ __forceinline__ T group_sum(T s, int wpc, int cslot, T* red) {
+  s = warp_sum(s);
+  if (wpc == 1) return s;
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  T t = red[cslot * wpc];
+  for (int w = 1; w < wpc; ++w) t = t + red[cslot * wpc + w];
+  __syncthreads();
+  return t;
+}
+
 // ------------------------------------------------------------------ A <- (I - conj(tau) v v^H) A   (stdlib reflectorApply!)
 template <class T>
 __device__ void left_apply(T* A, i64 lda, i64 rows, i64 cols, const T* v, T tau, T* red) {
+  constexpr int U = TsU<T>::value;
   const T ctau = cj(tau);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const i64 nwarps = (i64)gridDim.x * TS_WARPS;
-  if (cols * 8 >= nwarps || rows < 4096) {   // a warp per column
-    for (i64 j = (i64)blockIdx.x * TS_WARPS + warp; j < cols; j += nwarps) {
-      T* a = A + j * lda;
-      T s0 = Sc<T>::zero(), s1 = Sc<T>::zero(), s2 = Sc<T>::zero(), s3 = Sc<T>::zero();
-      i64 k = lane;
-      for (; k + 96 < rows; k += 128) {
-        const T a0 = a[k], a1 = a[k + 32], a2 = a[k + 64], a3 = a[k + 96];
-        s0 = fmad(cj(v[k]), a0, s0);
-        s1 = fmad(cj(v[k + 32]), a1, s1);
-        s2 = fmad(cj(v[k + 64]), a2, s2);
-        s3 = fmad(cj(v[k + 96]), a3, s3);
+  const int wpc = warps_per_column(rows, cols);
+  const int cpc = TS_WARPS / wpc, cslot = warp / wpc;
+  const int tig = (warp % wpc) * 32 + lane, gs = wpc * 32;
+  const bool single = rows <= (i64)gs * U;
+  for (i64 base = (i64)blockIdx.x * cpc; base < cols; base += (i64)gridDim.x * cpc) {
+    const i64 j = base + cslot;
+    const bool ok = j < cols;
+    T* a = A + (ok ? j : 0) * lda;
+    T s0 = Sc<T>::zero(), s1 = Sc<T>::zero();
+    T xs[U];
+    if (ok && single) {   // one batch covers the column: keep it in registers for the update
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const i64 k = tig + (i64)u * gs;
+        xs[u] = k < rows ? a[k] : Sc<T>::zero();
       }
-      for (; k < rows; k += 32) s0 = fmad(cj(v[k]), a[k], s0);
-      T s = warp_sum((s0 + s1) + (s2 + s3));
-      s = ctau * s;
-      const T ms = -s;
-#pragma unroll 4
-      for (k = lane; k < rows; k += 32) a[k] = fmad(v[k], ms, a[k]);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const i64 k = tig + (i64)u * gs;
+        if (k < rows) {
+          if (u & 1) s1 = fmad(cj(v[k]), xs[u], s1);
+          else s0 = fmad(cj(v[k]), xs[u], s0);
+        }
+      }
+    } else if (ok) {
+      for (i64 k0 = tig; k0 < rows; k0 += (i64)gs * U) {
+        T x[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const i64 k = k0 + (i64)u * gs;
+          x[u] = k < rows ? a[k] : Sc<T>::zero();
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const i64 k = k0 + (i64)u * gs;
+          if (k < rows) {
+            if (u & 1) s1 = fmad(cj(v[k]), x[u], s1);
+            else s0 = fmad(cj(v[k]), x[u], s0);
+          }
+        }
+      }
     }
-  } else {   // tall and few columns: a CTA per column
-    for (i64 j = blockIdx.x; j < cols; j += gridDim.x) {
-      T* a = A + j * lda;
-      T s0 = Sc<T>::zero();
-#pragma unroll 4
-      for (i64 k = threadIdx.x; k < rows; k += TS_THREADS) s0 = fmad(cj(v[k]), a[k], s0);
-      T s = cta_sum<T>(s0, red);
-      s = ctau * s;
-      const T ms = -s;
-#pragma unroll 4
-      for (i64 k = threadIdx.x; k < rows; k += TS_THREADS) a[k] = fmad(v[k], ms, a[k]);
+    T s = group_sum<T>(s0 + s1, wpc, cslot, red);
+    const T ms = -(ctau * s);
+    if (ok && single) {   // the column is still in registers
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const i64 k = tig + (i64)u * gs;
+        if (k < rows) a[k] = fmad(v[k], ms, xs[u]);
+      }
+    } else if (ok) {
+      for (i64 k0 = tig; k0 < rows; k0 += (i64)gs * U) {
+        T x[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const i64 k = k0 + (i64)u * gs;
+          x[u] = k < rows ? a[k] : Sc<T>::zero();
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const i64 k = k0 + (i64)u * gs;
+          if (k < rows) a[k] = fmad(v[k], ms, x[u]);
+        }
+      }
     }
   }
 }
@@ -206,51 +269,110 @@ __device__ void left_apply(T* A, i64 lda, i64 rows, i64 cols, const T* v, T tau,
 template <class T, int RB>
 __device__ void right_apply_rb(T* A, i64 lda, i64 rows, i64 cols, const T* v, T tau, T* ysm) {
   constexpr int NCG = TS_THREADS / RB;
+  constexpr int U = TsU<T>::value;
   const int rx = threadIdx.x % RB, cgp = threadIdx.x / RB;
   const i64 nblk = (rows + RB - 1) / RB;
+  const bool single = cols <= (i64)NCG * U;
   for (i64 b = blockIdx.x; b < nblk; b += gridDim.x) {
     const i64 r = b * RB + rx;
     const bool ok = r < rows;
     T* a = A + (ok ? r : 0);
-    T s0 = Sc<T>::zero(), s1 = Sc<T>::zero(), s2 = Sc<T>::zero(), s3 = Sc<T>::zero();
-    if (ok) {
-      i64 j = cgp;
-      for (; j + 3 * NCG < cols; j += 4 * NCG) {
-        const T a0 = a[j * lda], a1 = a[(j + NCG) * lda], a2 = a[(j + 2 * NCG) * lda], a3 = a[(j + 3 * NCG) * lda];
-        s0 = fmad(a0, v[j], s0);
-        s1 = fmad(a1, v[j + NCG], s1);
-        s2 = fmad(a2, v[j + 2 * NCG], s2);
-        s3 = fmad(a3, v[j + 3 * NCG], s3);
+    T s0 = Sc<T>::zero(), s1 = Sc<T>::zero();
+    T xs[U];
+    if (ok && single) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const i64 j = cgp + (i64)u * NCG;
+        xs[u] = j < cols ? a[j * lda] : Sc<T>::zero();
       }
-      for (; j < cols; j += NCG) s0 = fmad(a[j * lda], v[j], s0);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const i64 j = cgp + (i64)u * NCG;
+        if (j < cols) {
+          if (u & 1) s1 = fmad(xs[u], v[j], s1);
+          else s0 = fmad(xs[u], v[j], s0);
+        }
+      }
+    } else if (ok) {
+      for (i64 j0 = cgp; j0 < cols; j0 += (i64)NCG * U) {
+        T x[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const i64 j = j0 + (i64)u * NCG;
+          x[u] = j < cols ? a[j * lda] : Sc<T>::zero();
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const i64 j = j0 + (i64)u * NCG;
+          if (j < cols) {
+            if (u & 1) s1 = fmad(x[u], v[j], s1);
+            else s0 = fmad(x[u], v[j], s0);
+          }
+        }
+      }
     }
-    ysm[cgp * RB + rx] = (s0 + s1) + (s2 + s3);
+    ysm[cgp * RB + rx] = s0 + s1;
     __syncthreads();
     T y = ysm[rx];
 #pragma unroll 4
     for (int c = 1; c < NCG; ++c) y = y + ysm[c * RB + rx];
     __syncthreads();
     const T my = -(y * tau);
-    if (ok) {
-#pragma unroll 4
-      for (i64 j = cgp; j < cols; j += NCG) a[j * lda] = fmad(my, cj(v[j]), a[j * lda]);
+    if (ok && single) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const i64 j = cgp + (i64)u * NCG;
+        if (j < cols) a[j * lda] = fmad(my, cj(v[j]), xs[u]);
+      }
+    } else if (ok) {
+      for (i64 j0 = cgp; j0 < cols; j0 += (i64)NCG * U) {
+        T x[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const i64 j = j0 + (i64)u * NCG;
+          x[u] = j < cols ? a[j * lda] : Sc<T>::zero();
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const i64 j = j0 + (i64)u * NCG;
+          if (j < cols) a[j * lda] = fmad(my, cj(v[j]), x[u]);
+        }
+      }
     }
   }
 }
+// rows per CTA block: the candidate with the fewest (rounds over the grid) x (columns per thread); ties -> wider rows
+__device__ __forceinline__ int pick_row_block(i64 rows) {
+  const i64 g = gridDim.x;
+  int best = 32;
+  i64 cost = ((rows + 31) / 32 + g - 1) / g * 32;
+#pragma unroll
+  for (int rb = 16; rb >= 4; rb >>= 1) {
+    const i64 c = ((rows + rb - 1) / rb + g - 1) / g * rb;
+    if (c < cost) {
+      cost = c;
+      best = rb;
+    }
+  }
+  return best;
+}
 template <class T>
 __device__ void right_apply(T* A, i64 lda, i64 rows, i64 cols, const T* v, T tau, T* ysm) {
-  const i64 g = gridDim.x;
-  if ((rows + 31) / 32 >= g) right_apply_rb<T, 32>(A, lda, rows, cols, v, tau, ysm);
-  else if ((rows + 15) / 16 >= g) right_apply_rb<T, 16>(A, lda, rows, cols, v, tau, ysm);
-  else right_apply_rb<T, 8>(A, lda, rows, cols, v, tau, ysm);
+  switch (pick_row_block(rows)) {
+    case 32: right_apply_rb<T, 32>(A, lda, rows, cols, v, tau, ysm); break;
+    case 16: right_apply_rb<T, 16>(A, lda, rows, cols, v, tau, ysm); break;
+    case 8: right_apply_rb<T, 8>(A, lda, rows, cols, v, tau, ysm); break;
+    default: right_apply_rb<T, 4>(A, lda, rows, cols, v, tau, ysm); break;
+  }
 }
 
 // ------------------------------------------------------------------ u = Hermitian(At, :L) v in two partial vectors
-// ucol[j] = re(At[j,j]) v_j + sum_{i>j} conj(At[i,j]) v_i   (a warp per column)
+// ucol[j] = re(At[j,j]) v_j + sum_{i>j} conj(At[i,j]) v_i   (`wpc` warps per column)
 // urow[r] = sum_{j<r} At[r,j] v_j                            (a CTA per block of RB rows)
 template <class T, int RB>
 __device__ void symv_lower_rows(const T* At, i64 lda, i64 L, const T* v, T* urow, T* ysm) {
   constexpr int NCG = TS_THREADS / RB;
+  constexpr int U = TsU<T>::value;
   const int rx = threadIdx.x % RB, cgp = threadIdx.x / RB;
   const i64 nblk = (L + RB - 1) / RB;
   // blocks are dealt from the bottom (longest rows first) so that the tail of the phase is made of short ones
@@ -260,17 +382,24 @@ __device__ void symv_lower_rows(const T* At, i64 lda, i64 L, const T* v, T* urow
     const bool ok = r < L;
     const T* a = At + (ok ? r : 0);
     const i64 jend = ok ? r : 0;   // columns j < r
-    T s0 = Sc<T>::zero(), s1 = Sc<T>::zero(), s2 = Sc<T>::zero(), s3 = Sc<T>::zero();
-    i64 j = cgp;
-    for (; j + 3 * NCG < jend; j += 4 * NCG) {
-      const T a0 = a[j * lda], a1 = a[(j + NCG) * lda], a2 = a[(j + 2 * NCG) * lda], a3 = a[(j + 3 * NCG) * lda];
-      s0 = fmad(a0, v[j], s0);
-      s1 = fmad(a1, v[j + NCG], s1);
-      s2 = fmad(a2, v[j + 2 * NCG], s2);
-      s3 = fmad(a3, v[j + 3 * NCG], s3);
+    T s0 = Sc<T>::zero(), s1 = Sc<T>::zero();
+    for (i64 j0 = cgp; j0 < jend; j0 += (i64)NCG * U) {
+      T x[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const i64 j = j0 + (i64)u * NCG;
+        x[u] = j < jend ? a[j * lda] : Sc<T>::zero();
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const i64 j = j0 + (i64)u * NCG;
+        if (j < jend) {
+          if (u & 1) s1 = fmad(x[u], v[j], s1);
+          else s0 = fmad(x[u], v[j], s0);
+        }
+      }
     }
-    for (; j < jend; j += NCG) s0 = fmad(a[j * lda], v[j], s0);
-    ysm[cgp * RB + rx] = (s0 + s1) + (s2 + s3);
+    ysm[cgp * RB + rx] = s0 + s1;
     __syncthreads();
     if (cgp == 0 && ok) {
       T y = ysm[rx];
@@ -281,44 +410,78 @@ __device__ void symv_lower_rows(const T* At, i64 lda, i64 L, const T* v, T* urow
   }
 }
 template <class T>
-__device__ void symv_lower(const T* At, i64 lda, i64 L, const T* v, T* ucol, T* urow, T* ysm) {
+__device__ void symv_lower(const T* At, i64 lda, i64 L, const T* v, T* ucol, T* urow, T* ysm, T* red) {
+  constexpr int U = TsU<T>::value;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const i64 nwarps = (i64)gridDim.x * TS_WARPS;
-  for (i64 j = (i64)blockIdx.x * TS_WARPS + warp; j < L; j += nwarps) {
-    const T* a = At + j * lda;
+  const int wpc = warps_per_column(L, L);
+  const int cpc = TS_WARPS / wpc, cslot = warp / wpc;
+  const int tig = (warp % wpc) * 32 + lane, gs = wpc * 32;
+  for (i64 base = (i64)blockIdx.x * cpc; base < L; base += (i64)gridDim.x * cpc) {
+    const i64 j = base + cslot;
+    const bool ok = j < L;
+    const T* a = At + (ok ? j : 0) * lda;
     T s0 = Sc<T>::zero(), s1 = Sc<T>::zero();
-    i64 k = j + 1 + lane;
-    for (; k + 32 < L; k += 64) {
-      const T a0 = a[k], a1 = a[k + 32];
-      s0 = fmad(cj(a0), v[k], s0);
-      s1 = fmad(cj(a1), v[k + 32], s1);
+    if (ok) {
+      for (i64 k0 = j + 1 + tig; k0 < L; k0 += (i64)gs * U) {
+        T x[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const i64 k = k0 + (i64)u * gs;
+          x[u] = k < L ? a[k] : Sc<T>::zero();
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const i64 k = k0 + (i64)u * gs;
+          if (k < L) {
+            if (u & 1) s1 = fmad(cj(x[u]), v[k], s1);
+            else s0 = fmad(cj(x[u]), v[k], s0);
+          }
+        }
+      }
     }
-    for (; k < L; k += 32) s0 = fmad(cj(a[k]), v[k], s0);
-    T s = warp_sum(s0 + s1);
-    if (lane == 0) ucol[j] = s + scale_real(v[j], re(a[j]));
+    const T s = group_sum<T>(s0 + s1, wpc, cslot, red);
+    if (ok && tig == 0) ucol[j] = s + scale_real(v[j], re(a[j]));
   }
-  const i64 g = gridDim.x;
-  if ((L + 31) / 32 >= g) symv_lower_rows<T, 32>(At, lda, L, v, urow, ysm);
-  else if ((L + 15) / 16 >= g) symv_lower_rows<T, 16>(At, lda, L, v, urow, ysm);
-  else symv_lower_rows<T, 8>(At, lda, L, v, urow, ysm);
+  switch (pick_row_block(L)) {
+    case 32: symv_lower_rows<T, 32>(At, lda, L, v, urow, ysm); break;
+    case 16: symv_lower_rows<T, 16>(At, lda, L, v, urow, ysm); break;
+    case 8: symv_lower_rows<T, 8>(At, lda, L, v, urow, ysm); break;
+    default: symv_lower_rows<T, 4>(At, lda, L, v, urow, ysm); break;
+  }
 }
 
 // At[i,j] += v_i conj(xi v_j) - v_i conj(u_j) - u_i conj(v_j), i >= j     (src/eigenSelfAdjoint.jl:483-490)
 template <class T>
 __device__ void rank2_lower(T* At, i64 lda, i64 L, const T* v, const T* u, typename Sc<T>::real xi) {
+  constexpr int U = TsU<T>::value;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const i64 nwarps = (i64)gridDim.x * TS_WARPS;
-  for (i64 j = (i64)blockIdx.x * TS_WARPS + warp; j < L; j += nwarps) {
+  const int wpc = warps_per_column(L, L);
+  const int cpc = TS_WARPS / wpc, cslot = warp / wpc;
+  const int tig = (warp % wpc) * 32 + lane, gs = wpc * 32;
+  for (i64 base = (i64)blockIdx.x * cpc; base < L; base += (i64)gridDim.x * cpc) {
+    const i64 j = base + cslot;
+    if (j >= L) continue;
     T* a = At + j * lda;
     const T vj = v[j], uj = u[j];
     const T t1 = cj(scale_real(vj, xi)) - cj(uj);   // multiplies v_i
     const T t2 = -cj(vj);                            // multiplies u_i
-#pragma unroll 4
-    for (i64 k = j + lane; k < L; k += 32) {
-      T e = fmad(v[k], t1, a[k]);
-      e = fmad(u[k], t2, e);
-      if (k == j) e = Sc<T>::from_real(re(e));
-      a[k] = e;
+    for (i64 k0 = j + tig; k0 < L; k0 += (i64)gs * U) {
+      T x[U];
+#pragma unroll
+      for (int u_ = 0; u_ < U; ++u_) {
+        const i64 k = k0 + (i64)u_ * gs;
+        x[u_] = k < L ? a[k] : Sc<T>::zero();
+      }
+#pragma unroll
+      for (int u_ = 0; u_ < U; ++u_) {
+        const i64 k = k0 + (i64)u_ * gs;
+        if (k < L) {
+          T e = fmad(v[k], t1, x[u_]);
+          e = fmad(u[k], t2, e);
+          if (k == j) e = Sc<T>::from_real(re(e));
+          a[k] = e;
+        }
+      }
     }
   }
 }
@@ -337,6 +500,7 @@ struct TsArgs {
   T* urow;
   unsigned long long* bar;
   int* err;
+  int debug;     // timing experiments only (GLA_TS_DEBUG): 1 skips the applications, 2 skips the reflectors
 };
 
 struct TsSmemHead {
@@ -381,19 +545,22 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bidiag_tall_kernel(TsArgs<T> a)
       cta_writeback<T>(A + (i - 1) + i * lda, n - i, lda, v, rrow);
       __syncthreads();
     }
-    const Refl<T> rc = cta_reflector<T>(A + i + i * lda, m - i, 1, false, v, red);
+    Refl<T> rc;
+    if (a.debug & 2) { rc.tau = Sc<T>::one(); rc.nu = 1; rc.nonzero = true; }
+    else rc = cta_reflector<T>(A + i + i * lda, m - i, 1, false, v, red);
     if (blockIdx.x == 0 && threadIdx.x == 0) a.tau1[i] = rc.tau;
-    if (rc.nonzero && i + 1 < n) left_apply<T>(A + i + (i + 1) * lda, lda, m - i, n - i - 1, v, rc.tau, red);
+    if (rc.nonzero && i + 1 < n && !(a.debug & 1)) left_apply<T>(A + i + (i + 1) * lda, lda, m - i, n - i - 1, v, rc.tau, red);
     if (!grid_barrier(bar, flag)) return;
     // ---- phase B: store the column reflector, row reflector, right application
     cta_writeback<T>(A + i + i * lda, m - i, 1, v, rc);
     __syncthreads();
     have_row = false;
     if (i + 1 < n) {
-      rrow = cta_reflector<T>(A + i + (i + 1) * lda, n - i - 1, lda, true, v, red);
+      if (a.debug & 2) { rrow.tau = Sc<T>::one(); rrow.nu = 1; rrow.nonzero = true; }
+      else rrow = cta_reflector<T>(A + i + (i + 1) * lda, n - i - 1, lda, true, v, red);
       have_row = true;
       if (blockIdx.x == 0 && threadIdx.x == 0) a.tau2[i] = rrow.tau;
-      if (rrow.nonzero && i + 1 < m)
+      if (rrow.nonzero && i + 1 < m && !(a.debug & 1))
         right_apply<T>(A + (i + 1) + (i + 1) * lda, lda, m - i - 1, n - i - 1, v, rrow.tau, ysm);
       if (!grid_barrier(bar, flag)) return;
     }
@@ -447,7 +614,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) symtri_lower_kernel(TsArgs<T> a
     T* At = A + (k + 1) + (k + 1) * lda;
     const Refl<T> rc = cta_reflector<T>(x, L, 1, false, v, red);
     if (blockIdx.x == 0 && threadIdx.x == 0) a.tau1[k] = rc.tau;
-    if (rc.nonzero) symv_lower<T>(At, lda, L, v, a.ucol, a.urow, ysm);
+    if (rc.nonzero) symv_lower<T>(At, lda, L, v, a.ucol, a.urow, ysm, red);
     if (!grid_barrier(bar, flag)) return;
     cta_writeback<T>(x, L, 1, v, rc);
     if (rc.nonzero) {
@@ -540,6 +707,8 @@ int ts_prepare(TsArgs<T>& a, TsWork<T>& w, int nvec, bool need_u, int* smem_byte
   GLA_CUDA(cudaMemsetAsync(w.small, 0, 16, st));
   a.bar = static_cast<unsigned long long*>(w.small);
   a.err = reinterpret_cast<int*>(static_cast<unsigned char*>(w.small) + 8);
+  const char* dbg = getenv("GLA_TS_DEBUG");
+  a.debug = dbg ? atoi(dbg) : 0;
   a.gvec = nullptr;
   if (!a.vec_in_smem) {
     GLA_TRY(pool_malloc(reinterpret_cast<void**>(&w.gvec), (size_t)*grid * nvec * a.veclen * sizeof(T), st));
