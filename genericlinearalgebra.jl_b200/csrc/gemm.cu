@@ -409,6 +409,308 @@ __global__ void __launch_bounds__(DmmaCfg<BM, BN, STAGES>::THREADS, 2)
       }
 }
 
+// ------------------------------------------------------------------------------- Float32 on tcgen05 (UMMA, 3xTF32)
+// The 5th-generation tensor core path for the Float32 contractions: tcgen05.mma.cta_group::1.kind::tf32 (SASS UTCHMMA),
+// operands read by the tensor core straight from the 128B-swizzled tiles TMA delivers (K-major for both operands: the TN
+// contraction is exactly UMMA's native K-major x K-major form), accumulators in tensor memory.  Persistent, warp
+// specialised, one CTA per SM:
+//     warp 0      TMA producer (one lane): 128 x 32-float boxes of At and B per stage into a 3-deep ring
+//     warps 2-3   operand split: x -> hi = tf32(x) (round to nearest), lo = x - hi (exact), hi written back over the raw
+//                 tile and lo into a sibling tile -- the same byte offsets, so the swizzle never has to be decoded; then
+//                 fence.proxy.async (generic-proxy stores -> tensor-core reads) and an arrive on the stage's `ready` barrier
+//     warp 1      MMA issuer (one lane): per stage 4 k-steps x {lo*hi, hi*lo, hi*hi} = 12 UMMAs of 128 x 128 x 8 into ONE
+//                 of four 128-column TMEM buffers, tcgen05.commit -> `empty` (stage back to TMA) and -> `tmem_full`
+//     warps 4-11  accumulation + epilogue: tcgen05.ld of the slab's partial product and a ROUNDED add into register
+//                 accumulators (the tensor core adds into its accumulator with truncation, a bias that grows linearly with
+//                 the chain length: every slab starts a fresh TMEM accumulator, exactly like the mma.sync kernel above);
+//                 after the last slab of a tile the 128 x 128 block goes to global memory (alpha / beta, edge masks)
+//                 while the MMA warp is already up to four slabs into the next tile.
+namespace umma {
+
+constexpr int BM = 128, BN = 128, BKF = 32;          // tile, floats of K per stage (one 128 B swizzle span)
+constexpr int STAGES = 3;
+constexpr int TBUF = 4;                              // TMEM accumulator buffers of BN columns
+constexpr int THREADS = 384;
+constexpr int SPLIT_WARP0 = 2, SPLIT_THREADS = 64, EPI_WARP0 = 4, EPI_THREADS = 256;
+constexpr int TILE_BYTES = BM * 128;                 // 16 KB: 128 rows of 128 B
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;          // A raw/hi, B raw/hi, A lo, B lo
+constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+// instruction descriptor: D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2), both K-major, N >> 3 at bit 17, M >> 4 at 24
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+// K-major, SWIZZLE_128B operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO = 1 (ignored for swizzled
+// K-major), descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(IDESC), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+      "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// mbarrier wait that cannot hang the device: a second without progress is a protocol bug -> trap (the launch fails loudly)
+__device__ __forceinline__ void wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t done = 0;
+  long long t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (done) return;
+    if ((spin & 0xfff) == 0xfff) {
+      const long long t = clock64();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 4000000000ll) __trap();
+    }
+  }
+}
+
+struct TileIter {   // static round-robin over (m tile, n tile, K slice), skipping tiles outside the requested triangle
+  int mt, nt, nz, lower_only;
+  __device__ __forceinline__ bool decode(int t, int& m0, int& n0, int& z) const {
+    const int per = mt * nt;
+    z = t / per;
+    const int r = t - z * per;
+    n0 = (r / mt) * BN;
+    m0 = (r % mt) * BM;
+    if (lower_only == 1 && n0 >= m0 + BM) return false;
+    if (lower_only == 2 && m0 >= n0 + BN) return false;
+    return true;
+  }
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+    gemm_tn_umma_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                               float* __restrict__ C, i64 ldc, int M, int N, int K, int klen, int nsplit, i64 split_stride,
+                               float alpha, int beta_one, int lower_only, int debug, long long* __restrict__ trace) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + STAGES * STAGE_BYTES);   // TMA landed
+  uint64_t* ready = full + STAGES;                                             // split done
+  uint64_t* empty = ready + STAGES;                                            // MMAs of the stage retired
+  uint64_t* tfull = empty + STAGES;                                            // TMEM buffer holds a slab product
+  uint64_t* tempty = tfull + TBUF;                                             // TMEM buffer drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + TBUF);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  TileIter ti{(M + BM - 1) / BM, (N + BN - 1) / BN, nsplit, lower_only};
+  const int ntiles = ti.mt * ti.nt * nsplit;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&ready[s], SPLIT_THREADS / 32);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < TBUF; ++b) {
+      mbar_init(&tfull[b], 1);
+      mbar_init(&tempty[b], EPI_THREADS / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {   // all of TMEM: TBUF x BN = 512 columns (one CTA per SM)
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TBUF * BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================== TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        int m0, n0, z;
+        if (!ti.decode(t, m0, n0, z)) continue;
+        const int kbeg = z * klen, kend = min(kbeg + klen, K);
+        const int nk = (kend - kbeg + BKF - 1) / BKF;
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % STAGES;
+          wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+          if (trace && blockIdx.x == 0 && it < 256) trace[it] = clock64();
+          unsigned char* st = base + s * STAGE_BYTES;
+          mbar_expect_tx(&full[s], 2 * TILE_BYTES);
+          tma_load_2d(st, &tmA, kbeg + kb * BKF, m0, &full[s]);
+          tma_load_2d(st + TILE_BYTES, &tmB, kbeg + kb * BKF, n0, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================== MMA issuer
+    if (lane == 0) {
+      uint32_t it = 0, sl = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        int m0, n0, z;
+        if (!ti.decode(t, m0, n0, z)) continue;
+        const int kbeg = z * klen, kend = min(kbeg + klen, K);
+        const int nk = (kend - kbeg + BKF - 1) / BKF;
+        for (int kb = 0; kb < nk; ++kb, ++it, ++sl) {
+          const int s = it % STAGES, b = sl % TBUF;
+          wait(&tempty[b], ((sl / TBUF) & 1) ^ 1);
+          wait(&ready[s], (it / STAGES) & 1);
+          if (trace && blockIdx.x == 0 && it < 256) trace[256 + it] = clock64();
+          fence_after();
+          const uint32_t st = smem_u32(base + s * STAGE_BYTES);
+          const uint64_t a_hi = smem_desc(st), b_hi = smem_desc(st + TILE_BYTES);
+          const uint64_t a_lo = smem_desc(st + 2 * TILE_BYTES), b_lo = smem_desc(st + 3 * TILE_BYTES);
+          const uint32_t d = tmem_base + (uint32_t)(b * BN);
+#pragma unroll
+          for (int k = 0; k < BKF / 8; ++k) {       // UMMA_K = 8 floats = 32 B: +2 in the descriptor's 16-byte units
+            const uint64_t o = (uint64_t)(2 * k);
+            mma_tf32_ss(d, a_lo + o, b_hi + o, k > 0 ? 1u : 0u);
+            if (debug & 4) continue;
+            mma_tf32_ss(d, a_hi + o, b_lo + o, 1u);
+            mma_tf32_ss(d, a_hi + o, b_hi + o, 1u);
+          }
+          commit(&empty[s]);    // the stage returns to TMA when these MMAs have read it
+          commit(&tfull[b]);    // and the slab product is complete in TMEM
+        }
+      }
+    }
+  } else if (warp >= SPLIT_WARP0 && warp < SPLIT_WARP0 + SPLIT_THREADS / 32) {
+    // ================================================================== operand split (hi / lo tiles)
+    const int tid = threadIdx.x - SPLIT_WARP0 * 32;
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      int m0, n0, z;
+      if (!ti.decode(t, m0, n0, z)) continue;
+      const int kbeg = z * klen, kend = min(kbeg + klen, K);
+      const int nk = (kend - kbeg + BKF - 1) / BKF;
+      for (int kb = 0; kb < nk; ++kb, ++it) {
+        const int s = it % STAGES;
+        wait(&full[s], (it / STAGES) & 1);
+        if (trace && blockIdx.x == 0 && it < 256 && tid == 0) trace[512 + it] = clock64();
+        const uint32_t st = smem_u32(base + s * STAGE_BYTES);
+#pragma unroll 4
+        for (int e = tid; e < ((debug & 1) ? 0 : 2 * TILE_BYTES / 16); e += SPLIT_THREADS) {
+          const uint32_t a = st + (uint32_t)e * 16;
+          uint32_t x0, x1, x2, x3;
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(a));
+          const uint32_t h0 = (x0 + 0x1000u) & 0xffffe000u, h1 = (x1 + 0x1000u) & 0xffffe000u;   // round to nearest TF32
+          const uint32_t h2 = (x2 + 0x1000u) & 0xffffe000u, h3 = (x3 + 0x1000u) & 0xffffe000u;   // (cvt.rna runs at 1/4 rate)
+          const uint32_t l0 = __float_as_uint(__uint_as_float(x0) - __uint_as_float(h0));
+          const uint32_t l1 = __float_as_uint(__uint_as_float(x1) - __uint_as_float(h1));
+          const uint32_t l2 = __float_as_uint(__uint_as_float(x2) - __uint_as_float(h2));
+          const uint32_t l3 = __float_as_uint(__uint_as_float(x3) - __uint_as_float(h3));
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a + 2 * TILE_BYTES), "r"(l0), "r"(l1), "r"(l2), "r"(l3)
+                       : "memory");
+        }
+        release_fence();          // generic-proxy stores -> async-proxy (tensor core) reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ready[s]);
+        if (trace && blockIdx.x == 0 && it < 256 && tid == 0) trace[768 + it] = clock64();
+      }
+    }
+  } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + EPI_THREADS / 32) {
+    // ================================================================== accumulate + epilogue
+    const int ew = warp - EPI_WARP0;              // 0..7
+    const int quarter = warp & 3;                 // the TMEM lanes this warp may touch: 32 * (warp % 4) ..
+    const int chalf = ew >> 2;                    // columns 64 * chalf .. + 63
+    const uint32_t lane_addr = ((uint32_t)(quarter * 32) << 16) + (uint32_t)(chalf * 64);
+    uint32_t sl = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      int m0, n0, z;
+      if (!ti.decode(t, m0, n0, z)) continue;
+      const int kbeg = z * klen, kend = min(kbeg + klen, K);
+      const int nk = (kend - kbeg + BKF - 1) / BKF;
+      float acc[64];
+#pragma unroll
+      for (int c = 0; c < 64; ++c) acc[c] = 0.f;
+      for (int kb = 0; kb < nk; ++kb, ++sl) {
+        const int b = sl % TBUF;
+        wait(&tfull[b], (sl / TBUF) & 1);
+        if (trace && blockIdx.x == 0 && sl < 256 && threadIdx.x == EPI_WARP0 * 32) trace[1024 + sl] = clock64();
+        fence_after();
+        const uint32_t ta = tmem_base + lane_addr + (uint32_t)(b * BN);
+        float v[32];
+        if (!(debug & 2)) tmem_ld32(ta, v);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[c] += v[c];
+        if (!(debug & 2)) tmem_ld32(ta + 32, v);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[32 + c] += v[c];
+        fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[b]);
+      }
+      const int i = m0 + quarter * 32 + lane;
+      if (i < M) {
+        float* Cz = C + (i64)z * split_stride + i;
+        const bool b1 = beta_one && nsplit == 1;
+        // read-modify-write in batches of 32 columns: all loads of a batch are in flight before its first store
+        // (interleaved ld/st pairs serialise on the store -> load ordering: one DRAM round trip per column)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float cv[32];
+          if (b1) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const int j = n0 + chalf * 64 + h * 32 + c;
+              const bool keep = j < N && !(lower_only == 1 && i < j) && !(lower_only == 2 && i > j);
+              cv[c] = keep ? __ldcg(Cz + (i64)j * ldc) : 0.f;
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const int j = n0 + chalf * 64 + h * 32 + c;
+            const bool keep = j < N && !(lower_only == 1 && i < j) && !(lower_only == 2 && i > j);
+            const float r = alpha * acc[h * 32 + c];
+            if (keep) Cz[(i64)j * ldc] = b1 ? cv[c] + r : r;
+          }
+        }
+      }
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TBUF * BN) : "memory");
+  }
+}
+
+}  // namespace umma
+
 // ------------------------------------------------------------------------------- ComplexF64 on the DMMA pipe
 // C(i,j) = sum_k op(At(k,i)) B(k,j) for interleaved complex operands, computed as TWO real contractions over the
 // 2K interleaved doubles of each operand row (the tile a TMA box delivers IS that real row):
@@ -715,6 +1017,41 @@ int launch_tf32x3(const GemmTN<float>& g, int klen, cudaStream_t st) {
   return 0;
 }
 
+int launch_umma_tf32x3(const GemmTN<float>& g, int klen, cudaStream_t st) {
+  CUtensorMap tmA, tmB;
+  GLA_TRY(make_map_t(&tmA, g.At, g.K, g.M, g.ldat, umma::BM, 4));
+  GLA_TRY(make_map_t(&tmB, g.B, g.K, g.N, g.ldb, umma::BN, 4));
+  static const int dbg = getenv("GLA_UMMA_DEBUG") ? atoi(getenv("GLA_UMMA_DEBUG")) : 0;   // timing experiments only
+  auto kern = umma::gemm_tn_umma_tf32x3_kernel;
+  GLA_TRY(ensure_dyn_smem((const void*)kern, umma::SMEM));
+  const i64 tiles = (i64)ceil_div(g.M, umma::BM) * ceil_div(g.N, umma::BN) * g.nsplit;
+  const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());   // persistent: one CTA per SM
+  long long* trace = nullptr;
+  static const char* trace_path = getenv("GLA_UMMA_TRACE");   // development aid: clock64 stamps of CTA 0's first 256 stages
+  if (trace_path && g.K >= 8192) {
+    GLA_CUDA(cudaMalloc(&trace, 1280 * sizeof(long long)));
+    GLA_CUDA(cudaMemset(trace, 0, 1280 * sizeof(long long)));
+  }
+  kern<<<grid, umma::THREADS, umma::SMEM, st>>>(tmA, tmB, g.C, g.ldc, (int)g.M, (int)g.N, (int)g.K, klen, g.nsplit,
+                                                g.split_stride, g.alpha, g.beta_one, g.lower_only, dbg, trace);
+  GLA_CUDA(cudaGetLastError());
+  if (trace) {
+    static long long host[1280];
+    GLA_CUDA(cudaStreamSynchronize(st));
+    GLA_CUDA(cudaMemcpy(host, trace, sizeof(host), cudaMemcpyDeviceToHost));
+    cudaFree(trace);
+    if (FILE* f = fopen(trace_path, "w")) {
+      fprintf(f, "# M=%lld N=%lld K=%lld: stage, tma_issue, split_sees_full, split_done, mma_sees_ready, epilogue_sees_tfull (cycles from the first TMA)\n",
+              (long long)g.M, (long long)g.N, (long long)g.K);
+      for (int i = 0; i < 256; ++i)
+        fprintf(f, "%d %lld %lld %lld %lld %lld\n", i, host[i] - host[0], host[512 + i] - host[0], host[768 + i] - host[0],
+                host[256 + i] - host[0], host[1024 + i] - host[0]);
+      fclose(f);
+    }
+  }
+  return 0;
+}
+
 bool tma_ok_f32(const GemmTN<float>& g) {
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   return al(g.At) && al(g.B) && (g.ldat & 3) == 0 && (g.ldb & 3) == 0 && g.K >= 1 && g.M < (1ll << 31) &&
@@ -812,6 +1149,10 @@ int gemm_tn<float>(const GemmTN<float>& g, cudaStream_t st) {
   i64 klen = ((g.K > 0 ? g.K : 1) + g.nsplit - 1) / g.nsplit;
   klen = (klen + 31) / 32 * 32;   // K slabs of 32 floats: slices must not share a slab
   static const bool force_fma = getenv("GLA_SGEMM_FMA") != nullptr;   // A/B switch
+  // tcgen05 path for products with at least one full 128 x 128 tile; GLA_SGEMM_MMASYNC=1 keeps the mma.sync kernel (A/B)
+  static const bool no_umma = getenv("GLA_SGEMM_MMASYNC") != nullptr;
+  if (!force_fma && !no_umma && g.K > 0 && tma_ok_f32(g) && g.M >= 128 && g.N >= 128)
+    return launch_umma_tf32x3(g, (int)klen, st);
   if (!force_fma && g.K > 0 && tma_ok_f32(g)) {
     if (g.M <= 64) {
       if ((i64)ceil_div(g.N, 128) * g.nsplit * 2 < sm_count()) return launch_tf32x3<64, 32, 4>(g, (int)klen, st);
