@@ -253,6 +253,184 @@ __global__ void __launch_bounds__(NWARPS * 32, 2)
   }
 }
 
+// ------------------------------------------------------------------------------- level 0, one chain per WARP
+// tsqr_warp_kernel: the first level of the reduction for long row ranges.  The CTA-per-chunk kernel above has two
+// chains per SM and pays a block barrier + a cross-warp exchange of partial dots in every column step.  Here every WARP
+// owns a chain of its own: a private R (packed upper triangle, 16.6 KB of shared memory) and 32-row chunks held in
+// registers with the same lane = column pair layout, so a column step needs no barrier and no reduction at all (a lane's
+// dot runs over the rows in its own registers; the pivot lane's dot with itself is the norm and travels by one shuffle).
+// Eight independent chains per SM (two warps per sub-partition: the 128 payload registers + the temporaries of a step
+// need ~250 registers) hide each other's scalar chains.  The next chunk is pulled into L2 by prefetch instructions while
+// the current one is reduced; its loads are 16-byte vector loads straight into the registers.  Measured: 10.2 ms against
+// 11.0 ms for the CTA-per-chunk kernel at 8,388,608 x 64 (a column step still costs ~2000 cycles of latency per warp).
+constexpr int TW_WARPS = 8;    // two warps per sub-partition = 255 registers: the 128 payload registers + the temporaries of a step do not fit the 168 of three
+constexpr int TW_RPACK = 64 * 65 / 2;             // packed upper triangle of a 64 x 64 R
+constexpr int TW_WARP_DOUBLES = TW_RPACK + 32;    // + the published pivot column
+constexpr size_t TW_SMEM = (size_t)TW_WARPS * TW_WARP_DOUBLES * sizeof(double);
+
+__device__ __forceinline__ int tw_row(int k) { return k * 64 - (k * (k - 1)) / 2 - k; }   // R(k, c) at tw_row(k) + c, c >= k
+
+template <bool TWO, int H>
+__device__ __forceinline__ void tw_step(double (&a0)[32], double (&a1)[32], const int kl, const int lane,
+                                        double* __restrict__ sR, double* __restrict__ pubw) {
+  const int k = 32 * H + kl;
+  if (lane == kl) {
+#pragma unroll
+    for (int r = 0; r < 32; r += 2)
+      *reinterpret_cast<double2*>(pubw + r) = H == 0 ? make_double2(a0[r], a0[r + 1]) : make_double2(a1[r], a1[r + 1]);
+  }
+  __syncwarp();
+  double* rk = sR + tw_row(k);
+  const bool own0 = H == 0 && lane >= kl;                    // this lane holds R(k, lane)
+  const bool own1 = TWO && (H == 0 || lane >= kl);           // ... and R(k, 32 + lane)
+  const double top0 = own0 ? rk[lane] : 0.0;
+  const double top1 = own1 ? rk[32 + lane] : 0.0;
+  // the published column is read twice (dot sweep, update sweep) with broadcast LDS.128: keeping it in 64 registers next to
+  // the 128 payload registers would not fit the 168-register budget of twelve warps per SM
+  double p0[4] = {0., 0., 0., 0.}, p1[4] = {0., 0., 0., 0.};
+#pragma unroll
+  for (int r = 0; r < 32; r += 4) {
+    const double2 xa = *reinterpret_cast<const double2*>(pubw + r);
+    const double2 xb = *reinterpret_cast<const double2*>(pubw + r + 2);
+    if (H == 0) {
+      p0[0] = fma(xa.x, a0[r], p0[0]);
+      p0[1] = fma(xa.y, a0[r + 1], p0[1]);
+      p0[2] = fma(xb.x, a0[r + 2], p0[2]);
+      p0[3] = fma(xb.y, a0[r + 3], p0[3]);
+    }
+    if (TWO) {
+      p1[0] = fma(xa.x, a1[r], p1[0]);
+      p1[1] = fma(xa.y, a1[r + 1], p1[1]);
+      p1[2] = fma(xb.x, a1[r + 2], p1[2]);
+      p1[3] = fma(xb.y, a1[r + 3], p1[3]);
+    }
+  }
+  const double d0 = (p0[0] + p0[1]) + (p0[2] + p0[3]);
+  const double d1 = (p1[0] + p1[1]) + (p1[2] + p1[3]);
+  const double dk = __shfl_sync(0xffffffffu, H == 0 ? d0 : d1, kl);
+  const double alpha = __shfl_sync(0xffffffffu, H == 0 ? top0 : top1, kl);
+  const double n2 = fma(alpha, alpha, dk);
+  if (n2 != 0.0) {  // warp-uniform; zero column: tau = 0, nothing changes
+    double nu, ixi, tau;
+    if (n2 > 1e-280 && n2 < 1e280) {   // same scalar chain as tsqr_stream_kernel (Goldschmidt from the MUFU seeds)
+      double y0, r;
+      asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(n2));
+      double g = n2 * y0, hh = 0.5 * y0;
+      asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(alpha + copysign(g, alpha)));
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const double e = fma(-g, hh, 0.5);
+        g = fma(g, e, g);
+        hh = fma(hh, e, hh);
+      }
+      g = fma(fma(-g, g, n2), hh, g);
+      nu = copysign(g, alpha);
+      const double xi = alpha + nu;
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const double e = fma(-xi, r, 1.0);
+        r = fma(r, e, r);
+      }
+      ixi = r;
+      tau = xi * copysign(hh + hh, alpha);
+    } else {
+      nu = copysign(sqrt(n2), alpha);
+      const double xi = alpha + nu;
+      ixi = 1.0 / xi;
+      tau = xi / nu;
+    }
+    double t0 = 0., t1 = 0.;
+    if (H == 0) {
+      const bool right = lane > kl;
+      const double s = tau * fma(d0, ixi, top0);
+      t0 = right ? -(s * ixi) : 0.;
+      if (own0) rk[lane] = right ? top0 - s : -nu;
+    }
+    if (TWO) {
+      const bool right = (H == 0) || lane > kl;
+      const double s = tau * fma(d1, ixi, top1);
+      t1 = right ? -(s * ixi) : 0.;
+      if (own1) rk[32 + lane] = right ? top1 - s : -nu;
+    }
+#pragma unroll
+    for (int r = 0; r < 32; r += 2) {
+      const double2 xa = *reinterpret_cast<const double2*>(pubw + r);
+      if (H == 0) {
+        a0[r] = fma(t0, xa.x, a0[r]);
+        a0[r + 1] = fma(t0, xa.y, a0[r + 1]);
+      }
+      if (TWO) {
+        a1[r] = fma(t1, xa.x, a1[r]);
+        a1[r + 1] = fma(t1, xa.y, a1[r + 1]);
+      }
+    }
+  }
+  __syncwarp();  // every lane has read the published column before the next owner overwrites it
+}
+
+template <bool TWO>
+__global__ void __launch_bounds__(TW_WARPS * 32, 1)
+    tsqr_warp_kernel(const double* __restrict__ A, const i64 lda, const i64 m, const int n, const i64 rows_per_warp,
+                     double* __restrict__ Rout, const i64 ldro, const i64 out_row_step, const int vec_ok) {
+  extern __shared__ __align__(16) double tw_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* sR = tw_smem + warp * TW_WARP_DOUBLES;
+  double* pubw = sR + TW_RPACK;
+  for (int e = lane; e < TW_RPACK; e += 32) sR[e] = 0.0;
+  __syncwarp();
+  const i64 gw = (i64)blockIdx.x * TW_WARPS + warp;
+  const i64 row_begin = gw * rows_per_warp;
+  i64 row_end = row_begin + rows_per_warp;
+  if (row_end > m) row_end = m;
+  const bool c0ok = lane < n, c1ok = TWO && lane + 32 < n;
+  const double* col0 = A + (i64)(c0ok ? lane : 0) * lda;
+  const double* col1 = A + (i64)(c1ok ? lane + 32 : 0) * lda;
+  const int k0max = n < 32 ? n : 32;
+  const int k1max = n - 32;
+  for (i64 row0 = row_begin; row0 < row_end; row0 += 32) {
+    double a0[32], a1[32];
+    const bool full = row0 + 32 <= row_end;
+    if (full && vec_ok) {
+#pragma unroll
+      for (int r = 0; r < 32; r += 2) {
+        const double2 v = c0ok ? *reinterpret_cast<const double2*>(col0 + row0 + r) : make_double2(0., 0.);
+        a0[r] = v.x;
+        a0[r + 1] = v.y;
+      }
+#pragma unroll
+      for (int r = 0; r < 32; r += 2) {
+        const double2 v = c1ok ? *reinterpret_cast<const double2*>(col1 + row0 + r) : make_double2(0., 0.);
+        a1[r] = v.x;
+        a1[r + 1] = v.y;
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 32; ++r) {
+        const bool rok = row0 + r < row_end;
+        a0[r] = (rok && c0ok) ? col0[row0 + r] : 0.0;
+        a1[r] = (rok && c1ok) ? col1[row0 + r] : 0.0;
+      }
+    }
+    if (row0 + 32 < row_end) {   // pull the next chunk of this lane's two columns (256 B each) into L2
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(col0 + row0 + 32));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(col0 + row0 + 48));
+      if (TWO) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(col1 + row0 + 32));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(col1 + row0 + 48));
+      }
+    }
+    for (int kl = 0; kl < k0max; ++kl) tw_step<TWO, 0>(a0, a1, kl, lane, sR, pubw);
+    if (TWO)
+      for (int kl = 0; kl < k1max; ++kl) tw_step<TWO, 1>(a0, a1, kl, lane, sR, pubw);
+  }
+  __syncwarp();
+  double* out = Rout + gw * out_row_step;
+  for (int e = lane; e < n * n; e += 32) {
+    const int j = e / n, i = e - j * n;
+    out[(i64)j * ldro + i] = i <= j ? sR[tw_row(i) + j] : 0.0;
+  }
+}
+
 constexpr int TS_WARPS = 4;   // warps per CTA
 constexpr int TS_RW = 32;     // rows per warp -> 128-row chunks (measured: 11.0 ms vs 14.3 ms for 8 warps x 16 rows)
 constexpr int TS_CTAS_PER_SM = 2;  // two independent CTAs per SM: one's scalar chain / barrier hides behind the other's FMA sweeps
@@ -293,6 +471,33 @@ static int run_reduction(TsqrSrc src, i64 m, int n, double* dR, i64 ldr, cudaStr
   double* buf[2] = {nullptr, nullptr};
   int rc = 0, cur = 0;
   bool first = true;
+  double* wbuf = nullptr;
+  // level 0 of a long plain column-major range: one chain per warp (tsqr_warp_kernel), 12 x #SM R factors out
+  static const bool no_warp = getenv("GLA_TSQR_NO_WARP") != nullptr;   // A/B switch
+  const i64 nwarps = (i64)sm_count() * TW_WARPS;
+  if (!no_warp && src.bstride == 0 && src.blk_rows >= m && m >= nwarps * 256) {
+    const i64 rows_per_warp = round_up((m + nwarps - 1) / nwarps, 32);
+    const i64 used = (m + rows_per_warp - 1) / rows_per_warp;        // warps that own rows (the others write a zero R)
+    const i64 tall = nwarps * n;
+    rc = pool_malloc(reinterpret_cast<void**>(&wbuf), (size_t)tall * n * sizeof(double), st);
+    if (!rc) {
+      const int vec_ok = ((reinterpret_cast<uintptr_t>(src.p) & 15) == 0 && (src.ld & 1) == 0) ? 1 : 0;
+      (void)used;
+      if (n > 32) {
+        auto kern = tsqr_warp_kernel<true>;
+        rc = ensure_dyn_smem((const void*)kern, (int)TW_SMEM);
+        if (!rc) kern<<<(unsigned)sm_count(), TW_WARPS * 32, TW_SMEM, st>>>(src.p, src.ld, m, n, rows_per_warp, wbuf, tall, n, vec_ok);
+      } else {
+        auto kern = tsqr_warp_kernel<false>;
+        rc = ensure_dyn_smem((const void*)kern, (int)TW_SMEM);
+        if (!rc) kern<<<(unsigned)sm_count(), TW_WARPS * 32, TW_SMEM, st>>>(src.p, src.ld, m, n, rows_per_warp, wbuf, tall, n, vec_ok);
+      }
+      if (!rc) rc = check_cuda(cudaGetLastError(), __FILE__, __LINE__);
+      src = TsqrSrc{wbuf, tall, tall, 0};
+      m = tall;
+      first = false;
+    }
+  }
   while (!rc) {
     i64 grid = (m + ROWS - 1) / ROWS;
     if (first && grid > sms) grid = sms;                 // persistent: every CTA streams many chunks
@@ -315,6 +520,7 @@ static int run_reduction(TsqrSrc src, i64 m, int n, double* dR, i64 ldr, cudaStr
   }
   for (double* b : buf)
     if (b) cudaFreeAsync(b, st);
+  if (wbuf) cudaFreeAsync(wbuf, st);
   return rc;
 }
 
