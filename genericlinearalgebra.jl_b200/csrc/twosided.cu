@@ -760,6 +760,8 @@ int bidiagonalize_dev(T* dA, i64 m, i64 n, i64 lda, T* dtaul, T* dtaur, cudaStre
   if (lda < (m > 1 ? m : 1)) return -4;
   if (m == 0 || n == 0) return 0;
   if (!dA) return -1;
+  if (!dtaul && (m >= n ? n : m - 1) > 0) return -5;
+  if (!dtaur && (m >= n ? n - 1 : m) > 0) return -6;
   if (m >= n) return bidiag_tall<T>(dA, m, n, lda, dtaul, dtaur, st);
   T* C = nullptr;
   const i64 ldc = round_up(n, 2);
@@ -783,6 +785,7 @@ int hessenberg_dev(T* dA, i64 n, i64 lda, T* dtau, cudaStream_t st) {
   if (lda < (n > 1 ? n : 1)) return -3;
   if (n <= 1) return 0;
   if (!dA) return -1;
+  if (!dtau) return -4;
   TsArgs<T> a{};
   a.A = dA;
   a.lda = lda;
@@ -807,6 +810,7 @@ int symtri_dev(T* dA, i64 n, i64 lda, int upper, T* dtau, cudaStream_t st) {
   if (lda < (n > 1 ? n : 1)) return -3;
   if (n == 0) return 0;
   if (!dA) return -1;
+  if (!dtau && n > 1) return -5;
   T* B = nullptr;
   i64 ldb = lda;
   T* W = dA;
