@@ -1112,6 +1112,26 @@ int choose_nsplit(i64 M, i64 N, i64 K, int bm, int bn) {
   return best;
 }
 
+// split count for the PERSISTENT tcgen05 kernel (one CTA per SM, 128 x 128 tiles): the number of (tile, slice) work items
+// should be a multiple of the SM count, or large against it (the static round-robin has no other tail balancing)
+int choose_nsplit_persistent(i64 M, i64 N, i64 K, int max_split) {
+  const i64 tiles = (i64)ceil_div(M, 128) * ceil_div(N, 128);
+  const i64 slots = sm_count();
+  i64 max_by_k = K / 1024 > 0 ? K / 1024 : 1;
+  if (max_by_k > max_split) max_by_k = max_split;
+  int best = 1;
+  double best_eff = 0.0;
+  for (int ns = 1; ns <= max_by_k; ++ns) {
+    const i64 items = tiles * ns;
+    const double eff = (double)items / (double)((items + slots - 1) / slots * slots) - 0.01 * (ns - 1);
+    if (eff > best_eff + 1e-9) {
+      best_eff = eff;
+      best = ns;
+    }
+  }
+  return best;
+}
+
 template <class T>
 static int launch_fma(const GemmTN<T>& g, int klen, cudaStream_t st) {
   dim3 grid((unsigned)ceil_div(g.M, 64), (unsigned)ceil_div(g.N, 64), (unsigned)g.nsplit);

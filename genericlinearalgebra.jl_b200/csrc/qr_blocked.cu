@@ -903,7 +903,11 @@ static int build_T(QrWork<T>& w, const T* Vc, i64 ldvc, i64 mk, int kk, const T*
   return 0;
 }
 
-static int wsplit_for(i64 kk, i64 nA, i64 mk) { return choose_nsplit(kk, nA, mk, kk <= 64 ? 64 : 128, kk <= 64 ? 128 : 64); }
+template <class T>
+static int wsplit_for(i64 kk, i64 nA, i64 mk) {
+  if (sizeof(T) == 4 && kk >= 128 && nA >= 128) return choose_nsplit_persistent(kk, nA, mk, 8);   // tcgen05 path (gemm.cu)
+  return choose_nsplit(kk, nA, mk, kk <= 64 ? 64 : 128, kk <= 64 ? 128 : 64);
+}
 
 // A2 (mk x nA, lda) <- (I - Vc op(T) Vc^H) A2 for ONE panel (kk <= NB reflectors); path 0 scratch
 template <class T>
@@ -916,7 +920,7 @@ static int apply_panel(QrWork<T>& w, const T* Vc, i64 ldvc, const T* VcT, i64 ld
   g1.C = w.Wp[0]; g1.ldc = NB;
   g1.M = kk; g1.N = nA; g1.K = mk;
   g1.conj_a = 1;
-  g1.nsplit = wsplit_for(kk, nA, mk);
+  g1.nsplit = wsplit_for<T>(kk, nA, mk);
   g1.split_stride = (i64)NB * nA;
   if ((i64)g1.nsplit * NB * nA > w.wp_elems[0]) g1.nsplit = (int)(w.wp_elems[0] / ((i64)NB * nA));
   if (g1.nsplit < 1) {
@@ -962,7 +966,7 @@ static int apply_outer(QrWork<T>& w, int b, i64 mo, int kbig, T* A2, i64 lda, i6
   g1.C = w.Wp[1]; g1.ldc = NBO;
   g1.M = kbig; g1.N = nA; g1.K = mo;
   g1.conj_a = 1;
-  g1.nsplit = wsplit_for(kbig, nA, mo);
+  g1.nsplit = wsplit_for<T>(kbig, nA, mo);
   g1.split_stride = (i64)NBO * nA;
   if ((i64)g1.nsplit * NBO * nA > w.wp_elems[1]) g1.nsplit = (int)(w.wp_elems[1] / ((i64)NBO * nA));
   if (g1.nsplit < 1) {
@@ -1153,7 +1157,7 @@ static int apply_outer_fwd(QrWork<T>& w, int b, i64 mo, int kbig, T* A2, i64 lda
   g1.C = w.Wp[1]; g1.ldc = NBO;
   g1.M = kbig; g1.N = nA; g1.K = mo;
   g1.conj_a = 1;
-  g1.nsplit = wsplit_for(kbig, nA, mo);
+  g1.nsplit = wsplit_for<T>(kbig, nA, mo);
   g1.split_stride = (i64)NBO * nA;
   if ((i64)g1.nsplit * NBO * nA > w.wp_elems[1]) g1.nsplit = (int)(w.wp_elems[1] / ((i64)NBO * nA));
   if (g1.nsplit < 1) {
