@@ -145,6 +145,7 @@ __device__ Refl<T> cta_reflector(const T* x, i64 len, i64 inc, bool conj_in, T* 
   r.tau = rs.tau;
   r.nu = rs.nu;
   r.nonzero = rs.nonzero;
+  __syncthreads();   // every thread has read alpha = v[0] before thread 0 overwrites it with the implicit 1 (racecheck finding)
   if (r.nonzero) {
     for (i64 k = threadIdx.x; k < len; k += TS_THREADS) v[k] = k == 0 ? Sc<T>::one() : v[k] * rs.ixi;
   }

@@ -117,3 +117,64 @@ def test_batched_and_tsqr_bitwise_reproducible_under_foreign_streams(gla):
             assert ((Ru.t() @ Ru - G).abs().amax() / G.abs().amax()).item() < 1e-12
         else:
             assert torch.equal(R, refR)
+
+
+def test_float32_qr_on_tcgen05_bitwise_reproducible_under_foreign_streams(gla):
+    """Float32 qrBlocked! (contractions on the tcgen05 kernel: TMA-written tiles rewritten by the split warps through the
+    generic proxy and read by the tensor core through the async proxy) with look-ahead active and a high-priority stream
+    flooding the GPU: bitwise equal run to run, Gram identity at Float32 accuracy."""
+    import torch
+    n = 2304
+    g = torch.Generator(device="cuda").manual_seed(23)
+    src = torch.randn((n, n), generator=g, device="cuda", dtype=torch.float32)
+    tau = torch.zeros(n, device="cuda", dtype=torch.float32)
+    main = torch.cuda.Stream()
+    noise = torch.cuda.Stream(priority=-1)
+    nz = [torch.zeros(1 << 22, device="cuda") for _ in range(4)]
+    big = torch.zeros((2048, 2048), device="cuda")
+    ref = None
+    torch.cuda.synchronize()
+    for it in range(6):
+        dA = src.clone()
+        torch.cuda.synchronize()
+        with torch.cuda.stream(main):
+            gla.qr_blocked_dev(dA.data_ptr(), n, n, n, tau.data_ptr(), 0, main.cuda_stream, np.float32)
+        if it > 0:
+            _noise(torch, noise, nz, big)
+        torch.cuda.synchronize()
+        if ref is None:
+            ref = dA
+            A0, R = src.t().double(), torch.triu(dA.t()).double()
+            G = A0.t() @ A0
+            assert ((R.t() @ R - G).abs().max() / G.abs().max()).item() < 2e-5
+        else:
+            assert torch.equal(dA, ref)
+
+
+def test_twosided_bitwise_reproducible(gla):
+    """The persistent two-sided kernels: redundant per-CTA reflectors and fixed-order sums -> bitwise equal run to run,
+    also with an unrelated stream competing for the SMs while the cooperative grid is resident."""
+    import torch
+    n = 700
+    g = torch.Generator(device="cuda").manual_seed(5)
+    src = torch.randn((n, n), generator=g, device="cuda", dtype=torch.float64)
+    t1 = torch.zeros(n, device="cuda", dtype=torch.float64)
+    t2 = torch.zeros(n, device="cuda", dtype=torch.float64)
+    main = torch.cuda.Stream()
+    noise = torch.cuda.Stream()
+    nz = [torch.zeros(1 << 20, device="cuda") for _ in range(4)]
+    big = torch.zeros((1024, 1024), device="cuda")
+    ref = None
+    torch.cuda.synchronize()
+    for it in range(4):
+        dA = src.clone()
+        torch.cuda.synchronize()
+        with torch.cuda.stream(main):
+            gla.bidiagonalize_dev(dA.data_ptr(), n, n, n, t1.data_ptr(), t2.data_ptr(), main.cuda_stream)
+        if it > 1:
+            _noise(torch, noise, nz, big, rounds=40)
+        torch.cuda.synchronize()
+        if ref is None:
+            ref = (dA, t1.clone(), t2.clone())
+        else:
+            assert torch.equal(dA, ref[0]) and torch.equal(t1, ref[1]) and torch.equal(t2, ref[2])
