@@ -1027,7 +1027,16 @@ int launch_umma_tf32x3(const GemmTN<float>& g, int klen, cudaStream_t st) {
   auto kern = umma::gemm_tn_umma_tf32x3_kernel;
   GLA_TRY(ensure_dyn_smem((const void*)kern, umma::SMEM));
   const i64 tiles = (i64)ceil_div(g.M, umma::BM) * ceil_div(g.N, umma::BN) * g.nsplit;
-  const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());   // persistent: one CTA per SM
+  // persistent, one CTA per SM -- but a CTA retires after at most `tpc` tiles: a grid of immortal CTAs would keep every SM
+  // until the whole product is done, and the high-priority panel chain of the look-ahead schedule (whose kernels need
+  // SMs NOW) would wait behind it
+  // (f32 qrBlocked! n = 16384: 136.5 ms with immortal CTAs, 131.9 / 127.9 / 125.1 ms with 8 / 4 / 2 tiles per CTA; a product that
+  // runs alone prefers the immortal form: 3.97 against 4.48 ms for the wide block application)
+  static const i64 tpc_env = [] { const char* e = getenv("GLA_UMMA_TILES_PER_CTA"); return e ? (i64)atoi(e) : -1ll; }();
+  const i64 tpc = tpc_env >= 0 ? tpc_env : (g.yield_sms ? 2 : 0);
+  i64 grid64 = tiles < sm_count() ? tiles : sm_count();
+  if (tpc > 0 && (tiles + tpc - 1) / tpc > grid64) grid64 = (tiles + tpc - 1) / tpc;
+  const unsigned grid = (unsigned)grid64;
   long long* trace = nullptr;
   static const char* trace_path = getenv("GLA_UMMA_TRACE");   // development aid: clock64 stamps of CTA 0's first 256 stages
   if (trace_path && g.K >= 8192) {

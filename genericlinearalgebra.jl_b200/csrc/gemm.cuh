@@ -33,6 +33,8 @@ struct GemmTN {
   int lower_only = 0;   // triangle mask: 1 = write only i >= j (lower), 2 = only i <= j (upper)
   int nsplit = 1;       // split-K slices (beta_one must be 0 when > 1)
   i64 split_stride = 0; // elements between partial outputs
+  int yield_sms = 0;    // 1: a high-priority stream needs SMs while this product runs (look-ahead schedules): persistent kernels
+                        //    bound the lifetime of their CTAs instead of holding every SM until the product is done
 };
 
 template <class T>

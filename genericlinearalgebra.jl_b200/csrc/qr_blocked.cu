@@ -687,6 +687,7 @@ struct QrWork {
   T* Wp[2] = {nullptr, nullptr};   // split-K partials of W = V^H A2, per path
   T* Z[2] = {nullptr, nullptr};    // NBO x nA, per path
   i64 wp_elems[2] = {0, 0};
+  int yield_sms = 0;               // look-ahead active: the far-update products leave SMs to the panel chain (GemmTN::yield_sms)
   ulonglong2* xd = nullptr;        // LL exchange buffers of the panel kernel
   ulonglong2* xr = nullptr;
   ulonglong2* xw = nullptr;
@@ -966,6 +967,7 @@ static int apply_outer(QrWork<T>& w, int b, i64 mo, int kbig, T* A2, i64 lda, i6
   g1.C = w.Wp[1]; g1.ldc = NBO;
   g1.M = kbig; g1.N = nA; g1.K = mo;
   g1.conj_a = 1;
+  g1.yield_sms = w.yield_sms;
   g1.nsplit = wsplit_for<T>(kbig, nA, mo);
   g1.split_stride = (i64)NBO * nA;
   if ((i64)g1.nsplit * NBO * nA > w.wp_elems[1]) g1.nsplit = (int)(w.wp_elems[1] / ((i64)NBO * nA));
@@ -1006,6 +1008,7 @@ static int apply_outer(QrWork<T>& w, int b, i64 mo, int kbig, T* A2, i64 lda, i6
   g2.C = A2; g2.ldc = lda;
   g2.M = mo; g2.N = nA; g2.K = kbig;
   g2.alpha = -1;
+  g2.yield_sms = w.yield_sms;
   g2.beta_one = 1;
   return gemm_tn<T>(g2, st);
 }
@@ -1061,6 +1064,7 @@ int geqr_blocked_dev(T* dA, i64 m, i64 n, i64 lda, T* dtau, i64 /*blocksize_hint
   const bool overlap = !no_overlap && n > 2 * NBO && m > 2 * NBO;   // small problems: one stream, one buffer
   QrWork<T> w;
   GLA_TRY(w.alloc(m, NBO, n > NBO ? n - NBO : 0, overlap ? 2 : 1, st));
+  w.yield_sms = overlap ? 1 : 0;
   AuxStream aux;
   cudaStream_t sc = st;  // chain stream
   int rc = 0;
@@ -1157,6 +1161,7 @@ static int apply_outer_fwd(QrWork<T>& w, int b, i64 mo, int kbig, T* A2, i64 lda
   g1.C = w.Wp[1]; g1.ldc = NBO;
   g1.M = kbig; g1.N = nA; g1.K = mo;
   g1.conj_a = 1;
+  g1.yield_sms = w.yield_sms;
   g1.nsplit = wsplit_for<T>(kbig, nA, mo);
   g1.split_stride = (i64)NBO * nA;
   if ((i64)g1.nsplit * NBO * nA > w.wp_elems[1]) g1.nsplit = (int)(w.wp_elems[1] / ((i64)NBO * nA));
@@ -1194,6 +1199,7 @@ static int apply_outer_fwd(QrWork<T>& w, int b, i64 mo, int kbig, T* A2, i64 lda
   g2.C = A2; g2.ldc = lda;
   g2.M = mo; g2.N = nA; g2.K = kbig;
   g2.alpha = -1;
+  g2.yield_sms = w.yield_sms;
   g2.beta_one = 1;
   return gemm_tn<T>(g2, st);
 }
