@@ -44,7 +44,7 @@ int gemm_tn(const GemmTN<T>& g, cudaStream_t st);
 template <class T>
 int sum_splits(T* out, i64 ldo, const T* part, i64 ldp, i64 stride, int nsplit, i64 M, i64 N, cudaStream_t st);
 
-// pick a split count so that tiles*nsplit fills the GPU; K slices stay multiples of 16 and >= 256
+// pick a split count so that tiles*nsplit fills the GPU; K slices stay multiples of 16 and >= 64 (GLA_GEMM_MINK)
 int choose_nsplit(i64 M, i64 N, i64 K, int bm, int bn);
 // the same for the persistent tcgen05 Float32 kernel (128 x 128 tiles, one CTA per SM), at most max_split slices
 int choose_nsplit_persistent(i64 M, i64 N, i64 K, int max_split);
