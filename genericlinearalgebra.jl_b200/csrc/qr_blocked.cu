@@ -454,13 +454,14 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) qr_panel_kernel(PanelArgs<T>
 // Semantics: qrUnblocked! (src/qr.jl:86-111) with stdlib reflector! / reflectorApply! (call sites :96, :102), then the
 // clean reflector block Vc (unit diagonal, zeros above) and its transpose VcT like qr_panel_kernel.
 constexpr int CL_MAX = 8;              // portable cluster size
-constexpr int CP_THREADS = 256;
+constexpr int CP_THREADS = 512;
+constexpr int CP_RG = CP_THREADS / NB;   // row groups: thread (c, rg) owns rows rg, rg + CP_RG, ... of column c
 constexpr int CP_LD = NB + 1;          // padded row of the slab
 
 template <class T>
 struct ClusterPanelSmem {   // fixed part; the slab follows
   T xbuf[2][CL_MAX][2 * NB];   // [parity][source rank][dots | pivot-row entries]
-  T part[4][NB];               // partial dots of the four row groups
+  T part[CP_RG][NB];           // partial dots of the row groups
   T tot[2 * NB];               // reduced dots | pivot row
 };
 
@@ -474,7 +475,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) qr_panel_cluster_kernel(PanelAr
   T* S = reinterpret_cast<T*>(smem_raw + sizeof(ClusterPanelSmem<T>));   // S[i * CP_LD + c]
   const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
   const int tid = threadIdx.x;
-  const int c = tid & (NB - 1), rg = tid >> 6;   // column, row group (rows rg, rg + 4, ...)
+  const int c = tid & (NB - 1), rg = tid >> 6;   // column, row group (rows rg, rg + CP_RG, ...)
   const int r0 = rank * a.rows_per;
   const int r1 = (r0 + a.rows_per < a.mk) ? r0 + a.rows_per : a.mk;
   const int rows = r1 > r0 ? r1 - r0 : 0;
@@ -513,21 +514,23 @@ __global__ void __launch_bounds__(CP_THREADS, 1) qr_panel_cluster_kernel(PanelAr
     if (c >= j && c < nb) {
       T d1 = Sc<T>::zero(), d2 = Sc<T>::zero(), d3 = Sc<T>::zero();
       int i = lo + rg;
-      for (; i + 12 < rows; i += 16) {   // four independent accumulators: the loads of a round are all in flight together
-        const T p0 = S[i * CP_LD + j], p1 = S[(i + 4) * CP_LD + j], p2 = S[(i + 8) * CP_LD + j], p3 = S[(i + 12) * CP_LD + j];
-        const T q0 = S[i * CP_LD + c], q1 = S[(i + 4) * CP_LD + c], q2 = S[(i + 8) * CP_LD + c], q3 = S[(i + 12) * CP_LD + c];
+      for (; i + 3 * CP_RG < rows; i += 4 * CP_RG) {   // four independent accumulators: the loads of a round are all in flight together
+        const T p0 = S[i * CP_LD + j], p1 = S[(i + CP_RG) * CP_LD + j], p2 = S[(i + 2 * CP_RG) * CP_LD + j], p3 = S[(i + 3 * CP_RG) * CP_LD + j];
+        const T q0 = S[i * CP_LD + c], q1 = S[(i + CP_RG) * CP_LD + c], q2 = S[(i + 2 * CP_RG) * CP_LD + c], q3 = S[(i + 3 * CP_RG) * CP_LD + c];
         d = fmad(cj(p0), q0, d);
         d1 = fmad(cj(p1), q1, d1);
         d2 = fmad(cj(p2), q2, d2);
         d3 = fmad(cj(p3), q3, d3);
       }
-      for (; i < rows; i += 4) d = fmad(cj(S[i * CP_LD + j]), S[i * CP_LD + c], d);
+      for (; i < rows; i += CP_RG) d = fmad(cj(S[i * CP_LD + j]), S[i * CP_LD + c], d);
       d = (d + d1) + (d2 + d3);
     }
     sm.part[rg][c] = d;
     __syncthreads();
     if (tid < NB) {
-      const T dsum = (sm.part[0][c] + sm.part[1][c]) + (sm.part[2][c] + sm.part[3][c]);
+      T dsum = sm.part[0][c];
+#pragma unroll
+      for (int g2 = 1; g2 < CP_RG; ++g2) dsum = dsum + sm.part[g2][c];
       const T rowj = (j >= r0 && j < r1 && c < nb) ? S[(j - r0) * CP_LD + c] : Sc<T>::zero();
       for (int r = 0; r < CL; ++r) {   // same slot of every CTA's exchange buffer (distributed shared memory)
         T* dst = cluster.map_shared_rank(&sm.xbuf[par][rank][0], r);
@@ -556,15 +559,15 @@ __global__ void __launch_bounds__(CP_THREADS, 1) qr_panel_cluster_kernel(PanelAr
       const T s = cj(rs.tau) * (sm.tot[NB + c] + cj(rs.ixi) * sm.tot[c]);
       const T t = s * rs.ixi;
       int i = lo + rg;
-      for (; i + 12 < rows; i += 16) {   // column c != column j: loads first, then the four stores
-        const T p0 = S[i * CP_LD + j], p1 = S[(i + 4) * CP_LD + j], p2 = S[(i + 8) * CP_LD + j], p3 = S[(i + 12) * CP_LD + j];
-        const T q0 = S[i * CP_LD + c], q1 = S[(i + 4) * CP_LD + c], q2 = S[(i + 8) * CP_LD + c], q3 = S[(i + 12) * CP_LD + c];
+      for (; i + 3 * CP_RG < rows; i += 4 * CP_RG) {   // column c != column j: loads first, then the four stores
+        const T p0 = S[i * CP_LD + j], p1 = S[(i + CP_RG) * CP_LD + j], p2 = S[(i + 2 * CP_RG) * CP_LD + j], p3 = S[(i + 3 * CP_RG) * CP_LD + j];
+        const T q0 = S[i * CP_LD + c], q1 = S[(i + CP_RG) * CP_LD + c], q2 = S[(i + 2 * CP_RG) * CP_LD + c], q3 = S[(i + 3 * CP_RG) * CP_LD + c];
         S[i * CP_LD + c] = q0 - p0 * t;
-        S[(i + 4) * CP_LD + c] = q1 - p1 * t;
-        S[(i + 8) * CP_LD + c] = q2 - p2 * t;
-        S[(i + 12) * CP_LD + c] = q3 - p3 * t;
+        S[(i + CP_RG) * CP_LD + c] = q1 - p1 * t;
+        S[(i + 2 * CP_RG) * CP_LD + c] = q2 - p2 * t;
+        S[(i + 3 * CP_RG) * CP_LD + c] = q3 - p3 * t;
       }
-      for (; i < rows; i += 4) S[i * CP_LD + c] = S[i * CP_LD + c] - S[i * CP_LD + j] * t;
+      for (; i < rows; i += CP_RG) S[i * CP_LD + c] = S[i * CP_LD + c] - S[i * CP_LD + j] * t;
       if (rg == 0 && j >= r0 && j < r1) S[(j - r0) * CP_LD + c] = S[(j - r0) * CP_LD + c] - s;
     }
     __syncthreads();
