@@ -210,12 +210,10 @@ constexpr int SW = 32;  // slice width
 template <class T>
 struct PanelSmem {
   using R = typename Sc<T>::real;
-  T S[CB][CB + 1];     // U_D, S[i][c]
-  T X[CB][CB + 1];     // U_D^-1 (upper); the strict lower triangle is scratch of the doubling steps
   T P[CB][CB + 1];     // pending operand U(rp + k, r + c) as P[k][c]
   T Ys[CB][SW + 1];    // slice of the row panel
   T Ps[CB][SW + 1];    // pending operand of the slice
-  T rowbuf[2][CB];
+  T rowbuf[2][CB + SW];   // row j of the diagonal block | row j of the slice, by step parity
   R dinv[CB];
 };
 
@@ -224,7 +222,8 @@ struct PanelSmem {
 // LDL = true: the unit upper factor of W = U^H D U instead (ldlt!, src/ldlt.jl: no square roots, D real and of either sign
 // on the diagonal, U(j, c) = W(j, c) / d_j, trailing block -= conj(W(j, i)) W(j, c) / d_j); dinv[j] = 1 / d_j.
 template <class T, bool LDL = false>
-__device__ __forceinline__ int factor_block_regs(T (&s)[4][4], const int nb, T (*rowbuf)[CB], typename Sc<T>::real* dinv) {
+__device__ __forceinline__ int factor_block_regs(T (&s)[4][4], T (&ys)[4][2], const int nb, T (*rowbuf)[CB + SW],
+                                                 typename Sc<T>::real* dinv) {
   using R = typename Sc<T>::real;
   const int tid = threadIdx.x;
   const int ty = tid >> 4, tx = tid & 15;
@@ -237,6 +236,12 @@ __device__ __forceinline__ int factor_block_regs(T (&s)[4][4], const int nb, T (
         const T v01 = ja == 0 ? s[0][b] : s[1][b];
         const T v23 = ja == 2 ? s[2][b] : s[3][b];
         rb[tx + 16 * b] = ja < 2 ? v01 : v23;
+      }
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {   // row j of the slice rides along: the solve is the same elimination
+        const T v01 = ja == 0 ? ys[0][b] : ys[1][b];
+        const T v23 = ja == 2 ? ys[2][b] : ys[3][b];
+        rb[CB + tx + 16 * b] = ja < 2 ? v01 : v23;
       }
     }
     __syncthreads();
@@ -253,10 +258,16 @@ __device__ __forceinline__ int factor_block_regs(T (&s)[4][4], const int nb, T (
       ui[a] = (ty + 16 * a > j) ? cj(LDL ? rb[ty + 16 * a] : scale_real(rb[ty + 16 * a], rd)) : Sc<T>::zero();
 #pragma unroll
     for (int b = 0; b < 4; ++b) uc[b] = scale_real(rb[tx + 16 * b], rd);
+    T us[2];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int b = 0; b < 2; ++b) us[b] = scale_real(rb[CB + tx + 16 * b], rd);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
 #pragma unroll
       for (int b = 0; b < 4; ++b) s[a][b] = s[a][b] - ui[a] * uc[b];
+#pragma unroll
+      for (int b = 0; b < 2; ++b) ys[a][b] = ys[a][b] - ui[a] * us[b];
+    }
     if (ty == (j & 15)) {   // row j of the factor: U(j, c) = W(j, c) / d for c > j, d on the diagonal
       const int ja = j >> 4;
 #pragma unroll
@@ -266,6 +277,10 @@ __device__ __forceinline__ int factor_block_regs(T (&s)[4][4], const int nb, T (
           for (int b = 0; b < 4; ++b) {
             const int c = tx + 16 * b;
             s[a][b] = c == j ? Sc<T>::from_real(d) : uc[b];
+          }
+          if (!LDL) {   // Cholesky: row j of the slice is final (U); LDL keeps Y = D U and scales at the store
+#pragma unroll
+            for (int b = 0; b < 2; ++b) ys[a][b] = us[b];
           }
         }
     }
@@ -355,81 +370,26 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(T* __restrict__ W, i64 
     }
   }
   // ---- factorisation of the diagonal block (registers), redundantly in every CTA
-  const int bad = factor_block_regs<T, LDL>(s, nb, sm.rowbuf, sm.dinv);
+  // The slice solve Y = U_D^-H Ys is carried out INSIDE the elimination: row j of the slice is scaled and eliminated from
+  // the rows below it together with row j of the diagonal block (same 64 steps, same barriers).  The earlier form -- explicit
+  // inverse of U_D by recursive doubling, then a 64-term product per slice entry -- cost 17,100 + 6,900 of the kernel's
+  // 65,300 cycles (clock64 trace, n = 4096).
+  const int bad = factor_block_regs<T, LDL>(s, ys, nb, sm.rowbuf, sm.dinv);
   if (bad) {
     if (blockIdx.x == 0 && tid == 0) atomicCAS(info, 0, r + bad);
     return;
   }
-  __syncthreads();   // dinv complete, rowbuf free
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int i = ty + 16 * a, c = tx + 16 * b;
-      sm.S[i][c] = s[a][b];
-      sm.X[i][c] = (i == c) ? Sc<T>::from_real((!LDL && i < nb) ? sm.dinv[i] : R(1)) : Sc<T>::zero();   // LDL: unit factor
-      if (blockIdx.x == 0 && i <= c && c < nb) Ud[(i64)c * CB + i] = s[a][b];
-    }
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 2; ++b) sm.Ys[ty + 16 * a][tx + 16 * b] = ys[a][b];
-  __syncthreads();
-  // ---- X = U_D^-1 by recursive doubling: X12 = -X11 (U12 X22) for blocks of b = 1, 2 .. 32; T = U12 X22 is parked in P
-  // (free after the pending update).  X stays exactly zero below its diagonal, so every dot runs over a whole block
-  // (fixed trip count b, no triangular bounds) and the loads of consecutive terms are independent.
-  for (int b = 1; b < CB; b <<= 1) {
-    const int elems = (CB / 2) * b;   // (CB / 2b) pairs x b x b
-    const int lb = 31 - __clz(b);     // log2 b
-    for (int e = tid; e < elems; e += 256) {
-      const int p = e >> (2 * lb), rem = e & (b * b - 1);
-      const int base = p * 2 * b;
-      const int i = base + (rem >> lb), c = base + b + (rem & (b - 1));
-      T acc0 = Sc<T>::zero(), acc1 = Sc<T>::zero();
-      int l = base + b;
-#pragma unroll 4
-      for (; l + 1 < base + 2 * b; l += 2) {
-        acc0 = fmad(sm.S[i][l], sm.X[l][c], acc0);
-        acc1 = fmad(sm.S[i][l + 1], sm.X[l + 1][c], acc1);
-      }
-      if (l < base + 2 * b) acc0 = fmad(sm.S[i][l], sm.X[l][c], acc0);
-      sm.P[i][c] = acc0 + acc1;
-    }
-    __syncthreads();
-    for (int e = tid; e < elems; e += 256) {
-      const int p = e >> (2 * lb), rem = e & (b * b - 1);
-      const int base = p * 2 * b;
-      const int i = base + (rem >> lb), c = base + b + (rem & (b - 1));
-      T acc0 = Sc<T>::zero(), acc1 = Sc<T>::zero();
-      int l = base;
-#pragma unroll 4
-      for (; l + 1 < base + b; l += 2) {
-        acc0 = fmad(sm.X[i][l], sm.P[l][c], acc0);
-        acc1 = fmad(sm.X[i][l + 1], sm.P[l + 1][c], acc1);
-      }
-      if (l < base + b) acc0 = fmad(sm.X[i][l], sm.P[l][c], acc0);
-      sm.X[i][c] = -(acc0 + acc1);   // the X12 block: nobody reads it at this level
-    }
-    __syncthreads();
-  }
-  // ---- slice solve: Y(i, c) = sum_{l <= i} conj(X(l, i)) * Ys(l, c)
-  if (sw > 0) {
-    T acc[4][2];
+  __syncthreads();   // dinv complete
+  if (blockIdx.x == 0) {
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int b = 0; b < 2; ++b) acc[a][b] = Sc<T>::zero();
-    for (int l = 0; l < nb; ++l) {
-      T xi[4], y[2];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) xi[a] = (l <= ty + 16 * a) ? cj(sm.X[l][ty + 16 * a]) : Sc<T>::zero();
-#pragma unroll
-      for (int b = 0; b < 2; ++b) y[b] = sm.Ys[l][tx + 16 * b];
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 2; ++b) acc[a][b] = fmad(xi[a], y[b], acc[a][b]);
-    }
+      for (int b = 0; b < 4; ++b) {
+        const int i = ty + 16 * a, c = tx + 16 * b;
+        if (i <= c && c < nb) Ud[(i64)c * CB + i] = s[a][b];
+      }
+  }
+  if (sw > 0) {
 #pragma unroll
     for (int b = 0; b < 2; ++b) {
       const int c = tx + 16 * b;
@@ -437,11 +397,11 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(T* __restrict__ W, i64 
       for (int a = 0; a < 4; ++a) {
         const int i = ty + 16 * a;
         if (c < sw && i < nb) {
-          if (LDL) {   // acc = (D U)(i, c): keep it for the trailing updates, store U = D^-1 acc
-            Yw[(i64)(c0 + c) * ldw + r + i] = acc[a][b];
-            W[(i64)(c0 + c) * ldw + r + i] = scale_real(acc[a][b], sm.dinv[i]);
+          if (LDL) {   // ys = (D U)(i, c): keep it for the trailing updates, store U = D^-1 ys
+            Yw[(i64)(c0 + c) * ldw + r + i] = ys[a][b];
+            W[(i64)(c0 + c) * ldw + r + i] = scale_real(ys[a][b], sm.dinv[i]);
           } else {
-            W[(i64)(c0 + c) * ldw + r + i] = acc[a][b];
+            W[(i64)(c0 + c) * ldw + r + i] = ys[a][b];
           }
         }
       }
