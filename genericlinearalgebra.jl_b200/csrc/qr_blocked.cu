@@ -288,7 +288,9 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) qr_panel_kernel(PanelArgs<T>
       __syncthreads();
       const T alpha = sh_row[jl];
       const R n2 = abs2(alpha) + re(sh_d[jl]);
-      const ReflScalars<T> rs = reflector_scalars<T>(alpha, n2);
+      ReflScalars<T> rs;   // real types: MUFU seeds + FMA refinement instead of the IEEE sqrt / division subroutines (per-column critical path)
+      if constexpr (Sc<T>::is_complex) rs = reflector_scalars<T>(alpha, n2);
+      else rs = reflector_scalars_fast<T>(alpha, n2);
       prev_nonzero = rs.nonzero;
       prev_ixi = rs.ixi;
       prev_nu = rs.nu;
