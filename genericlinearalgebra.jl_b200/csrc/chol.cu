@@ -195,16 +195,14 @@ __global__ void __launch_bounds__(256) potrf_block_kernel(T* __restrict__ W, i64
 // ------------------------------------------------------------------------------- fused row-panel kernel (real types)
 // Right-looking step for the row panel U(r : r+nb, r : n) of the mirror (nb <= 64).  The 64 x 64 diagonal block is the
 // sequential part of the whole factorisation (4096 dependent column steps at n = 4096), so it must not also pay kernel
-// boundaries: EVERY CTA of the launch factorises and inverts the diagonal block redundantly (same arithmetic, so bitwise
-// the same factor; no inter-CTA synchronisation) and then solves ITS OWN 32-column slice of the row panel,
-//     Y = U_D^-H * W(r : r+nb, slice)            (rdiv!, src/cholesky.jl:48, as a product with the explicit inverse).
+// boundaries: EVERY CTA of the launch factorises the diagonal block redundantly (same arithmetic, so bitwise the same
+// factor; no inter-CTA synchronisation) and solves ITS OWN 32-column slice of the row panel in the same elimination,
+//     Y = U_D^-H * W(r : r+nb, slice)            (rdiv!, src/cholesky.jl:48: forward substitution, one row per step).
 // kpend > 0: the panel has not yet received the update of the finished rows rp : rp+kpend right above it (the previous
 // panel of its outer block and, for 128-row outer blocks, the whole previous outer block: kpend <= 192):
 //     W(r : r+nb, r : n) -= U(rp : rp+kpend, r : r+nb)^H * U(rp : rp+kpend, r : n)     (rankUpdate!, :51)
 // is applied first, in chunks of 64 rows, to the diagonal block by every CTA and to the slice by its owner.  The factor of the diagonal block
 // goes to a scratch copy (Ud), not into W: other CTAs of the same launch may still be reading the block.
-//   inverse: recursive doubling, X12 = -X11 U12 X22 for blocks of 1, 2, 4 .. 32 (12 barriers, all threads busy) instead of
-//   63 dependent back-substitution steps.
 constexpr int SW = 32;  // slice width
 
 template <class T>
