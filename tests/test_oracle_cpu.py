@@ -158,3 +158,47 @@ def test_ldlt_restatement(oracle):
     assert np.array_equal(got, np.array([[1.0, 1.0], [1.0, -2.0]]))
     got = oracle.ldlt(np.array([[1.0, 1.0], [1.0, 1.0]]), "L")
     assert np.array_equal(got, np.array([[1.0, 1.0], [1.0, 0.0]]))
+
+
+# ---------------------------------------------------------------------------------------------- two-sided reductions (f3)
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex128])
+def test_twosided_restatements(oracle, dtype):
+    """bidiagonalize! / _hessenberg! / symtri! restatements (src/svd.jl:328-381, src/eigenGeneral.jl:18-31,
+    src/eigenSelfAdjoint.jl:450-564): the stored reflectors reproduce the condensed form from the input (what
+    test/svd.jl:100-112, test/eigengeneral.jl:239-249 and test/eigenselfadjoint.jl:61-68 rely on), spectra are invariant,
+    the other triangle of symtri! is untouched."""
+    from twosided_helpers import bidiag_residual, hessenberg_residual, symtri_residual
+    rng = np.random.default_rng(42)
+    eps = np.finfo(np.float32 if dtype == np.float32 else np.float64).eps
+
+    def rand(shape):
+        A = rng.standard_normal(shape)
+        if dtype == np.complex128:
+            A = A + 1j * rng.standard_normal(shape)
+        return np.asfortranarray(A.astype(dtype))
+
+    for shape in [(1, 1), (5, 1), (1, 5), (10, 10), (50, 30), (30, 50), (129, 65)]:
+        A = rand(shape)
+        F, tl, tr, dv, ev, uplo = oracle.bidiagonalize(A.copy(order="F"))
+        assert uplo == ("U" if shape[0] >= shape[1] else "L")
+        assert bidiag_residual(A, F, tl, tr) <= 30 * max(shape) * eps * max(1.0, np.abs(A).max())
+        k = min(shape)
+        B = np.diag(dv.astype(np.float64)) + (np.diag(ev.astype(np.float64), 1 if uplo == "U" else -1) if k > 1 else 0)
+        s_ref = np.linalg.svd(A.astype(np.complex128), compute_uv=False)
+        assert np.max(np.abs(np.sort(s_ref) - np.sort(np.linalg.svd(B, compute_uv=False)))) <= 200 * k * eps * max(1.0, s_ref.max())
+    for n in (1, 2, 3, 10, 65):
+        A = rand((n, n))
+        F, tau = oracle.hessenberg(A.copy(order="F"))
+        assert hessenberg_residual(A, F, tau) <= 30 * n * eps * max(1.0, np.abs(A).max()) * max(1.0, np.sqrt(n))
+        S = np.asfortranarray(A + A.conj().T)
+        for uplo in "LU":
+            poison = np.full_like(S, 7)
+            Sin = np.asfortranarray(np.tril(S) + np.triu(poison, 1) if uplo == "L" else np.triu(S) + np.tril(poison, -1))
+            F, tau, dv, ev = oracle.symtri(Sin.copy(order="F"), uplo)
+            assert symtri_residual(S, F, tau, uplo) <= 30 * n * eps * max(1.0, np.abs(S).max()) * max(1.0, np.sqrt(n))
+            if uplo == "L":
+                assert np.array_equal(np.triu(F, 1), np.triu(Sin, 1))
+            else:
+                assert np.array_equal(np.tril(F, -1), np.tril(Sin, -1))
+            if dtype != np.complex128 and n >= 2:
+                assert tau[n - 2] == 0   # real element types stop one step earlier (src/eigenSelfAdjoint.jl:462)
