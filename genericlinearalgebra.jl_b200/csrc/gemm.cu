@@ -515,7 +515,7 @@ struct TileIter {   // static round-robin over (m tile, n tile, K slice), skippi
 __global__ void __launch_bounds__(THREADS, 1)
     gemm_tn_umma_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                float* __restrict__ C, i64 ldc, int M, int N, int K, int klen, int nsplit, i64 split_stride,
-                               float alpha, int beta_one, int lower_only, int debug, long long* __restrict__ trace) {
+                               float alpha, int beta_one, int lower_only, long long* __restrict__ trace) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(base + STAGES * STAGE_BYTES);   // TMA landed
@@ -597,7 +597,6 @@ __global__ void __launch_bounds__(THREADS, 1)
           for (int k = 0; k < BKF / 8; ++k) {       // UMMA_K = 8 floats = 32 B: +2 in the descriptor's 16-byte units
             const uint64_t o = (uint64_t)(2 * k);
             mma_tf32_ss(d, a_lo + o, b_hi + o, k > 0 ? 1u : 0u);
-            if (debug & 4) continue;
             mma_tf32_ss(d, a_hi + o, b_lo + o, 1u);
             mma_tf32_ss(d, a_hi + o, b_hi + o, 1u);
           }
@@ -621,7 +620,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         if (trace && blockIdx.x == 0 && it < 256 && tid == 0) trace[512 + it] = clock64();
         const uint32_t st = smem_u32(base + s * STAGE_BYTES);
 #pragma unroll 4
-        for (int e = tid; e < ((debug & 1) ? 0 : 2 * TILE_BYTES / 16); e += SPLIT_THREADS) {
+        for (int e = tid; e < 2 * TILE_BYTES / 16; e += SPLIT_THREADS) {
           const uint32_t a = st + (uint32_t)e * 16;
           uint32_t x0, x1, x2, x3;
           asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(a));
@@ -665,10 +664,10 @@ __global__ void __launch_bounds__(THREADS, 1)
         fence_after();
         const uint32_t ta = tmem_base + lane_addr + (uint32_t)(b * BN);
         float v[32];
-        if (!(debug & 2)) tmem_ld32(ta, v);
+        tmem_ld32(ta, v);
 #pragma unroll
         for (int c = 0; c < 32; ++c) acc[c] += v[c];
-        if (!(debug & 2)) tmem_ld32(ta + 32, v);
+        tmem_ld32(ta + 32, v);
 #pragma unroll
         for (int c = 0; c < 32; ++c) acc[32 + c] += v[c];
         fence_before();
@@ -1023,7 +1022,6 @@ int launch_umma_tf32x3(const GemmTN<float>& g, int klen, cudaStream_t st) {
   CUtensorMap tmA, tmB;
   GLA_TRY(make_map_t(&tmA, g.At, g.K, g.M, g.ldat, umma::BM, 4));
   GLA_TRY(make_map_t(&tmB, g.B, g.K, g.N, g.ldb, umma::BN, 4));
-  static const int dbg = getenv("GLA_UMMA_DEBUG") ? atoi(getenv("GLA_UMMA_DEBUG")) : 0;   // timing experiments only
   auto kern = umma::gemm_tn_umma_tf32x3_kernel;
   GLA_TRY(ensure_dyn_smem((const void*)kern, umma::SMEM));
   const i64 tiles = (i64)ceil_div(g.M, umma::BM) * ceil_div(g.N, umma::BN) * g.nsplit;
@@ -1044,7 +1042,7 @@ int launch_umma_tf32x3(const GemmTN<float>& g, int klen, cudaStream_t st) {
     GLA_CUDA(cudaMemset(trace, 0, 1280 * sizeof(long long)));
   }
   kern<<<grid, umma::THREADS, umma::SMEM, st>>>(tmA, tmB, g.C, g.ldc, (int)g.M, (int)g.N, (int)g.K, klen, g.nsplit,
-                                                g.split_stride, g.alpha, g.beta_one, g.lower_only, dbg, trace);
+                                                g.split_stride, g.alpha, g.beta_one, g.lower_only, trace);
   GLA_CUDA(cudaGetLastError());
   if (trace) {
     static long long host[1280];

@@ -501,7 +501,6 @@ struct TsArgs {
   T* urow;
   unsigned long long* bar;
   int* err;
-  int debug;     // timing experiments only (GLA_TS_DEBUG): 1 skips the applications, 2 skips the reflectors
 };
 
 struct TsSmemHead {
@@ -546,22 +545,19 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bidiag_tall_kernel(TsArgs<T> a)
       cta_writeback<T>(A + (i - 1) + i * lda, n - i, lda, v, rrow);
       __syncthreads();
     }
-    Refl<T> rc;
-    if (a.debug & 2) { rc.tau = Sc<T>::one(); rc.nu = 1; rc.nonzero = true; }
-    else rc = cta_reflector<T>(A + i + i * lda, m - i, 1, false, v, red);
+    const Refl<T> rc = cta_reflector<T>(A + i + i * lda, m - i, 1, false, v, red);
     if (blockIdx.x == 0 && threadIdx.x == 0) a.tau1[i] = rc.tau;
-    if (rc.nonzero && i + 1 < n && !(a.debug & 1)) left_apply<T>(A + i + (i + 1) * lda, lda, m - i, n - i - 1, v, rc.tau, red);
+    if (rc.nonzero && i + 1 < n) left_apply<T>(A + i + (i + 1) * lda, lda, m - i, n - i - 1, v, rc.tau, red);
     if (!grid_barrier(bar, flag)) return;
     // ---- phase B: store the column reflector, row reflector, right application
     cta_writeback<T>(A + i + i * lda, m - i, 1, v, rc);
     __syncthreads();
     have_row = false;
     if (i + 1 < n) {
-      if (a.debug & 2) { rrow.tau = Sc<T>::one(); rrow.nu = 1; rrow.nonzero = true; }
-      else rrow = cta_reflector<T>(A + i + (i + 1) * lda, n - i - 1, lda, true, v, red);
+      rrow = cta_reflector<T>(A + i + (i + 1) * lda, n - i - 1, lda, true, v, red);
       have_row = true;
       if (blockIdx.x == 0 && threadIdx.x == 0) a.tau2[i] = rrow.tau;
-      if (rrow.nonzero && i + 1 < m && !(a.debug & 1))
+      if (rrow.nonzero && i + 1 < m)
         right_apply<T>(A + (i + 1) + (i + 1) * lda, lda, m - i - 1, n - i - 1, v, rrow.tau, ysm);
       if (!grid_barrier(bar, flag)) return;
     }
@@ -708,8 +704,6 @@ int ts_prepare(TsArgs<T>& a, TsWork<T>& w, int nvec, bool need_u, int* smem_byte
   GLA_CUDA(cudaMemsetAsync(w.small, 0, 16, st));
   a.bar = static_cast<unsigned long long*>(w.small);
   a.err = reinterpret_cast<int*>(static_cast<unsigned char*>(w.small) + 8);
-  const char* dbg = getenv("GLA_TS_DEBUG");
-  a.debug = dbg ? atoi(dbg) : 0;
   a.gvec = nullptr;
   if (!a.vec_in_smem) {
     GLA_TRY(pool_malloc(reinterpret_cast<void**>(&w.gvec), (size_t)*grid * nvec * a.veclen * sizeof(T), st));

@@ -1,6 +1,6 @@
-"""Float32 contraction throughput through the Cholesky-free route: orgqr/ormqr would mix kernels, so this times
-gla_sgeqr's big products indirectly -- instead use the rank-k update on device-resident data via potrf-free herk:
-not exported as _dev, so time the wide block application (ormqr, 384-wide passes = two big GEMMs per block)."""
+"""Float32 contraction throughput on device-resident data: times the wide block application (ormqr_blocked_dev with 384
+reflectors = W = V^H A and A -= V Z, the two big products of the blocked QR's far update, plus the panel preparation).
+usage: python tools/time_sgemm.py [nA ...]   (REPS=1 for ncu launch lists, GLA_SGEMM_MMASYNC=1 for the mma.sync kernel)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, numpy as np
