@@ -211,7 +211,7 @@ struct PanelSmem {
   T P[CB][CB + 1];     // pending operand U(rp + k, r + c) as P[k][c]
   T Ys[CB][SW + 1];    // slice of the row panel
   T Ps[CB][SW + 1];    // pending operand of the slice
-  T rowbuf[2][CB + SW];   // row j of the diagonal block | row j of the slice, by step parity
+  T rowbuf[2][2 * (CB + SW)];   // rows j, j + 1 of the diagonal block and of the slice, by pair parity
   R dinv[CB];
 };
 
@@ -220,13 +220,101 @@ struct PanelSmem {
 // LDL = true: the unit upper factor of W = U^H D U instead (ldlt!, src/ldlt.jl: no square roots, D real and of either sign
 // on the diagonal, U(j, c) = W(j, c) / d_j, trailing block -= conj(W(j, i)) W(j, c) / d_j); dinv[j] = 1 / d_j.
 template <class T, bool LDL = false>
-__device__ __forceinline__ int factor_block_regs(T (&s)[4][4], T (&ys)[4][2], const int nb, T (*rowbuf)[CB + SW],
+__device__ __forceinline__ int factor_block_regs(T (&s)[4][4], T (&ys)[4][2], const int nb, T (*rowbuf)[2 * (CB + SW)],
                                                  typename Sc<T>::real* dinv) {
   using R = typename Sc<T>::real;
   const int tid = threadIdx.x;
   const int ty = tid >> 4, tx = tid & 15;
-  for (int j = 0; j < nb; ++j) {
-    T* rb = rowbuf[j & 1];
+  int j = 0;
+  if constexpr (!LDL) {
+    // TWO pivot rows per barrier: rows j and j + 1 are published as they stand; after the barrier every thread eliminates row j
+    // from row j + 1 redundantly (the entries it needs: its four columns, its four rows, its two slice columns), so that both
+    // reflectors of the pair are known without a second barrier / shared-memory round trip, and applies a rank-2 update.
+    // Same arithmetic per entry as two single steps (row j + 1 is updated by row j exactly as the general update does it).
+    for (; j + 1 < nb; j += 2) {
+      T* rb0 = rowbuf[(j >> 1) & 1];
+      T* rb1 = rb0 + (CB + SW);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int jr = j + h;
+        if (ty == (jr & 15)) {
+          const int ja = jr >> 4;
+          T* rb = h ? rb1 : rb0;
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const T v01 = ja == 0 ? s[0][b] : s[1][b];
+            const T v23 = ja == 2 ? s[2][b] : s[3][b];
+            rb[tx + 16 * b] = ja < 2 ? v01 : v23;
+          }
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            const T v01 = ja == 0 ? ys[0][b] : ys[1][b];
+            const T v23 = ja == 2 ? ys[2][b] : ys[3][b];
+            rb[CB + tx + 16 * b] = ja < 2 ? v01 : v23;
+          }
+        }
+      }
+      __syncthreads();
+      const R piv0 = re(rb0[j]);
+      if (!(piv0 > R(0))) return j + 1;
+      const R rd0 = Fast<R>::rsqrt(piv0);
+      T w0[4], uc0[4], us0[2];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) w0[a] = scale_real(rb0[ty + 16 * a], rd0);
+#pragma unroll
+      for (int b = 0; b < 4; ++b) uc0[b] = scale_real(rb0[tx + 16 * b], rd0);
+#pragma unroll
+      for (int b = 0; b < 2; ++b) us0[b] = scale_real(rb0[CB + tx + 16 * b], rd0);
+      const T u01 = scale_real(rb0[j + 1], rd0);      // U(j, j + 1)
+      const T m = cj(u01);
+      const R piv1 = re(rb1[j + 1] - m * u01);
+      if (!(piv1 > R(0))) return j + 2;
+      const R rd1 = Fast<R>::rsqrt(piv1);
+      if (tid == 0) {
+        dinv[j] = rd0;
+        dinv[j + 1] = rd1;
+      }
+      T ui0[4], ui1[4], uc1[4], us1[2];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        ui0[a] = (ty + 16 * a > j) ? cj(w0[a]) : Sc<T>::zero();
+        ui1[a] = (ty + 16 * a > j + 1) ? cj(scale_real(rb1[ty + 16 * a] - m * w0[a], rd1)) : Sc<T>::zero();
+      }
+#pragma unroll
+      for (int b = 0; b < 4; ++b) uc1[b] = scale_real(rb1[tx + 16 * b] - m * uc0[b], rd1);
+#pragma unroll
+      for (int b = 0; b < 2; ++b) us1[b] = scale_real(rb1[CB + tx + 16 * b] - m * us0[b], rd1);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) s[a][b] = (s[a][b] - ui0[a] * uc0[b]) - ui1[a] * uc1[b];
+#pragma unroll
+        for (int b = 0; b < 2; ++b) ys[a][b] = (ys[a][b] - ui0[a] * us0[b]) - ui1[a] * us1[b];
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int jr = j + h;
+        if (ty == (jr & 15)) {   // rows j, j + 1 of the factor (and of the solved slice)
+          const int ja = jr >> 4;
+          const R d = h ? Fast<R>::sqrt_from_rsqrt(piv1, rd1) : Fast<R>::sqrt_from_rsqrt(piv0, rd0);
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+            if (a == ja) {
+#pragma unroll
+              for (int b = 0; b < 4; ++b) {
+                const int c = tx + 16 * b;
+                s[a][b] = c == jr ? Sc<T>::from_real(d) : (h ? uc1[b] : uc0[b]);
+              }
+#pragma unroll
+              for (int b = 0; b < 2; ++b) ys[a][b] = h ? us1[b] : us0[b];
+            }
+        }
+      }
+    }
+  }
+  int par = (j >> 1) & 1;   // the buffer the last pair did NOT use; single steps (LDL, odd tail) alternate from there
+  for (; j < nb; ++j, par ^= 1) {
+    T* rb = rowbuf[par];
     if (ty == (j & 15)) {
       const int ja = j >> 4;
 #pragma unroll
