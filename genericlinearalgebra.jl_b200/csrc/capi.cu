@@ -577,6 +577,11 @@ int gla_zpotrf_blocked_L(void* A, int64_t n, int64_t lda, int64_t blocksize) { r
 // ---- LDL^H without pivoting (real element types; ComplexF64 / Quaternion stay on the reference path)
 int gla_sldlt(float* A, int64_t n, int64_t lda, int uplo, int64_t blocksize) { return ldlt_host<float>(A, n, lda, uplo, blocksize); }
 int gla_dldlt(double* A, int64_t n, int64_t lda, int uplo, int64_t blocksize) { return ldlt_host<double>(A, n, lda, uplo, blocksize); }
+int gla_zldlt(void* A, int64_t n, int64_t lda, int uplo, int64_t blocksize) { return ldlt_host<zd>(ZP(A), n, lda, uplo, blocksize); }
+int gla_zldlt_dev(void* dA, int64_t n, int64_t lda, int uplo, int* dinfo, void* stream) {
+  if (uplo != 'L' && uplo != 'U') return -4;
+  return ldlt_dev<zd>(ZP(dA), n, lda, uplo == 'U', dinfo, STREAM(stream));
+}
 int gla_sldlt_dev(float* dA, int64_t n, int64_t lda, int uplo, int* dinfo, void* stream) {
   if (uplo != 'L' && uplo != 'U') return -4;
   return ldlt_dev<float>(dA, n, lda, uplo == 'U', dinfo, STREAM(stream));

@@ -584,14 +584,13 @@ static bool use_panel_path() {
     const char* e = getenv("GLA_CHOL_RECURSIVE");
     return e && atoi(e) != 0;
   }();
-  return !Sc<T>::is_complex && !off;   // ComplexF64: the panel kernel's tiles do not fit in shared memory
+  static const bool zoff = getenv("GLA_CHOL_Z_RECURSIVE") != nullptr;   // A/B: ComplexF64 on the round-1 recursion
+  return !off && !(Sc<T>::is_complex && zoff);   // (ComplexF64 fits since the explicit inverse left the kernel: 140 KB of tiles)
 }
 
 template <class T, bool LDL = false>
 static int chol_right_looking(CholCtx<T>& cx, i64 n) {
-  if constexpr (Sc<T>::is_complex) {
-    return GLA_ERR_INTERNAL;
-  } else {
+  {
     const int smem = (int)sizeof(PanelSmem<T>);
     GLA_TRY(ensure_dyn_smem((const void*)chol_panel_kernel<T, LDL>, smem));
     static const int dbg_skip = [] {   // timing experiments only: 1 = no trailing updates, 2 = no panel kernels
@@ -743,9 +742,7 @@ int ldlt_dev(T* dA, i64 n, i64 lda, int upper, int* dinfo, cudaStream_t st) {
   if (n == 0) return 0;
   if (!dA) return -1;
   if (!dinfo) return -5;
-  if constexpr (Sc<T>::is_complex) {
-    return -1;   // no ComplexF64 method: stays on the reference path
-  } else {
+  {   // ComplexF64: Hermitian input, the imaginary part of the diagonal is ignored (D is real)
     CholCtx<T> cx;
     cx.ldw = round_up(n, 16);
     cx.st = st;

@@ -373,12 +373,10 @@ def cholBlocked_(A, uplo="L", blocksize: int = 64):
 
 def ldlt_(A, uplo="L", blocksize=None):
     """LinearAlgebra.ldlt!(Hermitian(A, uplo), blocksize) of the reference (src/ldlt.jl:155-162), without pivoting:
-    in place, D on the diagonal, the unit factor in the strict `uplo` triangle.  Float32 / Float64."""
+    in place, D on the diagonal, the unit factor in the strict `uplo` triangle.  Float32 / Float64 / ComplexF64 (Hermitian)."""
     lda = _colmajor(A, "ldlt!")
     if A.shape[0] != A.shape[1]:
         raise DimensionMismatch(f"matrix is not square: dimensions are {A.shape}")
-    if A.dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
-        raise TypeError("ldlt!: only Float32/Float64 have a GPU method; other element types stay on the reference path")
     u = uplo[-1]
     if u not in ("L", "U"):
         raise ArgumentError("uplo must be :L or :U")

@@ -79,8 +79,8 @@ for T in (Float32, Float64, ComplexF64)
     end
 end
 
-# ---- ldlt!(A::Hermitian, blocksize)                      replaces src/ldlt.jl:155-162 for real element types
-for T in (Float32, Float64)
+# ---- ldlt!(A::Hermitian, blocksize)                      replaces src/ldlt.jl:155-162
+for T in (Float32, Float64, ComplexF64)
     @eval function LinearAlgebra.ldlt!(A::Hermitian{$T,Matrix{$T}}, blocksize::Int = max(1, 128 ÷ sizeof($T)))
         GLACuda.ldlt_inplace!(A.data, A.uplo, blocksize)
         return LDLt(A)

@@ -185,9 +185,9 @@ for (T, p) in ((Float32, "s"), (Float64, "d"), (ComplexF64, "z"))
     end
 end
 
-# gla_{s,d}ldlt: LDL^H without pivoting, in place                      (ldlt!, src/ldlt.jl:155-162; real types only)
+# gla_{s,d,z}ldlt: LDL^H without pivoting, in place                    (ldlt!, src/ldlt.jl:155-162)
 const GLA_ERR_SINGULAR = Cint(901)
-for (T, sym) in ((Float32, :gla_sldlt), (Float64, :gla_dldlt))
+for (T, sym) in ((Float32, :gla_sldlt), (Float64, :gla_dldlt), (ComplexF64, :gla_zldlt))
     @eval function ldlt_inplace!(A::Matrix{$T}, uplo::Char, blocksize::Integer)
         n = LinearAlgebra.checksquare(A)
         rc = GC.@preserve A ccall(($(QuoteNode(sym)), libgla), Cint,

@@ -178,12 +178,15 @@ GLA_API int gla_zpotrf_blocked_L(void* A, int64_t n, int64_t lda, int64_t blocks
  * replaces ldlt!(A::Hermitian, blocksize)   src/ldlt.jl:155-162  ->  _ldlt_lower_blocked! (:80-103) for uplo = 'L',
  * _ldlt_upper_blocked! (:122-146) for uplo = 'U'.  In place: D on the diagonal, the unit factor in the strict `uplo`
  * triangle, the other triangle untouched; `blocksize` >= 1 is a hint (the reference's default is 128 / sizeof(T)).
- * Float32 / Float64 only (ComplexF64, Quaternion, Rational stay on the reference path).  A zero pivot returns
+ * Float32 / Float64 / ComplexF64 (Hermitian: the imaginary part of the diagonal is ignored, D is real; Quaternion and Rational
+ * stay on the reference path).  A zero pivot returns
  * GLA_ERR_SINGULAR with its index in gla_last_info() (the reference divides by it). */
 GLA_API int gla_sldlt(float* A, int64_t n, int64_t lda, int uplo, int64_t blocksize);
 GLA_API int gla_dldlt(double* A, int64_t n, int64_t lda, int uplo, int64_t blocksize);
+GLA_API int gla_zldlt(void* A, int64_t n, int64_t lda, int uplo, int64_t blocksize);
 GLA_API int gla_sldlt_dev(float* dA, int64_t n, int64_t lda, int uplo, int* dinfo, void* stream);
 GLA_API int gla_dldlt_dev(double* dA, int64_t n, int64_t lda, int uplo, int* dinfo, void* stream);
+GLA_API int gla_zldlt_dev(void* dA, int64_t n, int64_t lda, int uplo, int* dinfo, void* stream);
 
 /* ---- two-sided Householder reductions (the step after QR in the reference's SVD / eigen pipelines) ----------
  * gla_?bidiagonalize   replaces bidiagonalize!(A)                      src/svd.jl:328-381

@@ -132,10 +132,12 @@ def test_panel_path_matches_recursion_bitwise_shape(gla, oracle):
 
 
 def _hermitian_dd(rng, n, dtype, indefinite):
-    """Diagonally dominant symmetric test matrix (all leading minors well conditioned, so LDL^T without pivoting is
+    """Diagonally dominant symmetric / Hermitian test matrix (all leading minors well conditioned, so LDL^T without pivoting is
     stable); with `indefinite` the diagonal alternates in sign."""
     X = rng.standard_normal((n, n))
-    H = (X + X.T) / 2
+    if dtype == np.complex128:
+        X = X + 1j * rng.standard_normal((n, n))
+    H = (X + X.conj().T) / 2
     d = np.abs(H).sum(axis=1) + 1.0
     if indefinite:
         d = d * np.where(np.arange(n) % 3 == 1, -1.0, 1.0)
@@ -143,7 +145,7 @@ def _hermitian_dd(rng, n, dtype, indefinite):
     return np.asfortranarray(H.astype(dtype))
 
 
-@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.complex128])
 @pytest.mark.parametrize("uplo", ["L", "U"])
 @pytest.mark.parametrize("n", [1, 2, 5, 50, 64, 65, 130, 500, 1000])
 def test_ldlt_vs_oracle(gla, oracle, dtype, uplo, n):
@@ -159,12 +161,13 @@ def test_ldlt_vs_oracle(gla, oracle, dtype, uplo, n):
         assert np.max(np.abs(tri(got) - tri(ref))) <= tol * np.max(np.abs(tri(ref)))
         other = (np.triu(got, 1), np.triu(H, 1)) if uplo == "L" else (np.tril(got, -1), np.tril(H, -1))
         assert np.array_equal(*other)
-        d = np.diag(got).astype(np.float64)
+        d = np.real(np.diag(got)).astype(np.float64)
         if indefinite and n >= 5:
             assert d.min() < 0 < d.max()
-        F = tri(got, -1 if uplo == "L" else 1).astype(np.float64) + np.eye(n)
-        R = F @ np.diag(d) @ F.T if uplo == "L" else F.T @ np.diag(d) @ F
-        Hs = np.tril(H) + np.tril(H, -1).T if uplo == "L" else np.triu(H) + np.triu(H, 1).T
+        wide = np.complex128 if dtype == np.complex128 else np.float64
+        F = tri(got, -1 if uplo == "L" else 1).astype(wide) + np.eye(n)
+        R = F @ np.diag(d) @ F.conj().T if uplo == "L" else F.conj().T @ np.diag(d) @ F
+        Hs = np.tril(H) + np.tril(H, -1).conj().T if uplo == "L" else np.triu(H) + np.triu(H, 1).conj().T
         assert np.max(np.abs(R - Hs)) <= tol * np.max(np.abs(Hs))
 
 
@@ -177,7 +180,7 @@ def test_ldlt_zero_pivot_and_errors(gla):
     with pytest.raises(gla.DimensionMismatch):
         gla.ldlt_(np.zeros((3, 4), order="F"))
     with pytest.raises(TypeError):
-        gla.ldlt_(np.asfortranarray(np.eye(3, dtype=np.complex128)))
+        gla.ldlt_(np.asfortranarray(np.eye(3, dtype=np.float16)))
     # the doc example of the reference (src/ldlt.jl docstring): [1 1; 1 -1] -> L = [1 0; 1 1], D = (1, -2)
     got = gla.ldlt_(np.asfortranarray(np.array([[1.0, 1.0], [1.0, -1.0]])), "U")
     assert np.array_equal(got, np.array([[1.0, 1.0], [1.0, -2.0]]))
