@@ -627,7 +627,21 @@ int64_t gla_workspace_query(int op, int elem_bytes, int64_t m, int64_t n) {
     case GLA_OP_GEQR_BLOCKED: return geqr_blocked_workspace_bytes(m, n, e);
     case GLA_OP_POTRF_L: return (round_up(n, 16) * n + (n + 63) / 64 * 64 * 64) * e + 256;   // mirror + diagonal blocks
     case GLA_OP_GEQR_BATCHED: return 0;
-    case GLA_OP_TSQR: return 2 * (int64_t)sm_count() * 2 * n * n * e;                          // two levels of per-CTA R factors
+    case GLA_OP_TSQR: return (2 * 2 + 8) * (int64_t)sm_count() * n * n * e;   // per-warp R factors of level 0 + two levels of per-CTA ones
+    case GLA_OP_LDLT: return (2 * round_up(n, 16) * n + (n + 63) / 64 * 64 * 64) * e + 512;   // mirror + Y = D U + diagonal blocks
+    case GLA_OP_BIDIAGONALIZE:
+    case GLA_OP_HESSENBERG:
+    case GLA_OP_SYMTRI: {
+      // barrier counter; per-CTA vector slabs when max(m, n) elements (two vectors for symtri) exceed the 200 KB shared-memory
+      // budget; symtri: the two partial vectors and (uplo = 'U') the flipped copy; bidiagonalize with m < n: the A^H copy
+      const int64_t len = m > n ? m : n;
+      const int64_t nvec = op == GLA_OP_SYMTRI ? 2 : 1;
+      int64_t bytes = 256;
+      if ((32 + 512) * e + 16 + nvec * len * e > 200 * 1024) bytes += (int64_t)sm_count() * nvec * len * e;
+      if (op == GLA_OP_SYMTRI) bytes += 2 * len * e + round_up(n, 2) * n * e;
+      if (op == GLA_OP_BIDIAGONALIZE && m < n) bytes += round_up(n, 2) * m * e;
+      return bytes;
+    }
     default: return -1;
   }
 }

@@ -386,7 +386,7 @@ def ldlt_(A, uplo="L", blocksize=None):
     return A
 
 
-OP_GEQR_BLOCKED, OP_POTRF_L, OP_GEQR_BATCHED, OP_TSQR = 1, 2, 3, 4
+OP_GEQR_BLOCKED, OP_POTRF_L, OP_GEQR_BATCHED, OP_TSQR, OP_LDLT, OP_BIDIAGONALIZE, OP_HESSENBERG, OP_SYMTRI = 1, 2, 3, 4, 5, 6, 7, 8
 
 
 def workspace_query(op: int, dtype, m: int, n: int) -> int:

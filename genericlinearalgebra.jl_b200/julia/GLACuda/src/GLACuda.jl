@@ -47,6 +47,7 @@ end
 
 # workspace query (the reference's LAPACK wrappers ask for their workspace first, src/lapack.jl:152-170)
 const OP_GEQR_BLOCKED, OP_POTRF_L, OP_GEQR_BATCHED, OP_TSQR = Cint(1), Cint(2), Cint(3), Cint(4)
+const OP_LDLT, OP_BIDIAGONALIZE, OP_HESSENBERG, OP_SYMTRI = Cint(5), Cint(6), Cint(7), Cint(8)
 function workspace_query(op::Integer, ::Type{T}, m::Integer, n::Integer) where {T<:GLAFloat}
     b = ccall((:gla_workspace_query, libgla), Int64, (Cint, Cint, Int64, Int64), op, sizeof(T), m, n)
     b < 0 && throw(ArgumentError("workspace_query: argument $(-b) is illegal"))

@@ -229,6 +229,10 @@ GLA_API int gla_zsymtri_dev(void* dA, int64_t n, int64_t lda, int uplo, void* dt
 #define GLA_OP_POTRF_L 2
 #define GLA_OP_GEQR_BATCHED 3
 #define GLA_OP_TSQR 4
+#define GLA_OP_LDLT 5            /* n x n (m ignored) */
+#define GLA_OP_BIDIAGONALIZE 6
+#define GLA_OP_HESSENBERG 7      /* n x n */
+#define GLA_OP_SYMTRI 8          /* n x n, upper bound over uplo */
 GLA_API int64_t gla_workspace_query(int op, int elem_bytes, int64_t m, int64_t n);
 
 /* ---- Hermitian rank-k update, lower ---------------------------------------------------

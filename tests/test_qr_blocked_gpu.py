@@ -172,6 +172,11 @@ def test_device_twins_and_workspace_query(gla, oracle):
     assert gla.workspace_query(gla.OP_GEQR_BLOCKED, np.float64, 4096, 4096) > 4096 * 384 * 8
     assert gla.workspace_query(gla.OP_POTRF_L, np.float64, 4096, 4096) >= 4096 * 4096 * 8
     assert gla.workspace_query(gla.OP_GEQR_BATCHED, np.float64, 32, 32) == 0
+    assert gla.workspace_query(gla.OP_LDLT, np.float64, 4096, 4096) >= 2 * 4096 * 4096 * 8
+    assert gla.workspace_query(gla.OP_HESSENBERG, np.float64, 2048, 2048) < 4096                      # vectors live in shared memory
+    assert gla.workspace_query(gla.OP_BIDIAGONALIZE, np.float64, 100, 300) >= 300 * 100 * 8          # the A^H copy of the wide case
+    assert gla.workspace_query(gla.OP_BIDIAGONALIZE, np.float64, 40000, 8) >= 148 * 40000 * 8        # per-CTA slabs: the column exceeds the budget
+    assert gla.workspace_query(gla.OP_SYMTRI, np.complex128, 500, 500) >= 500 * 500 * 16             # the flipped copy of uplo = 'U'
     with pytest.raises(gla.ArgumentError):
         gla.workspace_query(99, np.float64, 4, 4)
 
