@@ -475,7 +475,9 @@ static int run_reduction(TsqrSrc src, i64 m, int n, double* dR, i64 ldr, cudaStr
   // level 0 of a long plain column-major range: one chain per warp (tsqr_warp_kernel), 12 x #SM R factors out
   static const bool no_warp = getenv("GLA_TSQR_NO_WARP") != nullptr;   // A/B switch
   const i64 nwarps = (i64)sm_count() * TW_WARPS;
-  if (!no_warp && src.bstride == 0 && src.blk_rows >= m && m >= nwarps * 256) {
+  // (worth it from ~1500 rows per warp on: below that the extra tree level over its 8 x #SM R factors costs more than the
+  //  level-0 gain -- 8-GPU shards of the 8,388,608-row config: 1.92 ms with it, 1.86 ms without)
+  if (!no_warp && src.bstride == 0 && src.blk_rows >= m && m >= nwarps * 1536) {
     const i64 rows_per_warp = round_up((m + nwarps - 1) / nwarps, 32);
     const i64 used = (m + rows_per_warp - 1) / rows_per_warp;        // warps that own rows (the others write a zero R)
     const i64 tall = nwarps * n;
