@@ -131,6 +131,22 @@ def test_panel_path_matches_recursion_bitwise_shape(gla, oracle):
         assert np.array_equal(np.triu(got, 1), np.triu(S, 1))
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.complex128])
+def test_panel_path_other_types_above_lookahead(gla, oracle, dtype):
+    """Float32 (trailing updates on the tcgen05 kernel with the triangle mask and bounded CTA lifetime) and ComplexF64 (panel
+    kernel at 254 registers, complex DMMA updates) through the look-ahead schedule of the right-looking driver."""
+    rng = np.random.default_rng(11)
+    for n in (449, 1500):
+        S = _spd(rng, n, dtype, shift=float(n) if dtype == np.float32 else 1.0)
+        got = gla.cholRecursive_(S.copy(order="F"))
+        ref = oracle.chol_recursive(S, 1, mt=True)
+        assert np.max(np.abs(np.tril(got) - np.tril(ref))) <= TOL[dtype] * n * np.max(np.abs(ref))
+        assert np.array_equal(np.triu(got, 1), np.triu(S, 1))
+        L = np.tril(got).astype(np.complex128 if dtype == np.complex128 else np.float64)
+        Sw = S.astype(L.dtype)
+        assert np.linalg.norm(L @ L.conj().T - Sw) / np.linalg.norm(Sw) <= 10 * n * np.finfo(np.float32 if dtype == np.float32 else np.float64).eps
+
+
 def _hermitian_dd(rng, n, dtype, indefinite):
     """Diagonally dominant symmetric / Hermitian test matrix (all leading minors well conditioned, so LDL^T without pivoting is
     stable); with `indefinite` the diagonal alternates in sign."""
