@@ -150,9 +150,18 @@ int geqr_blocked_host(T* A, i64 m, i64 n, i64 lda, T* tau, i64 hint) {
   GLA_TRY(e0.create());
   GLA_TRY(e1.create());
   GLA_CUDA(cudaEventRecord(e0.e, st.s));
-  GLA_TRY(geqr_blocked_dev<T>(dA.p(), m, n, dA.ld, dtau.as<T>(), hint, st.s));
+  // finished outer blocks go home on a second stream while the later far updates run (see QrHostSink)
+  Stream cp;
+  GLA_TRY(cp.create());
+  QrHostSink<T> sink;
+  sink.hA = A;
+  sink.ldh = lda;
+  sink.copy = cp.s;
+  GLA_TRY(geqr_blocked_dev<T>(dA.p(), m, n, dA.ld, dtau.as<T>(), hint, st.s, &sink));
   GLA_CUDA(cudaEventRecord(e1.e, st.s));
-  GLA_TRY(dA.download(A, lda, m, n, st.s));
+  if (sink.copied_cols < n)
+    GLA_TRY(d2h_matrix<T>(A + sink.copied_cols * lda, lda, dA.p() + sink.copied_cols * dA.ld, dA.ld, m, n - sink.copied_cols, st.s));
+  GLA_CUDA(cudaStreamSynchronize(cp.s));
   GLA_CUDA(cudaMemcpyAsync(tau, dtau.p, k * sizeof(T), cudaMemcpyDeviceToHost, st.s));
   GLA_CUDA(cudaStreamSynchronize(st.s));
   float ms = 0;

@@ -13,8 +13,18 @@ template <class T>
 int geqr_batched_dev(T* dA, i64 m, i64 n, i64 batch, T* dtau, cudaStream_t st);
 
 // K1/K2/K3: blocked QR of one large matrix (qr_blocked.cu)
+// Host destination of a factorisation driven through the host-pointer entry point: the columns of an outer block are final
+// as soon as its panel chain is done, so they travel device -> host on `copy` WHILE the far updates of the later blocks
+// run (PCIe is otherwise idle during the factorisation).  copied_cols = columns already on their way when the call returns.
 template <class T>
-int geqr_blocked_dev(T* dA, i64 m, i64 n, i64 lda, T* dtau, i64 blocksize_hint, cudaStream_t st);
+struct QrHostSink {
+  T* hA = nullptr;
+  i64 ldh = 0;
+  cudaStream_t copy = nullptr;
+  i64 copied_cols = 0;
+};
+template <class T>
+int geqr_blocked_dev(T* dA, i64 m, i64 n, i64 lda, T* dtau, i64 blocksize_hint, cudaStream_t st, QrHostSink<T>* sink = nullptr);
 i64 geqr_blocked_workspace_bytes(i64 m, i64 n, i64 elem_bytes);
 // compact-WY T of all k=min(m,n) reflectors; dT is k x k (ldt)
 template <class T>

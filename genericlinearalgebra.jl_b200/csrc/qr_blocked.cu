@@ -1056,7 +1056,7 @@ i64 geqr_blocked_workspace_bytes(i64 m, i64 n, i64 elem_bytes) {
 //   far A(o)  on the caller's    : outer block o applied to the columns of outer block o+1
 //   far B(o)  on the caller's    : ... and to everything right of it, concurrently with chain(o+1)
 template <class T>
-int geqr_blocked_dev(T* dA, i64 m, i64 n, i64 lda, T* dtau, i64 /*blocksize_hint*/, cudaStream_t st) {
+int geqr_blocked_dev(T* dA, i64 m, i64 n, i64 lda, T* dtau, i64 /*blocksize_hint*/, cudaStream_t st, QrHostSink<T>* sink) {
   if (m < 0) return -2;
   if (n < 0) return -3;
   if (lda < (m > 1 ? m : 1)) return -4;
@@ -1122,6 +1122,14 @@ int geqr_blocked_dev(T* dA, i64 m, i64 n, i64 lda, T* dtau, i64 /*blocksize_hint
       if (overlap) {
         if ((rc = check_cuda(cudaEventRecord(aux.ev[1], sc), __FILE__, __LINE__))) break;       // chain(o) done
         if ((rc = check_cuda(cudaStreamWaitEvent(st, aux.ev[1], 0), __FILE__, __LINE__))) break;
+        if (sink && sink->copy && sink->copied_cols == o0) {   // columns o0 .. o0 + nbo are final: start their way home
+          if ((rc = check_cuda(cudaStreamWaitEvent(sink->copy, aux.ev[1], 0), __FILE__, __LINE__))) break;
+          if ((rc = check_cuda(cudaMemcpy2DAsync(sink->hA + o0 * sink->ldh, sink->ldh * sizeof(T), dA + o0 * lda, lda * sizeof(T),
+                                                 m * sizeof(T), nbo, cudaMemcpyDeviceToHost, sink->copy),
+                               __FILE__, __LINE__)))
+            break;
+          sink->copied_cols = o0 + nbo;
+        }
       }
       // ---- far update of outer block o: Gram once, then the next outer block's columns first
       if ((rc = gram<T>(w, 1, w.V[b], w.ldv, mo, kbig, w.G[b], NBO, st))) break;
@@ -1375,7 +1383,7 @@ int reflector_apply_right_dev(T* dA, i64 m, i64 n, i64 lda, const T* dx, T tau, 
 }
 
 #define INST(T)                                                                                             \
-  template int geqr_blocked_dev<T>(T*, i64, i64, i64, T*, i64, cudaStream_t);                               \
+  template int geqr_blocked_dev<T>(T*, i64, i64, i64, T*, i64, cudaStream_t, QrHostSink<T>*);                               \
   template int ormqr_blocked_dev<T>(const T*, i64, i64, i64, const T*, T*, i64, i64, i64, int, cudaStream_t); \
   template int orgqr_thin_dev<T>(const T*, i64, i64, i64, const T*, T*, i64, cudaStream_t);                        \
   template int larft_dev<T>(const T*, i64, i64, i64, const T*, T*, i64, cudaStream_t);                      \
