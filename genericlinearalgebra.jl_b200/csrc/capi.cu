@@ -117,6 +117,44 @@ int geqr_batched_host(T* A, i64 m, i64 n, i64 batch, T* tau) {
 
 // ------------------------------------------------------------------ device copy of a host matrix
 // ld is padded to an even number of elements (16-byte column alignment for TMA / vector access)
+// Lower-trapezoid transfers for the Hermitian entry points (only the lower triangle is read and written by the reference,
+// src/cholesky.jl:37-55, src/ldlt.jl:80-103): block columns of TRI_BC columns, rows from the block's first row down --
+// 1/2 + TRI_BC/(2n) of the square instead of all of it, in both directions.
+constexpr i64 TRI_BC = 256;
+template <class T>
+int h2d_lower(T* d, i64 ldd, const T* h, i64 ldh, i64 n, cudaStream_t st) {
+  for (i64 j = 0; j < n; j += TRI_BC) {
+    const i64 nc = n - j < TRI_BC ? n - j : TRI_BC;
+    GLA_TRY(h2d_matrix<T>(d + j + j * ldd, ldd, h + j + j * ldh, ldh, n - j, nc, st));
+  }
+  return 0;
+}
+template <class T>
+int d2h_lower(T* h, i64 ldh, const T* d, i64 ldd, i64 n, cudaStream_t st) {
+  for (i64 j = 0; j < n; j += TRI_BC) {
+    const i64 nc = n - j < TRI_BC ? n - j : TRI_BC;
+    GLA_TRY(d2h_matrix<T>(h + j + j * ldh, ldh, d + j + j * ldd, ldd, n - j, nc, st));
+  }
+  return 0;
+}
+
+template <class T>
+int h2d_upper(T* d, i64 ldd, const T* h, i64 ldh, i64 n, cudaStream_t st) {
+  for (i64 j = 0; j < n; j += TRI_BC) {
+    const i64 nc = n - j < TRI_BC ? n - j : TRI_BC;
+    GLA_TRY(h2d_matrix<T>(d + j * ldd, ldd, h + j * ldh, ldh, j + nc, nc, st));
+  }
+  return 0;
+}
+template <class T>
+int d2h_upper(T* h, i64 ldh, const T* d, i64 ldd, i64 n, cudaStream_t st) {
+  for (i64 j = 0; j < n; j += TRI_BC) {
+    const i64 nc = n - j < TRI_BC ? n - j : TRI_BC;
+    GLA_TRY(d2h_matrix<T>(h + j * ldh, ldh, d + j * ldd, ldd, j + nc, nc, st));
+  }
+  return 0;
+}
+
 template <class T>
 struct DevMatrix {
   DevBuf buf;
@@ -282,7 +320,9 @@ int potrf_host(T* A, i64 n, i64 lda, i64 cutoff) {
   GLA_TRY(st.create());
   DevMatrix<T> dA;
   DevBuf dinfo;
-  GLA_TRY(dA.upload(A, lda, n, n, st.s));
+  dA.ld = round_up(n, 16 / sizeof(T) > 2 ? 16 / sizeof(T) : 2);
+  GLA_TRY(dA.buf.alloc((size_t)dA.ld * n * sizeof(T), st.s));
+  GLA_TRY(h2d_lower<T>(dA.p(), dA.ld, A, lda, n, st.s));   // the strict upper triangle is neither read nor written on the device
   GLA_TRY(dinfo.alloc(sizeof(int), st.s));
   Event e0, e1;
   GLA_TRY(e0.create());
@@ -298,7 +338,7 @@ int potrf_host(T* A, i64 n, i64 lda, i64 cutoff) {
   g_last_ms = ms;
   // like the reference (DomainError out of sqrt at src/cholesky.jl:40 with A partially overwritten), a failed call
   // still returns the partially factorised lower triangle; the index of the minor goes out of band (gla_last_info)
-  GLA_TRY(dA.download(A, lda, n, n, st.s));
+  GLA_TRY(d2h_lower<T>(A, lda, dA.p(), dA.ld, n, st.s));
   GLA_CUDA(cudaStreamSynchronize(st.s));
   if (info != 0) {
     g_last_info = info;
@@ -319,12 +359,16 @@ int ldlt_host(T* A, i64 n, i64 lda, int uplo, i64 blocksize) {
   GLA_TRY(st.create());
   DevMatrix<T> dA;
   DevBuf dinfo;
-  GLA_TRY(dA.upload(A, lda, n, n, st.s));
+  dA.ld = round_up(n, 16 / sizeof(T) > 2 ? 16 / sizeof(T) : 2);
+  GLA_TRY(dA.buf.alloc((size_t)dA.ld * n * sizeof(T), st.s));
+  if (uplo == 'U') GLA_TRY(h2d_upper<T>(dA.p(), dA.ld, A, lda, n, st.s));   // only the `uplo` triangle is referenced
+  else GLA_TRY(h2d_lower<T>(dA.p(), dA.ld, A, lda, n, st.s));
   GLA_TRY(dinfo.alloc(sizeof(int), st.s));
   GLA_TRY(ldlt_dev<T>(dA.p(), n, dA.ld, uplo == 'U', dinfo.as<int>(), st.s));
   int info = 0;
   GLA_CUDA(cudaMemcpyAsync(&info, dinfo.p, sizeof(int), cudaMemcpyDeviceToHost, st.s));
-  GLA_TRY(dA.download(A, lda, n, n, st.s));
+  if (uplo == 'U') GLA_TRY(d2h_upper<T>(A, lda, dA.p(), dA.ld, n, st.s));
+  else GLA_TRY(d2h_lower<T>(A, lda, dA.p(), dA.ld, n, st.s));
   GLA_CUDA(cudaStreamSynchronize(st.s));
   if (info != 0) {
     g_last_info = info;
