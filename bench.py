@@ -705,6 +705,21 @@ def other_configs(g, torch, dist, dev, rank, world, stream, cpu=False):
                                                "unit": "TFLOP/s", "frac": tf / (FP64_TENSOR_PEAK_TFLOPS * world),
                                                "hbm_frac": m_total * n * 8 / (ms * 1e-3) / 1e9 / (_peaks()[0] * world)},
                                   "collective": "ncclAllGather of 64x64 R factors inside gla_dtsqr_allreduce_dev" if world > 1 else "none"}
+    if world == 1:
+        # end to end through the host-pointer entry point gla_dtsqr on a pinned host matrix (4.3 GB): the call streams 2^20-row
+        # chunks (H2D under the reduction of the previous chunk), so this is the upload rate of the box
+        hA = torch.empty((n, rows), dtype=torch.float64, pin_memory=True)
+        hA.copy_(A)
+        torch.cuda.synchronize()
+        e2e = 1e30
+        for _ in range(2):
+            t0 = time.perf_counter()
+            Rh = g.tsqr_R(hA.numpy().T)
+            e2e = min(e2e, (time.perf_counter() - t0) * 1e3)
+        out["tsqr_f64_8388608x64"]["e2e_ms"] = e2e
+        out["tsqr_f64_8388608x64"]["e2e_host_gb_per_s"] = m_total * n * 8 / (e2e * 1e-3) / 1e9
+        out["tsqr_f64_8388608x64"]["e2e_gram_check"] = float(np.max(np.abs(Rh.T @ Rh - G.cpu().numpy())) / G.abs().amax().item())
+        del hA
     if oracle is not None and world == 1:
         # oracle on a leading row block is not comparable (R depends on all rows); compare |R| of a 2^16-row problem instead
         mm = 1 << 16

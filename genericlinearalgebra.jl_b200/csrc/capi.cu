@@ -469,11 +469,46 @@ int tsqr_host(const double* A, i64 m, i64 n, i64 lda, double* R, i64 ldr) {
   if (n == 0) return 0;
   Stream st;
   GLA_TRY(st.create());
-  DevMatrix<double> dA, dR;
-  GLA_TRY(dA.upload(A, lda, m, n, st.s));
+  DevMatrix<double> dR;
   dR.ld = n;
   GLA_TRY(dR.buf.alloc((size_t)n * n * sizeof(double), st.s));
-  GLA_TRY(tsqr_local_dev(dA.p(), m, n, dA.ld, dR.p(), n, st.s));
+  // TSQR streams: row chunks of 2^20 rows go through a three-deep ring (H2D of chunk i+1 / i+2 under the reduction of chunk
+  // i, which is ~6x shorter than its upload), every chunk leaves an n x n R in a stack, the stack is reduced at the end.  End
+  // to end = the upload; 1.5 GB of device memory instead of the whole matrix.
+  constexpr i64 CH = 1 << 20;
+  if (m <= CH + CH / 2) {
+    DevMatrix<double> dA;
+    GLA_TRY(dA.upload(A, lda, m, n, st.s));
+    GLA_TRY(tsqr_local_dev(dA.p(), m, n, dA.ld, dR.p(), n, st.s));
+  } else {
+    constexpr int NS = 3;
+    const i64 nch = (m + CH - 1) / CH;
+    Stream ss[NS];
+    DevBuf buf[NS], stack;
+    Event done_ev[NS];
+    GLA_TRY(stack.alloc((size_t)nch * n * n * sizeof(double), st.s));
+    GLA_CUDA(cudaStreamSynchronize(st.s));   // the stack exists before the chunk streams write into it
+    for (int i = 0; i < NS; ++i) {
+      GLA_TRY(ss[i].create());
+      GLA_TRY(buf[i].alloc((size_t)CH * n * sizeof(double), ss[i].s));
+      GLA_TRY(done_ev[i].create());
+    }
+    for (i64 c = 0; c < nch; ++c) {
+      const int i = (int)(c % NS);
+      const i64 r0 = c * CH, rows = (m - r0 < CH) ? m - r0 : CH;
+      GLA_TRY(h2d_matrix<double>(buf[i].as<double>(), CH, A + r0, lda, rows, n, ss[i].s));
+      GLA_TRY(tsqr_local_dev(buf[i].as<double>(), rows, n, CH, stack.as<double>() + c * n * n, n, ss[i].s));
+    }
+    for (int i = 0; i < NS; ++i) {
+      GLA_CUDA(cudaEventRecord(done_ev[i].e, ss[i].s));
+      GLA_CUDA(cudaStreamWaitEvent(st.s, done_ev[i].e, 0));
+    }
+    GLA_TRY(tsqr_combine_dev(stack.as<double>(), nch, n, dR.p(), n, st.s));
+    GLA_TRY(dR.download(R, ldr, n, n, st.s));
+    GLA_CUDA(cudaStreamSynchronize(st.s));
+    for (int i = 0; i < NS; ++i) GLA_CUDA(cudaStreamSynchronize(ss[i].s));
+    return 0;
+  }
   GLA_TRY(dR.download(R, ldr, n, n, st.s));
   GLA_CUDA(cudaStreamSynchronize(st.s));
   return 0;

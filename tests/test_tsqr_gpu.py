@@ -32,6 +32,19 @@ def test_tsqr_matches_oracle_up_to_row_signs(gla, oracle, m, n):
     assert np.max(np.abs(R.T @ R - G)) <= 1e-12 * np.max(np.abs(G)) * max(1, m // 1000)
 
 
+def test_tsqr_host_path_streams_row_chunks(gla, oracle):
+    """m > 1.5 * 2^20 rows: the host-pointer entry point pipelines 2^20-row chunks (upload / reduce / stack of R factors /
+    final fold) instead of uploading the whole matrix; 3,500,003 x 16 has a ragged last chunk and uses every ring slot."""
+    m, n = 3500003, 16
+    rng = np.random.default_rng(17)
+    A = np.asfortranarray(rng.standard_normal((m, n)))
+    R = gla.tsqr_R(A)
+    assert np.array_equal(np.tril(R, -1), np.zeros((n, n)))
+    ref_f, _ = oracle.qr_blocked(A, 12)
+    a, b = _normalise(R), _normalise(np.triu(ref_f)[:n])
+    assert np.max(np.abs(a - b)) <= 1e-10 * np.max(np.abs(b))
+
+
 def test_tsqr_sharded_combine(gla, oracle):
     """The multi-GPU path on one device: 4 row shards -> local R -> stacked combine == single-shot R."""
     import torch
