@@ -17,8 +17,10 @@
 //                     its transpose VcT, the K-contiguous operands of the trailing contractions.
 //   gemm_tn (x3)      G = Vc^H Vc (split-K), W = Vc^H A2 (split-K), A2 -= Vc (T^H W): FP64 tensor
 //                     pipe fed by TMA (gemm.cu)
-//   larft_finish      T = (I + diag(tau) striu(G))^-1 diag(tau) in one CTA (shared memory)
-//   apply_t           W2 = T^H * sum(split-K partials of W)
+//   larft_finish      T = (I + diag(tau) striu(G))^-1 diag(tau) in one CTA (shared memory, recursive doubling)
+//   qr_panel_cluster_kernel   panels of <= 2048 rows: one thread-block cluster, the per-column exchange through
+//                     distributed shared memory instead of L2
+// Q application and thin Q (ormqr_blocked_dev, orgqr_thin_dev) reuse the same outer-block machinery in both directions.
 #include "gemm.cuh"
 #include "gla_internal.cuh"
 #include "smallqr.cuh"
