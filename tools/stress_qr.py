@@ -1,5 +1,5 @@
 """Determinism / race stress: the blocked QR is deterministic by construction, so repeated factorisations of the
-same input must be BITWISE equal.  python tools/stress_qr.py dtype n reps   (dtype: d | z)"""
+same input must be BITWISE equal.  python tools/stress_qr.py dtype n reps [noise]   (dtype: d | z | s; s = Float32 on tcgen05)"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -8,8 +8,8 @@ import __graft_entry__ as ge
 g = ge.load()
 kind = sys.argv[1]; n = int(sys.argv[2]); reps = int(sys.argv[3])
 noise_mode = sys.argv[4] if len(sys.argv) > 4 else "none"     # none | normal | high: unrelated kernels on another stream
-dt = torch.complex128 if kind == "z" else torch.float64
-npdt = np.complex128 if kind == "z" else np.float64
+dt = {"z": torch.complex128, "s": torch.float32}.get(kind, torch.float64)
+npdt = {"z": np.complex128, "s": np.float32}.get(kind, np.float64)
 st = torch.cuda.current_stream().cuda_stream
 src = torch.randn((n, n), device="cuda", dtype=dt)
 dtau = torch.zeros(n, device="cuda", dtype=dt)
