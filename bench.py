@@ -576,8 +576,21 @@ def other_configs(g, torch, dist, dev, rank, world, stream, cpu=False):
             dA.copy_(src)
             ms, _ = _time(torch, lambda: g.qr_blocked_dev(dA.data_ptr(), n, n, n, stau.data_ptr(), 0, stream, np.float32), reps=1)
             best = min(best, ms)
-        out["qr_f32_n16384"] = {"ms": best, "tflops": 4.0 / 3.0 * n ** 3 / (best * 1e-3) / 1e12, "unit": "TFLOP/s (Float32)",
-                                "contraction": "TMA-fed 3xTF32 mma.sync (HMMA.1688.F32.TF32) with per-slab accumulators"}
+        tf32 = 4.0 / 3.0 * n ** 3 / (best * 1e-3) / 1e12
+        bf16_peak = None
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                bf16_peak = float(json.load(f).get("bf16_tflops_sustained", 0.0)) or None
+        except OSError:
+            pass
+        out["qr_f32_n16384"] = {"ms": best, "tflops": tf32, "unit": "TFLOP/s (Float32)",
+                                "contraction": "tcgen05.mma kind::tf32 (UTCHMMA), TMA-fed, TMEM accumulators, 3xTF32 split with "
+                                               "per-slab rounded accumulation; products with a dimension < 128 on the mma.sync kernel"}
+        if bf16_peak:
+            # 3xTF32 costs three TF32 MMAs per product and TF32 runs at half the dense bf16 rate
+            peak32 = bf16_peak / 6.0
+            out["qr_f32_n16384"]["roofline"] = {"bound": "tensor", "achieved": tf32, "peak": peak32, "unit": "TFLOP/s", "frac": tf32 / peak32,
+                                                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 rate) / 3 (3xTF32)"}
         if oracle is not None:
             out["qr_f32_n16384"]["oracle_leading_panel"] = _panel_check(np, torch, oracle, (dA, stau), src, 128, False)
         del src, dA, stau
