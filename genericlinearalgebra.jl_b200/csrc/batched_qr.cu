@@ -13,7 +13,8 @@
 //    sharing without lock step), pivot column loaded once per step.  GLA_BATCHED_VARIANT=1 selects the round-1 form (pivot
 //    column re-read by the axpy sweep) for A/B runs.  Earlier generations and the round-2 four-matrices-per-warp experiment
 //    live in tools/retired/ and are not part of the library.
-//  * batched_qr_smem_kernel<T>: any (m,n) whose matrix fits in shared memory, one CTA per matrix (also ComplexF64).
+//  * batched_qr_warp_kernel<T>: n <= 32, m <= 64 (any element type, e.g. ComplexF64 32 x 32): one WARP per matrix, eight per CTA.
+//  * batched_qr_smem_kernel<T>: any other (m,n) whose matrix fits in shared memory, one CTA per matrix.
 // What bounds the 32x32 kernel: DESIGN.md section 8 (operand bandwidth of the FP64 pipe: a DFMA with three distinct
 // register-pair operands issues every 3.5 cycles per SM sub-partition, tools/fp64_pattern.cu).
 #include "common.cuh"
@@ -371,6 +372,35 @@ __global__ void __launch_bounds__(SMALLQR_THREADS)
   }
 }
 
+// ====================================================================================== generic small shapes, one WARP per matrix
+// n <= 32 and a matrix of at most WQ_MAX_BYTES: WQ warps per CTA, each with its own matrix in its own slice of shared
+// memory (leading dimension padded so that the lanes' columns start in different banks); grid-stride over the batch.
+constexpr int WQ_WARPS = 8;
+constexpr int WQ_MAX_BYTES = 24 * 1024;
+template <class T>
+__global__ void __launch_bounds__(WQ_WARPS * 32) batched_qr_warp_kernel(T* __restrict__ A, T* __restrict__ tau, int m, int n, int ld,
+                                                                        i64 batch) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  T* sA = reinterpret_cast<T*>(smem_raw) + (size_t)warp * ld * n;
+  const int k = m < n ? m : n;
+  for (i64 mat = (i64)blockIdx.x * WQ_WARPS + warp; mat < batch; mat += (i64)gridDim.x * WQ_WARPS) {
+    T* Ag = A + mat * (i64)m * n;
+    for (int e = lane; e < m * n; e += 32) {   // coalesced along the rows of the column-major matrix
+      const int c = e / m, r = e - c * m;
+      sA[c * ld + r] = Ag[e];
+    }
+    __syncwarp();
+    warp_qr_smem<T>(sA, m, n, ld, tau + mat * k);
+    __syncwarp();
+    for (int e = lane; e < m * n; e += 32) {
+      const int c = e / m, r = e - c * m;
+      Ag[e] = sA[c * ld + r];
+    }
+    __syncwarp();
+  }
+}
+
 // ====================================================================================== launchers
 template <class T>
 struct IsReal {
@@ -405,6 +435,26 @@ int geqr_batched_dev(T* dA, i64 m, i64 n, i64 batch, T* dtau, cudaStream_t st) {
     // (an offset view) goes through the generic shared-memory kernel below, which only uses element accesses
     if (m == 32 && n == 32 && (reinterpret_cast<uintptr_t>(dA) & 15) == 0 && (reinterpret_cast<uintptr_t>(dtau) & 15) == 0)
       return launch_reg32<T>(dA, dtau, batch, st);
+  }
+  {
+    // small shapes: a warp per matrix (GLA_BATCHED_NO_WARP=1: one CTA per matrix as in round 1, for A/B)
+    static const bool no_warp = getenv("GLA_BATCHED_NO_WARP") != nullptr;
+    // odd leading dimension in 16-byte units: the 32 lanes' columns start in different bank groups
+    int ld = (int)m;
+    const int unit = 16 / (int)sizeof(T) > 1 ? 16 / (int)sizeof(T) : 1;
+    ld = (int)round_up(ld, unit);
+    if (((ld / unit) & 1) == 0) ld += unit;
+    const size_t bytes = (size_t)ld * n * sizeof(T);
+    if (!no_warp && n <= 32 && m <= 64 && bytes <= (size_t)WQ_MAX_BYTES) {
+      auto kern = batched_qr_warp_kernel<T>;
+      const size_t smem = bytes * WQ_WARPS;
+      GLA_TRY(ensure_dyn_smem(reinterpret_cast<const void*>(kern), (int)smem));
+      const i64 ctas = (batch + WQ_WARPS - 1) / WQ_WARPS;
+      const i64 grid = ctas < (i64)sm_count() * 8 ? ctas : (i64)sm_count() * 8;
+      kern<<<(unsigned)grid, WQ_WARPS * 32, smem, st>>>(dA, dtau, (int)m, (int)n, ld, batch);
+      GLA_CUDA(cudaGetLastError());
+      return 0;
+    }
   }
   size_t smem = (size_t)m * n * sizeof(T);
   if (smem > 96 * 1024) return -2;

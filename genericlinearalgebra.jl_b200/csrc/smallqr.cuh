@@ -160,4 +160,74 @@ __device__ void cta_qr_smem(T* sA, int m, int n, int ld, T* tau) {
   __syncthreads();
 }
 
+// The same factorisation by ONE WARP on a matrix in (warp-private) shared memory: lane = column, so the dots of a step
+// run over the rows inside each lane (no shuffle reduction per column, no block barrier); only the pivot column's norm is
+// a warp reduction.  For the small batched shapes (n <= 32 columns per pass, any element type): eight independent
+// matrices per CTA instead of one CTA per matrix.  Same arithmetic order per entry as cta_qr_smem except for the dots
+// (serial over the rows here, a butterfly over 32 partial sums there).
+template <class T>
+__device__ void warp_qr_smem(T* sA, int m, int n, int ld, T* tau) {
+  using R = typename Sc<T>::real;
+  const int lane = threadIdx.x & 31;
+  const int kmax = m < n ? m : n;
+  for (int k = 0; k < kmax; ++k) {
+    T* ck = sA + k * ld;
+    R part = R(0);
+    for (int i = k + 1 + lane; i < m; i += 32) part += abs2(ck[i]);
+    part = warp_sum(part);
+    const T alpha = ck[k];
+    R n2 = abs2(alpha) + part;
+    R up = R(1);
+    if (!(n2 >= SafeRange<R>::lo() && n2 <= SafeRange<R>::hi())) {   // scaled norm, as in cta_qr_smem
+      R amax = absmax_part(alpha);
+      for (int i = k + 1 + lane; i < m; i += 32) amax = fmax(amax, absmax_part(ck[i]));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+      if (amax > R(0) && amax <= SafeRange<R>::fmax()) {
+        int e;
+        (void)frexp(amax, &e);
+        const R sc = ldexp(R(1), -e);
+        up = ldexp(R(1), e);
+        R p2 = R(0);
+        for (int i = k + 1 + lane; i < m; i += 32) p2 += abs2(scale_real(ck[i], sc));
+        p2 = warp_sum(p2);
+        n2 = abs2(scale_real(alpha, sc)) + p2;
+      }
+    }
+    ReflScalars<T> rs = reflector_scalars<T>(up == R(1) ? alpha : scale_real(alpha, R(1) / up), n2);
+    if (up != R(1)) {
+      rs.nu *= up;
+      rs.ixi = scale_real(rs.ixi, R(1) / up);
+    }
+    if (tau && lane == 0) tau[k] = rs.tau;
+    if (rs.nonzero) {
+      const T ctau = cj(rs.tau);
+      const R isup = R(1) / up;
+      const T cixi = cj(up == R(1) ? rs.ixi : scale_real(rs.ixi, up));
+      for (int c = k + 1 + lane; c < n; c += 32) {
+        T* cc = sA + c * ld;
+        T d0 = Sc<T>::zero(), d1 = Sc<T>::zero();
+        int i = k + 1;
+        if (up == R(1)) {
+          for (; i + 1 < m; i += 2) {
+            d0 = fmad(cj(ck[i]), cc[i], d0);
+            d1 = fmad(cj(ck[i + 1]), cc[i + 1], d1);
+          }
+          if (i < m) d0 = fmad(cj(ck[i]), cc[i], d0);
+        } else {
+          for (; i < m; ++i) d0 = fmad(cj(scale_real(ck[i], isup)), cc[i], d0);
+        }
+        const T s = ctau * (cc[k] + cixi * (d0 + d1));
+        const T t = s * rs.ixi;
+        for (i = k + 1; i < m; ++i) cc[i] = cc[i] - ck[i] * t;
+        cc[k] = cc[k] - s;
+      }
+      __syncwarp();   // every lane has used the un-normalised pivot column
+      for (int i = k + 1 + lane; i < m; i += 32) ck[i] = ck[i] * rs.ixi;
+      if (lane == 0) ck[k] = Sc<T>::from_real(-rs.nu);
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace gla
