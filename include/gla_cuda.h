@@ -123,8 +123,9 @@ GLA_API int gla_zreflector_apply_right_dev(void* dA, int64_t m, int64_t n, int64
  * `batch` independent qrBlocked! problems (src/qr.jl:113-146 per matrix); matrices are
  * contiguous, column-major, stride m*n elements; tau has stride min(m,n).
  * 32x32 real runs register-resident, two matrices per warp (the device stack must be
- * 16-byte aligned for this path; an unaligned stack silently takes the next one); other
- * shapes with m*n*sizeof(T) <= 96 KiB run one matrix per CTA in shared memory. */
+ * 16-byte aligned for this path; an unaligned stack silently takes the next one); shapes
+ * with n <= 32, m <= 64 (any element type, e.g. ComplexF64 32x32) run one matrix per WARP,
+ * eight per CTA, in shared memory; other shapes with m*n*sizeof(T) <= 96 KiB one per CTA. */
 GLA_API int gla_sgeqr_batched(float* A, int64_t m, int64_t n, int64_t batch, float* tau);
 GLA_API int gla_dgeqr_batched(double* A, int64_t m, int64_t n, int64_t batch, double* tau);
 GLA_API int gla_zgeqr_batched(void* A, int64_t m, int64_t n, int64_t batch, void* tau);
