@@ -467,7 +467,54 @@ struct ClusterPanelSmem {   // fixed part; the slab follows
   T xbuf[2][CL_MAX][2 * NB];   // [parity][source rank][dots | pivot-row entries]
   T part[CP_RG][NB];           // partial dots of the row groups
   T tot[2 * NB];               // reduced dots | pivot row
+  unsigned long long xbar[2];  // one transaction barrier per parity: the exchange of a column is complete when the
+                               // 2 x NB entries of every rank have landed in xbuf[parity]
 };
+
+// st.async: a store into the shared memory of a CTA of the cluster that completes `sizeof(T)` bytes on a transaction
+// barrier of THAT CTA.  The receiver waits on its own barrier: one one-way trip instead of the all-to-all
+// barrier.cluster round (clock64 trace: 1000 - 1250 of the 4600 cycles of a column went into cluster.sync()).
+__device__ __forceinline__ unsigned cl_smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned cl_mapa(unsigned addr, unsigned rank) {
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cl_st_async(unsigned dst, float v, unsigned bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(dst),
+               "r"(__float_as_uint(v)), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void cl_st_async(unsigned dst, double v, unsigned bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(dst),
+               "l"(__double_as_longlong(v)), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void cl_st_async(unsigned dst, zd v, unsigned bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];" ::"r"(dst),
+               "l"(__double_as_longlong(v.x)), "l"(__double_as_longlong(v.y)), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void cl_bar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void cl_bar_expect(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool cl_bar_wait(unsigned bar, unsigned parity) {   // false: watchdog expired
+  for (unsigned spins = 0; spins < (1u << 20); ++spins) {
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return true;
+  }
+  return false;
+}
 
 template <class T>
 __global__ void __launch_bounds__(CP_THREADS, 1) qr_panel_cluster_kernel(PanelArgs<T> a) {
@@ -491,9 +538,17 @@ __global__ void __launch_bounds__(CP_THREADS, 1) qr_panel_cluster_kernel(PanelAr
     const int col = e / rows, i = e - col * rows;
     S[i * CP_LD + col] = ldcg_t(a.A + (i64)col * a.lda + r0 + i);
   }
-  // every CTA of the cluster must be running before anybody writes into its shared memory (compute-sanitizer:
-  // "address located in a block that might not have entered yet"); the barrier also orders the slab loads
+  const unsigned xbar0 = cl_smem_addr(&sm.xbar[0]), xbar1 = cl_smem_addr(&sm.xbar[1]);
+  if (tid == 0) {
+    cl_bar_init(xbar0, 1);
+    cl_bar_init(xbar1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // every CTA of the cluster must be running (and its barriers initialised) before anybody writes into its shared
+  // memory (compute-sanitizer: "address located in a block that might not have entered yet"); the barrier also orders
+  // the slab loads
   cluster.sync();
+  const unsigned xbytes = (unsigned)(CL * 2 * NB * sizeof(T));
 
   T pend_ixi = Sc<T>::one();   // deferred finish of the previous pivot column (rows below the diagonal *= 1/xi, diagonal <- -nu)
   R pend_nu = R(0);
@@ -530,20 +585,24 @@ __global__ void __launch_bounds__(CP_THREADS, 1) qr_panel_cluster_kernel(PanelAr
       d = (d + d1) + (d2 + d3);
     }
     sm.part[rg][c] = d;
+    // the exchange of column j uses barrier `par` for the (j / 2)-th time.  No CTA can be two columns ahead: its stores
+    // of column j + 2 come after its wait of column j + 1, which needs this CTA's stores of column j + 1, which come
+    // after this CTA's reads of column j -- so two parities are enough for the buffers and for the barrier phases.
+    if (tid == 0) cl_bar_expect(par ? xbar1 : xbar0, xbytes);
     __syncthreads();
-    if (tid < NB) {
-      T dsum = sm.part[0][c];
-#pragma unroll
-      for (int g2 = 1; g2 < CP_RG; ++g2) dsum = dsum + sm.part[g2][c];
-      const T rowj = (j >= r0 && j < r1 && c < nb) ? S[(j - r0) * CP_LD + c] : Sc<T>::zero();
-      for (int r = 0; r < CL; ++r) {   // same slot of every CTA's exchange buffer (distributed shared memory)
-        T* dst = cluster.map_shared_rank(&sm.xbuf[par][rank][0], r);
-        dst[c] = dsum;
-        dst[NB + c] = rowj;
-      }
-    }
-    cluster.sync();
     if (tid < 2 * NB) {
+      T val;
+      if (tid < NB) {   // warps 0-1: the dots of this CTA; warps 2-3: its pivot-row entries
+        val = sm.part[0][c];
+#pragma unroll
+        for (int g2 = 1; g2 < CP_RG; ++g2) val = val + sm.part[g2][c];
+      } else {
+        val = (j >= r0 && j < r1 && c < nb) ? S[(j - r0) * CP_LD + c] : Sc<T>::zero();
+      }
+      const unsigned slot = cl_smem_addr(&sm.xbuf[par][rank][tid]), bar = par ? xbar1 : xbar0;
+      for (int r = 0; r < CL; ++r)   // same slot of every CTA's exchange buffer (distributed shared memory)
+        cl_st_async(cl_mapa(slot, (unsigned)r), val, cl_mapa(bar, (unsigned)r));
+      if (!cl_bar_wait(bar, (unsigned)((j >> 1) & 1))) __trap();
       T t = sm.xbuf[par][0][tid];
       for (int r = 1; r < CL; ++r) t = t + sm.xbuf[par][r][tid];
       sm.tot[tid] = t;
@@ -622,17 +681,29 @@ __global__ void __launch_bounds__(256) larft_finish_kernel(const T* __restrict__
   Row* Pk = X + NB;
   T* st = reinterpret_cast<T*>(Pk + NB);
   const int tid = threadIdx.x;
+  // this kernel sits on the panel chain of every QR: all loads of a thread (its 16 entries of G, one tau) are issued
+  // before the first use -- one L2 round trip instead of seventeen dependent ones
+  constexpr int PER = NB * NB / 256;
+  T gv[PER];
+#pragma unroll
+  for (int q = 0; q < PER; ++q) {
+    const int e = tid + q * 256, j = e / NB, i = e - j * NB;
+    gv[q] = (i < j && j < kk) ? ldcg_t(Gp + (i64)j * kk + i) : Sc<T>::zero();
+  }
   if (tid < kk) st[tid] = ldcg_t(tau + tid);
-  __syncthreads();
-  for (int e = tid; e < NB * NB; e += blockDim.x) {   // identity padding beyond kk
-    const int j = e / NB, i = e - j * NB;
-    T g = Sc<T>::zero();
-    if (i < j && j < kk) {
-      g = ldcg_t(Gp + (i64)j * kk + i);
-      for (int z = 1; z < nsplit; ++z) g = g + ldcg_t(Gp + (i64)z * gstride + (i64)j * kk + i);
-      g = st[i] * g;
+  if (nsplit > 1) {
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const int e = tid + q * 256, j = e / NB, i = e - j * NB;
+      if (i < j && j < kk)
+        for (int z = 1; z < nsplit; ++z) gv[q] = gv[q] + ldcg_t(Gp + (i64)z * gstride + (i64)j * kk + i);
     }
-    U[i][j] = g;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < PER; ++q) {   // identity padding beyond kk
+    const int e = tid + q * 256, j = e / NB, i = e - j * NB;
+    U[i][j] = (i < j && j < kk) ? st[i] * gv[q] : Sc<T>::zero();
     X[i][j] = (i == j) ? Sc<T>::one() : Sc<T>::zero();
   }
   __syncthreads();
@@ -812,7 +883,8 @@ static int launch_panel(T* A, i64 lda, i64 mk, int nb, T* tau, QrWork<T>& w, int
     const i64 rows_max = slab_cap / ((i64)CP_LD * sizeof(T)) / 4 * 4;
     // measured (profiles/r02_qr_panel_cluster.txt): n = 1024 5.74 -> 4.30 ms, n = 2048 11.5 -> 10.4 ms, n = 4096 equal; beyond
     // 256 rows per CTA the rank-1 update of the whole slab per column costs more than the sub-panel form of qr_panel_kernel
-    const i64 rows_use = rows_max < 256 ? rows_max : 256;
+    static const i64 rows_cap = [] { const char* e = getenv("GLA_PANEL_CLUSTER_ROWS"); return e ? (i64)atoi(e) : (i64)320; }();
+    const i64 rows_use = rows_max < rows_cap ? rows_max : rows_cap;
     if (!no_cluster && mk <= CL_MAX * rows_use) {
       int CL = (int)((mk + 63) / 64);
       if (CL > CL_MAX) CL = CL_MAX;
