@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) qr_panel_cluster_kernel(PanelAr
     // the exchange of column j uses barrier `par` for the (j / 2)-th time.  No CTA can be two columns ahead: its stores
     // of column j + 2 come after its wait of column j + 1, which needs this CTA's stores of column j + 1, which come
     // after this CTA's reads of column j -- so two parities are enough for the buffers and for the barrier phases.
-    if (tid == 0) cl_bar_expect(par ? xbar1 : xbar0, xbytes);
+    if (tid == 0 && CL > 1) cl_bar_expect(par ? xbar1 : xbar0, xbytes);
     __syncthreads();
     if (tid < 2 * NB) {
       T val;
@@ -599,13 +599,15 @@ __global__ void __launch_bounds__(CP_THREADS, 1) qr_panel_cluster_kernel(PanelAr
       } else {
         val = (j >= r0 && j < r1 && c < nb) ? S[(j - r0) * CP_LD + c] : Sc<T>::zero();
       }
-      const unsigned slot = cl_smem_addr(&sm.xbuf[par][rank][tid]), bar = par ? xbar1 : xbar0;
-      for (int r = 0; r < CL; ++r)   // same slot of every CTA's exchange buffer (distributed shared memory)
-        cl_st_async(cl_mapa(slot, (unsigned)r), val, cl_mapa(bar, (unsigned)r));
-      if (!cl_bar_wait(bar, (unsigned)((j >> 1) & 1))) __trap();
-      T t = sm.xbuf[par][0][tid];
-      for (int r = 1; r < CL; ++r) t = t + sm.xbuf[par][r][tid];
-      sm.tot[tid] = t;
+      if (CL > 1) {
+        const unsigned slot = cl_smem_addr(&sm.xbuf[par][rank][tid]), bar = par ? xbar1 : xbar0;
+        for (int r = 0; r < CL; ++r)   // same slot of every CTA's exchange buffer (distributed shared memory)
+          cl_st_async(cl_mapa(slot, (unsigned)r), val, cl_mapa(bar, (unsigned)r));
+        if (!cl_bar_wait(bar, (unsigned)((j >> 1) & 1))) __trap();
+        val = sm.xbuf[par][0][tid];
+        for (int r = 1; r < CL; ++r) val = val + sm.xbuf[par][r][tid];
+      }
+      sm.tot[tid] = val;   // (a panel of one CTA has nothing to exchange)
     }
     __syncthreads();
     const T alpha = sm.tot[NB + j];

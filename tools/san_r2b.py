@@ -1,5 +1,6 @@
 """Small problems through the kernels added late in round 2 (tcgen05 Float32 contraction, two-sided reductions,
-per-warp TSQR) for compute-sanitizer memcheck / racecheck / synccheck."""
+per-warp TSQR, the st.async exchange of the cluster panel kernel, the warp-per-matrix batched kernel) for
+compute-sanitizer memcheck / racecheck / synccheck."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -39,4 +40,20 @@ if which in ("all", "tsqr"):
     R = g.tsqr_R(A)
     G = A.T @ A
     assert np.abs(R.T @ R - G).max() / np.abs(G).max() < 1e-12
+if which in ("all", "cluster"):
+    # cluster panel kernel (st.async exchange on transaction barriers): 1 ... 8 CTAs per cluster, ragged last slab
+    for dt, shapes in ((np.float64, ((70, 70), (300, 130), (1000, 200))), (np.complex128, ((260, 100),)), (np.float32, ((520, 70),))):
+        for (m, n) in shapes:
+            A = rng.standard_normal((m, n)).astype(dt)
+            if dt == np.complex128:
+                A = A + 1j * rng.standard_normal((m, n))
+            qr = g.qrBlocked_(np.asfortranarray(A))
+            R = np.triu(qr.factors[:n, :]).astype(np.complex128 if dt == np.complex128 else np.float64)
+            A64 = A.astype(R.dtype)
+            G = A64.conj().T @ A64
+            assert np.abs(R.conj().T @ R - G).max() / np.abs(G).max() < (1e-4 if dt == np.float32 else 1e-12)
+if which in ("all", "batched"):
+    for dt in (np.complex128, np.float64):
+        A = rng.standard_normal((37, 24, 20)).astype(dt)   # 37 matrices 24 x 20, each stored column-major
+        g.qr_batched_(np.array(np.transpose(A, (0, 2, 1)), order="C", copy=True))
 print("san ok")
