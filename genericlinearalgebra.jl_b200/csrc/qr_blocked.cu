@@ -18,8 +18,9 @@
 //   gemm_tn (x3)      G = Vc^H Vc (split-K), W = Vc^H A2 (split-K), A2 -= Vc (T^H W): FP64 tensor
 //                     pipe fed by TMA (gemm.cu)
 //   larft_finish      T = (I + diag(tau) striu(G))^-1 diag(tau) in one CTA (shared memory, recursive doubling)
-//   qr_panel_cluster_kernel   panels of <= 2048 rows: one thread-block cluster, the per-column exchange through
-//                     distributed shared memory instead of L2
+//   qr_panel_cluster_kernel   panels of <= 5120 rows: one thread-block cluster of up to 16 CTAs, the per-column
+//                     exchange through distributed shared memory (st.async onto the receiver's transaction barrier)
+//                     instead of L2
 // Q application and thin Q (ormqr_blocked_dev, orgqr_thin_dev) reuse the same outer-block machinery in both directions.
 #include "gemm.cuh"
 #include "gla_internal.cuh"
@@ -447,17 +448,18 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) qr_panel_kernel(PanelArgs<T>
 }
 
 // ------------------------------------------------------------------------------- K1c: cluster panel kernel
-// Panels of at most 8 x ROWS rows (3072 in Float64): ONE thread-block cluster, CTA r holds rows [r*ROWS, ...) of the
-// panel in shared memory (row-major, padded), and the per-column exchange goes through DISTRIBUTED SHARED MEMORY
-// instead of L2: every CTA writes its 2 x 64 partials (dots of the un-normalised pivot column with every column, and
-// its contribution to pivot row j) into the same slot of every CTA's exchange buffer, one barrier.cluster per column,
-// every CTA sums the slots in rank order (bitwise identical scalars everywhere, deterministic).  The L2 flag exchange of
-// qr_panel_kernel costs ~7000 cycles per column at m = 1024 (profiles/r02_ncu_qr_panel_n1024.txt: long_scoreboard on the
-// spinning loads + four CTA barriers); this one ~1500.  Plain right-looking steps (no 16-column sub-panels): at
-// <= 384 rows per CTA the rank-1 update of the whole slab is cheaper than the bookkeeping of the blocked form.
+// Panels of at most 16 x 320 rows: ONE thread-block cluster, CTA r holds rows [r*ROWS, ...) of the panel in shared
+// memory (row-major, padded), and the per-column exchange goes through DISTRIBUTED SHARED MEMORY instead of L2: every
+// CTA sends its 2 x 64 partials (dots of the un-normalised pivot column with every column, and its contribution to
+// pivot row j) into the same slot of every CTA's exchange buffer with st.async, which completes the bytes on a
+// transaction barrier of the receiver; every CTA waits on its own barrier and sums the slots in rank order (bitwise
+// identical scalars everywhere, deterministic).  The L2 flag exchange of qr_panel_kernel costs ~4000 cycles per column;
+// remote stores + barrier.cluster (the first version of this kernel) 1000 - 1250; this one a one-way trip.  Plain
+// right-looking steps (no 16-column sub-panels): at <= 320 rows per CTA the rank-1 update of the whole slab is cheaper
+// than the bookkeeping of the blocked form.
 // Semantics: qrUnblocked! (src/qr.jl:86-111) with stdlib reflector! / reflectorApply! (call sites :96, :102), then the
 // clean reflector block Vc (unit diagonal, zeros above) and its transpose VcT like qr_panel_kernel.
-constexpr int CL_MAX = 8;              // portable cluster size
+constexpr int CL_MAX = 16;             // largest cluster (8 is the portable size; 16 needs the non-portable opt-in, see launch_panel)
 constexpr int CP_THREADS = 512;
 constexpr int CP_RG = CP_THREADS / NB;   // row groups: thread (c, rg) owns rows rg, rg + CP_RG, ... of column c
 constexpr int CP_LD = NB + 1;          // padded row of the slab
@@ -887,9 +889,40 @@ static int launch_panel(T* A, i64 lda, i64 mk, int nb, T* tau, QrWork<T>& w, int
     // 256 rows per CTA the rank-1 update of the whole slab per column costs more than the sub-panel form of qr_panel_kernel
     static const i64 rows_cap = [] { const char* e = getenv("GLA_PANEL_CLUSTER_ROWS"); return e ? (i64)atoi(e) : (i64)320; }();
     const i64 rows_use = rows_max < rows_cap ? rows_max : rows_cap;
-    if (!no_cluster && mk <= CL_MAX * rows_use) {
+    auto kern = qr_panel_cluster_kernel<T>;
+    // clusters of 16 CTAs (one GPC holds them): opt-in, and only if the occupancy query says such a cluster can be resident
+    static const int cl_max = [&]() -> int {
+      const char* e = getenv("GLA_PANEL_CLUSTER_MAX");
+      int want = e ? atoi(e) : 16;
+      if (want > CL_MAX) want = CL_MAX;
+      if (want <= 8) return want < 1 ? 1 : want;
+      if (ensure_dyn_smem((const void*)kern, (int)(sizeof(ClusterPanelSmem<T>) + slab_cap))) return 8;
+      if (cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        cudaGetLastError();
+        return 8;
+      }
+      cudaLaunchConfig_t q;
+      memset(&q, 0, sizeof(q));
+      q.gridDim = dim3((unsigned)want);
+      q.blockDim = dim3(CP_THREADS);
+      q.dynamicSmemBytes = sizeof(ClusterPanelSmem<T>) + (size_t)slab_cap;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = (unsigned)want;
+      qa[0].val.clusterDim.y = 1;
+      qa[0].val.clusterDim.z = 1;
+      q.attrs = qa;
+      q.numAttrs = 1;
+      int nclusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&nclusters, (const void*)kern, &q) != cudaSuccess || nclusters < 1) {
+        cudaGetLastError();
+        return 8;
+      }
+      return want;
+    }();
+    if (!no_cluster && mk <= cl_max * rows_use) {
       int CL = (int)((mk + 63) / 64);
-      if (CL > CL_MAX) CL = CL_MAX;
+      if (CL > cl_max) CL = cl_max;
       if (CL < 1) CL = 1;
       const i64 rows_per = round_up((mk + CL - 1) / CL, 4);
       CL = (int)((mk + rows_per - 1) / rows_per);
@@ -897,7 +930,6 @@ static int launch_panel(T* A, i64 lda, i64 mk, int nb, T* tau, QrWork<T>& w, int
       a.resident = 1;
       a.lds = CP_LD;
       const size_t smem = sizeof(ClusterPanelSmem<T>) + (size_t)rows_per * CP_LD * sizeof(T);
-      auto kern = qr_panel_cluster_kernel<T>;
       GLA_TRY(ensure_dyn_smem((const void*)kern, (int)(sizeof(ClusterPanelSmem<T>) + slab_cap)));
       cudaLaunchConfig_t cfg;
       memset(&cfg, 0, sizeof(cfg));
