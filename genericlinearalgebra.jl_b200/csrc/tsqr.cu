@@ -263,20 +263,24 @@ __global__ void __launch_bounds__(NWARPS * 32, 2)
 // need ~250 registers) hide each other's scalar chains.  The next chunk is pulled into L2 by prefetch instructions while
 // the current one is reduced; its loads are 16-byte vector loads straight into the registers.  Measured: 10.2 ms against
 // 11.0 ms for the CTA-per-chunk kernel at 8,388,608 x 64 (a column step still costs ~2000 cycles of latency per warp).
-constexpr int TW_WARPS = 8;    // two warps per sub-partition = 255 registers: the 128 payload registers + the temporaries of a step do not fit the 168 of three
+// For n <= 32 half of the payload registers are dead: 24-row chunks and twelve warps per SM there (tw_config below).
+// two configurations: 8 warps x 32-row chunks (two warps per sub-partition, 255 registers: 128 payload registers + the
+// temporaries of a step) and 12 warps x 24-row chunks (three per sub-partition, 168 registers, 96 of them payload).
+constexpr int TW_WARPS = 8;
+constexpr int TW_WARPS_24 = 12;
 constexpr int TW_RPACK = 64 * 65 / 2;             // packed upper triangle of a 64 x 64 R
 constexpr int TW_WARP_DOUBLES = TW_RPACK + 32;    // + the published pivot column
-constexpr size_t TW_SMEM = (size_t)TW_WARPS * TW_WARP_DOUBLES * sizeof(double);
+constexpr size_t tw_smem(int nw) { return (size_t)nw * TW_WARP_DOUBLES * sizeof(double); }
 
 __device__ __forceinline__ int tw_row(int k) { return k * 64 - (k * (k - 1)) / 2 - k; }   // R(k, c) at tw_row(k) + c, c >= k
 
-template <bool TWO, int H>
-__device__ __forceinline__ void tw_step(double (&a0)[32], double (&a1)[32], const int kl, const int lane,
+template <bool TWO, int H, int RW>
+__device__ __forceinline__ void tw_step(double (&a0)[RW], double (&a1)[RW], const int kl, const int lane,
                                         double* __restrict__ sR, double* __restrict__ pubw) {
   const int k = 32 * H + kl;
   if (lane == kl) {
 #pragma unroll
-    for (int r = 0; r < 32; r += 2)
+    for (int r = 0; r < RW; r += 2)
       *reinterpret_cast<double2*>(pubw + r) = H == 0 ? make_double2(a0[r], a0[r + 1]) : make_double2(a1[r], a1[r + 1]);
   }
   __syncwarp();
@@ -289,7 +293,7 @@ __device__ __forceinline__ void tw_step(double (&a0)[32], double (&a1)[32], cons
   // the 128 payload registers would not fit the 168-register budget of twelve warps per SM
   double p0[4] = {0., 0., 0., 0.}, p1[4] = {0., 0., 0., 0.};
 #pragma unroll
-  for (int r = 0; r < 32; r += 4) {
+  for (int r = 0; r < RW; r += 4) {
     const double2 xa = *reinterpret_cast<const double2*>(pubw + r);
     const double2 xb = *reinterpret_cast<const double2*>(pubw + r + 2);
     if (H == 0) {
@@ -353,7 +357,7 @@ __device__ __forceinline__ void tw_step(double (&a0)[32], double (&a1)[32], cons
       if (own1) rk[32 + lane] = right ? top1 - s : -nu;
     }
 #pragma unroll
-    for (int r = 0; r < 32; r += 2) {
+    for (int r = 0; r < RW; r += 2) {
       const double2 xa = *reinterpret_cast<const double2*>(pubw + r);
       if (H == 0) {
         a0[r] = fma(t0, xa.x, a0[r]);
@@ -368,8 +372,8 @@ __device__ __forceinline__ void tw_step(double (&a0)[32], double (&a1)[32], cons
   __syncwarp();  // every lane has read the published column before the next owner overwrites it
 }
 
-template <bool TWO>
-__global__ void __launch_bounds__(TW_WARPS * 32, 1)
+template <bool TWO, int RW, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
     tsqr_warp_kernel(const double* __restrict__ A, const i64 lda, const i64 m, const int n, const i64 rows_per_warp,
                      double* __restrict__ Rout, const i64 ldro, const i64 out_row_step, const int vec_ok) {
   extern __shared__ __align__(16) double tw_smem[];
@@ -378,7 +382,7 @@ __global__ void __launch_bounds__(TW_WARPS * 32, 1)
   double* pubw = sR + TW_RPACK;
   for (int e = lane; e < TW_RPACK; e += 32) sR[e] = 0.0;
   __syncwarp();
-  const i64 gw = (i64)blockIdx.x * TW_WARPS + warp;
+  const i64 gw = (i64)blockIdx.x * NW + warp;
   const i64 row_begin = gw * rows_per_warp;
   i64 row_end = row_begin + rows_per_warp;
   if (row_end > m) row_end = m;
@@ -387,41 +391,41 @@ __global__ void __launch_bounds__(TW_WARPS * 32, 1)
   const double* col1 = A + (i64)(c1ok ? lane + 32 : 0) * lda;
   const int k0max = n < 32 ? n : 32;
   const int k1max = n - 32;
-  for (i64 row0 = row_begin; row0 < row_end; row0 += 32) {
-    double a0[32], a1[32];
-    const bool full = row0 + 32 <= row_end;
+  for (i64 row0 = row_begin; row0 < row_end; row0 += RW) {
+    double a0[RW], a1[RW];
+    const bool full = row0 + RW <= row_end;
     if (full && vec_ok) {
 #pragma unroll
-      for (int r = 0; r < 32; r += 2) {
+      for (int r = 0; r < RW; r += 2) {
         const double2 v = c0ok ? *reinterpret_cast<const double2*>(col0 + row0 + r) : make_double2(0., 0.);
         a0[r] = v.x;
         a0[r + 1] = v.y;
       }
 #pragma unroll
-      for (int r = 0; r < 32; r += 2) {
+      for (int r = 0; r < RW; r += 2) {
         const double2 v = c1ok ? *reinterpret_cast<const double2*>(col1 + row0 + r) : make_double2(0., 0.);
         a1[r] = v.x;
         a1[r + 1] = v.y;
       }
     } else {
 #pragma unroll
-      for (int r = 0; r < 32; ++r) {
+      for (int r = 0; r < RW; ++r) {
         const bool rok = row0 + r < row_end;
         a0[r] = (rok && c0ok) ? col0[row0 + r] : 0.0;
         a1[r] = (rok && c1ok) ? col1[row0 + r] : 0.0;
       }
     }
-    if (row0 + 32 < row_end) {   // pull the next chunk of this lane's two columns (256 B each) into L2
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(col0 + row0 + 32));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(col0 + row0 + 48));
+    if (row0 + RW < row_end) {   // pull the next chunk of this lane's two columns (8 * RW bytes each) into L2
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(col0 + row0 + RW));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(col0 + row0 + RW + 16));
       if (TWO) {
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(col1 + row0 + 32));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(col1 + row0 + 48));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(col1 + row0 + RW));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(col1 + row0 + RW + 16));
       }
     }
-    for (int kl = 0; kl < k0max; ++kl) tw_step<TWO, 0>(a0, a1, kl, lane, sR, pubw);
+    for (int kl = 0; kl < k0max; ++kl) tw_step<TWO, 0, RW>(a0, a1, kl, lane, sR, pubw);
     if (TWO)
-      for (int kl = 0; kl < k1max; ++kl) tw_step<TWO, 1>(a0, a1, kl, lane, sR, pubw);
+      for (int kl = 0; kl < k1max; ++kl) tw_step<TWO, 1, RW>(a0, a1, kl, lane, sR, pubw);
   }
   __syncwarp();
   double* out = Rout + gw * out_row_step;
@@ -463,6 +467,37 @@ static int launch_stream(const TsqrSrc& src, i64 m, int n, i64 rows_per_cta, i64
   return launch_stream_cfg<TS_WARPS, TS_RW>(src, m, n, rows_per_cta, grid, out, ldro, out_row_step, st);
 }
 
+// rows per chunk of the per-warp level 0: 32 (8 warps per SM) for n > 32, 24 (12 warps) for n <= 32.  Measured at
+// 8,388,608 rows: n = 64 10.23 ms with 32 rows against 10.66 ms with 24 (the FP64 pipe, at the 2.9 cycles per DFMA of
+// these operand patterns, is what bounds it: a third warp per sub-partition only adds scalar chains); n = 32 4.34 against
+// 3.99 ms (half the payload registers are dead there, the third warp is free).  GLA_TSQR_WARP_ROWS = 24 | 32 forces one.
+static int tw_config(int n) {
+  static const int forced = [] {
+    const char* e = getenv("GLA_TSQR_WARP_ROWS");
+    const int v = e ? atoi(e) : 0;
+    return (v == 24 || v == 32) ? v : 0;
+  }();
+  return forced ? forced : (n > 32 ? 32 : 24);
+}
+
+template <bool TWO, int RW, int NW>
+static int launch_warp_cfg(const TsqrSrc& src, i64 m, int n, i64 rows_per_warp, double* wbuf, i64 tall, int vec_ok,
+                           cudaStream_t st) {
+  auto kern = tsqr_warp_kernel<TWO, RW, NW>;
+  GLA_TRY(ensure_dyn_smem((const void*)kern, (int)tw_smem(NW)));
+  kern<<<(unsigned)sm_count(), NW * 32, tw_smem(NW), st>>>(src.p, src.ld, m, n, rows_per_warp, wbuf, tall, n, vec_ok);
+  return check_cuda(cudaGetLastError(), __FILE__, __LINE__);
+}
+
+static int launch_warp(const TsqrSrc& src, i64 m, int n, i64 rows_per_warp, double* wbuf, i64 tall, int vec_ok,
+                       cudaStream_t st) {
+  if (tw_config(n) == 32)
+    return n > 32 ? launch_warp_cfg<true, 32, TW_WARPS>(src, m, n, rows_per_warp, wbuf, tall, vec_ok, st)
+                  : launch_warp_cfg<false, 32, TW_WARPS>(src, m, n, rows_per_warp, wbuf, tall, vec_ok, st);
+  return n > 32 ? launch_warp_cfg<true, 24, TW_WARPS_24>(src, m, n, rows_per_warp, wbuf, tall, vec_ok, st)
+                : launch_warp_cfg<false, 24, TW_WARPS_24>(src, m, n, rows_per_warp, wbuf, tall, vec_ok, st);
+}
+
 // src (m rows) -> dR (n x n, ldr).  Level 0 uses one CTA per SM; the stacked per-CTA R factors (a tall
 // (grid*n) x n matrix) are reduced by the same kernel, one chunk per CTA, until a single CTA remains.
 static int run_reduction(TsqrSrc src, i64 m, int n, double* dR, i64 ldr, cudaStream_t st) {
@@ -474,26 +509,19 @@ static int run_reduction(TsqrSrc src, i64 m, int n, double* dR, i64 ldr, cudaStr
   double* wbuf = nullptr;
   // level 0 of a long plain column-major range: one chain per warp (tsqr_warp_kernel), 12 x #SM R factors out
   static const bool no_warp = getenv("GLA_TSQR_NO_WARP") != nullptr;   // A/B switch
-  const i64 nwarps = (i64)sm_count() * TW_WARPS;
+  const int tw_rows = tw_config(n);
+  const i64 nwarps = (i64)sm_count() * (tw_rows == 32 ? TW_WARPS : TW_WARPS_24);
   // (worth it from ~1500 rows per warp on: below that the extra tree level over its 8 x #SM R factors costs more than the
   //  level-0 gain -- 8-GPU shards of the 8,388,608-row config: 1.92 ms with it, 1.86 ms without)
-  if (!no_warp && src.bstride == 0 && src.blk_rows >= m && m >= nwarps * 1536) {
-    const i64 rows_per_warp = round_up((m + nwarps - 1) / nwarps, 32);
+  if (!no_warp && src.bstride == 0 && src.blk_rows >= m && m >= (i64)sm_count() * TW_WARPS * 1536) {
+    const i64 rows_per_warp = round_up((m + nwarps - 1) / nwarps, tw_rows);
     const i64 used = (m + rows_per_warp - 1) / rows_per_warp;        // warps that own rows (the others write a zero R)
     const i64 tall = nwarps * n;
     rc = pool_malloc(reinterpret_cast<void**>(&wbuf), (size_t)tall * n * sizeof(double), st);
     if (!rc) {
       const int vec_ok = ((reinterpret_cast<uintptr_t>(src.p) & 15) == 0 && (src.ld & 1) == 0) ? 1 : 0;
       (void)used;
-      if (n > 32) {
-        auto kern = tsqr_warp_kernel<true>;
-        rc = ensure_dyn_smem((const void*)kern, (int)TW_SMEM);
-        if (!rc) kern<<<(unsigned)sm_count(), TW_WARPS * 32, TW_SMEM, st>>>(src.p, src.ld, m, n, rows_per_warp, wbuf, tall, n, vec_ok);
-      } else {
-        auto kern = tsqr_warp_kernel<false>;
-        rc = ensure_dyn_smem((const void*)kern, (int)TW_SMEM);
-        if (!rc) kern<<<(unsigned)sm_count(), TW_WARPS * 32, TW_SMEM, st>>>(src.p, src.ld, m, n, rows_per_warp, wbuf, tall, n, vec_ok);
-      }
+      rc = launch_warp(src, m, n, rows_per_warp, wbuf, tall, vec_ok, st);
       if (!rc) rc = check_cuda(cudaGetLastError(), __FILE__, __LINE__);
       src = TsqrSrc{wbuf, tall, tall, 0};
       m = tall;
