@@ -1,6 +1,6 @@
 """Per-kernel counts of the SASS mnemonics that prove the data path of lib/libgla_cuda.so:
 TMA = UTMALDG, tcgen05 = UTCHMMA / UTCBAR / UTCATOMSWS / LDTM, FP64 tensor pipe = DMMA, TF32 mma.sync = HMMA,
-cp.async = LDGSTS, mbarrier = SYNCS, cluster barrier = UCGABAR.   usage: python tools/sass_excerpt.py > profiles/...txt"""
+cp.async = LDGSTS, mbarrier = SYNCS, st.async to a peer CTA = STAS, cluster barrier = UCGABAR.   usage: python tools/sass_excerpt.py > profiles/...txt"""
 import collections
 import os
 import re
@@ -8,7 +8,7 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "genericlinearalgebra.jl_b200", "lib", "libgla_cuda.so")
-PAT = re.compile(r"\b(UTCHMMA|UTCBAR|UTCATOMSWS|LDTM|UTMALDG|UTMACCTL|DMMA|HMMA|LDGSTS|SYNCS|UCGABAR_ARV|UCGABAR_WAIT|DFMA|FFMA)(\.[A-Z0-9_.]+)?")
+PAT = re.compile(r"\b(UTCHMMA|UTCBAR|UTCATOMSWS|LDTM|UTMALDG|UTMACCTL|DMMA|HMMA|LDGSTS|SYNCS|STAS|UCGABAR_ARV|UCGABAR_WAIT|DFMA|FFMA)(\.[A-Z0-9_.]+)?")
 sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
 names = {}
 per = collections.OrderedDict()
@@ -28,7 +28,7 @@ for line in sass.splitlines():
 dem = subprocess.run(["c++filt"], input="\n".join(per), capture_output=True, text=True).stdout.splitlines()
 print("# cuobjdump -sass genericlinearalgebra.jl_b200/lib/libgla_cuda.so: per-kernel counts of the mnemonics that prove the data path")
 print("# (tcgen05 = UTCHMMA / UTCBAR / UTCATOMSWS / LDTM, TMA = UTMALDG, FP64 tensor pipe = DMMA.8x8x4, TF32 mma.sync = HMMA.1688,")
-print("#  cp.async = LDGSTS, mbarrier = SYNCS, cluster barrier = UCGABAR); kernels without any of them are omitted\n")
+print("#  cp.async = LDGSTS, mbarrier = SYNCS, st.async into a peer CTA of the cluster = STAS, cluster barrier = UCGABAR); kernels without any of them are omitted\n")
 tot = collections.Counter()
 for (fn, c), d in zip(per.items(), dem):
     tc = {k: v for k, v in c.items() if k not in ("DFMA", "FFMA")}
