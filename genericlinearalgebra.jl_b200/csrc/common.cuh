@@ -165,12 +165,13 @@ inline i64 round_up(i64 a, i64 b) { return (a + b - 1) / b * b; }
 int sm_count();  // of the current device (cached)
 // stream-ordered allocation from the library-owned pool of the current device; release with cudaFreeAsync
 int pool_malloc(void** p, size_t bytes, cudaStream_t st);
-// High-priority side stream + four timing-free events for the look-ahead schedules (blocked QR, Cholesky), created once
+// High-priority side streams + six timing-free events for the look-ahead schedules (blocked QR, Cholesky), created once
 // per (host thread, device) and reused by every call: work is stream-ordered, so consecutive asynchronous calls of one
 // thread may share them.  Released when the thread exits.
 struct AuxCtx {
   cudaStream_t hi = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t hi2 = nullptr;   // second high-priority stream: the T build of a QR panel beside the W product (qr_blocked.cu)
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 int aux_ctx(AuxCtx** out);
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel, size): the launch paths are host-bound for

@@ -81,6 +81,7 @@ struct AuxCache {
       for (auto& e : kv.second.ev)
         if (e) cudaEventDestroy(e);
       if (kv.second.hi) cudaStreamDestroy(kv.second.hi);
+      if (kv.second.hi2) cudaStreamDestroy(kv.second.hi2);
     }
   }
 };
@@ -95,6 +96,7 @@ int aux_ctx(AuxCtx** out) {
     int lo = 0, hi = 0;
     GLA_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     GLA_CUDA(cudaStreamCreateWithPriority(&a.hi, cudaStreamNonBlocking, hi));
+    GLA_CUDA(cudaStreamCreateWithPriority(&a.hi2, cudaStreamNonBlocking, hi));
     for (auto& e : a.ev) GLA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
   *out = &a;

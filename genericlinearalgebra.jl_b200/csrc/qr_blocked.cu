@@ -863,9 +863,22 @@ __global__ void zero_top_kernel(T* __restrict__ V, i64 ldv, T* __restrict__ VT, 
   }
 }
 
+// the same for every panel of an outer block of nbo columns at once (one launch per outer block, off the panel chain)
+template <class T>
+__global__ void zero_top_block_kernel(T* __restrict__ V, i64 ldv, T* __restrict__ VT, int nbo) {
+  const int total = nbo * nbo;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int col = e / nbo, i = e - col * nbo;
+    if (i < (col / NB) * NB) {
+      V[(i64)col * ldv + i] = Sc<T>::zero();
+      VT[(i64)i * NBO + col] = Sc<T>::zero();
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------- panel launch
 template <class T>
-static int launch_panel(T* A, i64 lda, i64 mk, int nb, T* tau, QrWork<T>& w, int j, cudaStream_t st) {
+static int launch_panel(T* A, i64 lda, i64 mk, int nb, T* tau, QrWork<T>& w, int j, cudaStream_t st, bool zero_top = true) {
   PanelArgs<T> a;
   a.A = A;
   a.lda = lda;
@@ -945,7 +958,7 @@ static int launch_panel(T* A, i64 lda, i64 mk, int nb, T* tau, QrWork<T>& w, int
       cfg.attrs = attr;
       cfg.numAttrs = 1;
       GLA_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
-      if (j > 0) {
+      if (j > 0 && zero_top) {
         const int kk = (int)(mk < nb ? mk : nb);
         zero_top_kernel<T><<<ceil_div((i64)j * NB * kk, 256), 256, 0, st>>>(w.V[w.cur], w.ldv, w.VT[w.cur], j * NB, kk);
         GLA_CUDA(cudaGetLastError());
@@ -982,7 +995,7 @@ static int launch_panel(T* A, i64 lda, i64 mk, int nb, T* tau, QrWork<T>& w, int
     kern<<<1, PANEL_THREADS, smem, st>>>(a);
     GLA_CUDA(cudaGetLastError());
   }
-  if (j > 0) {
+  if (j > 0 && zero_top) {
     const int kk = (int)(mk < nb ? mk : nb);
     zero_top_kernel<T><<<ceil_div((i64)j * NB * kk, 256), 256, 0, st>>>(w.V[w.cur], w.ldv, w.VT[w.cur], j * NB, kk);
     GLA_CUDA(cudaGetLastError());
@@ -1026,7 +1039,7 @@ static int wsplit_for(i64 kk, i64 nA, i64 mk) {
 // A2 (mk x nA, lda) <- (I - Vc op(T) Vc^H) A2 for ONE panel (kk <= NB reflectors); path 0 scratch
 template <class T>
 static int apply_panel(QrWork<T>& w, const T* Vc, i64 ldvc, const T* VcT, i64 ldvct, const T* Tj, i64 mk, int kk,
-                       T* A2, i64 lda, i64 nA, int adjoint, cudaStream_t st) {
+                       T* A2, i64 lda, i64 nA, int adjoint, cudaStream_t st, cudaEvent_t t_ready = nullptr) {
   if (nA <= 0) return 0;
   GemmTN<T> g1;
   g1.At = Vc; g1.ldat = ldvc;
@@ -1050,6 +1063,7 @@ static int apply_panel(QrWork<T>& w, const T* Vc, i64 ldvc, const T* VcT, i64 ld
   // Z = T_j^H (sum of the split-K slices of W): T_j (column-major, zeros below the diagonal) is the K-contiguous
   // operand of the TN contraction as it stands
   if (g1.nsplit > 1) GLA_TRY(sum_splits<T>(w.Wp[0], NB, w.Wp[0], NB, g1.split_stride, g1.nsplit, kk, nA, st));
+  if (t_ready) GLA_CUDA(cudaStreamWaitEvent(st, t_ready, 0));   // T_j was built on another stream meanwhile
   {
     GemmTN<T> gz;
     gz.At = Tj; gz.ldat = NB;
@@ -1128,14 +1142,19 @@ static int apply_outer(QrWork<T>& w, int b, i64 mo, int kbig, T* A2, i64 lda, i6
 
 // ------------------------------------------------------------------------------- drivers
 namespace {
-struct AuxStream {  // high-priority side stream + the events of the look-ahead schedule (cached per thread and device)
+struct AuxStream {  // high-priority side streams + the events of the look-ahead schedule (cached per thread and device)
   cudaStream_t s = nullptr;
+  cudaStream_t s2 = nullptr;                              // T build of a panel, beside the W product of its application
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_panel = nullptr, ev_t = nullptr;         // panel factored (fork), T ready (join)
   int create() {
     AuxCtx* a = nullptr;
     GLA_TRY(aux_ctx(&a));
     s = a->hi;
+    s2 = a->hi2;
     for (int i = 0; i < 3; ++i) ev[i] = a->ev[i];
+    ev_panel = a->ev[4];
+    ev_t = a->ev[5];
     return 0;
   }
 };
@@ -1181,8 +1200,13 @@ int geqr_blocked_dev(T* dA, i64 m, i64 n, i64 lda, T* dtau, i64 /*blocksize_hint
   AuxStream aux;
   cudaStream_t sc = st;  // chain stream
   int rc = 0;
+  // T fork: the Gram + larft_finish launches that build T_j do not depend on W = V_j^H A2 -- they run on a second
+  // high-priority stream beside the W product and its split-K sum, and the chain waits for T_j right before Z = T_j^H W
+  // (three launches off the critical path of every panel).  GLA_QR_NO_TFORK=1: everything on the chain stream.
+  static const bool no_tfork = getenv("GLA_QR_NO_TFORK") != nullptr;
+  const bool tfork = !no_tfork && n > NB && m > NB;
+  if (overlap || tfork) rc = aux.create();
   if (overlap) {
-    rc = aux.create();
     if (!rc) rc = check_cuda(cudaEventRecord(aux.ev[0], st), __FILE__, __LINE__);      // workspace ready
     if (!rc) rc = check_cuda(cudaStreamWaitEvent(aux.s, aux.ev[0], 0), __FILE__, __LINE__);
     sc = aux.s;
@@ -1196,6 +1220,16 @@ int geqr_blocked_dev(T* dA, i64 m, i64 n, i64 lda, T* dtau, i64 /*blocksize_hint
     w.cur = b;
     int kbig = 0;
     // ---- chain(o)
+    // zeros above the diagonal blocks of V / VT for the whole outer block: one launch on the second side stream (the
+    // panel kernels write only rows at and below their diagonal block; the first forked T build of the block follows it
+    // on that stream, so the chain -- and through it the far update -- is ordered after it)
+    const bool zero_ahead = tfork && nbo > NB && mo > NB;
+    if (zero_ahead) {
+      if ((rc = check_cuda(cudaEventRecord(aux.ev_panel, sc), __FILE__, __LINE__))) break;   // V[b] is free from here on
+      if ((rc = check_cuda(cudaStreamWaitEvent(aux.s2, aux.ev_panel, 0), __FILE__, __LINE__))) break;
+      zero_top_block_kernel<T><<<ceil_div((i64)nbo * nbo, 256), 256, 0, aux.s2>>>(w.V[b], w.ldv, w.VT[b], nbo);
+      if ((rc = check_cuda(cudaGetLastError(), __FILE__, __LINE__))) break;
+    }
     for (int j = 0; j * NB < nbo; ++j) {
       const i64 k0 = o0 + (i64)j * NB;
       const i64 mk = m - k0;
@@ -1206,15 +1240,25 @@ int geqr_blocked_dev(T* dA, i64 m, i64 n, i64 lda, T* dtau, i64 /*blocksize_hint
       const int nb = (int)(n - k0 < NB ? n - k0 : NB);
       const int kk = (int)(mk < nb ? mk : nb);
       T* Ak = dA + k0 + k0 * lda;
-      if ((rc = launch_panel<T>(Ak, lda, mk, nb, dtau + k0, w, j, sc))) break;
+      if ((rc = launch_panel<T>(Ak, lda, mk, nb, dtau + k0, w, j, sc, !zero_ahead))) break;
       kbig += kk;
       const i64 nin = (o0 + nbo) - (k0 + nb);  // remaining columns INSIDE the outer block
       const i64 nfar = n - (o0 + nbo);
+      bool t_forked = false;
       if (nin > 0 || nfar > 0) {
-        if ((rc = build_T<T>(w, w.Vj(j), w.ldv, mk, kk, dtau + k0, w.Tj(j), sc))) break;
+        if (tfork && nin > 0) {
+          if ((rc = check_cuda(cudaEventRecord(aux.ev_panel, sc), __FILE__, __LINE__))) break;
+          if ((rc = check_cuda(cudaStreamWaitEvent(aux.s2, aux.ev_panel, 0), __FILE__, __LINE__))) break;
+          if ((rc = build_T<T>(w, w.Vj(j), w.ldv, mk, kk, dtau + k0, w.Tj(j), aux.s2))) break;
+          if ((rc = check_cuda(cudaEventRecord(aux.ev_t, aux.s2), __FILE__, __LINE__))) break;
+          t_forked = true;
+        } else {
+          if ((rc = build_T<T>(w, w.Vj(j), w.ldv, mk, kk, dtau + k0, w.Tj(j), sc))) break;
+        }
       }
       if (nin > 0) {
-        if ((rc = apply_panel<T>(w, w.Vj(j), w.ldv, w.VTj(j), NBO, w.Tj(j), mk, kk, Ak + (i64)nb * lda, lda, nin, 1, sc)))
+        if ((rc = apply_panel<T>(w, w.Vj(j), w.ldv, w.VTj(j), NBO, w.Tj(j), mk, kk, Ak + (i64)nb * lda, lda, nin, 1, sc,
+                                 t_forked ? aux.ev_t : nullptr)))
           break;
       }
       if (!(mk > nb && n - k0 > nb)) {  // reference recursion stops: src/qr.jl:136
