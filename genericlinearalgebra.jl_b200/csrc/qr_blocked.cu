@@ -1086,8 +1086,12 @@ static int apply_panel(QrWork<T>& w, const T* Vc, i64 ldvc, const T* VcT, i64 ld
 // A2 (mo x nA) <- Q_{nj-1}^H ... Q_0^H A2 for the whole outer block held in buffer b (kbig reflectors, Gram
 // already in w.G[b]); path 1 scratch
 template <class T>
-static int apply_outer(QrWork<T>& w, int b, i64 mo, int kbig, T* A2, i64 lda, i64 nA, cudaStream_t st) {
-  if (nA <= 0) return 0;
+static int apply_outer(QrWork<T>& w, int b, i64 mo, int kbig, T* A2, i64 lda, i64 nA, cudaStream_t st,
+                       cudaEvent_t g_ready = nullptr) {
+  if (nA <= 0) {
+    if (g_ready) GLA_CUDA(cudaStreamWaitEvent(st, g_ready, 0));
+    return 0;
+  }
   GemmTN<T> g1;
   g1.At = w.V[b]; g1.ldat = w.ldv;
   g1.B = A2; g1.ldb = lda;
@@ -1108,6 +1112,7 @@ static int apply_outer(QrWork<T>& w, int b, i64 mo, int kbig, T* A2, i64 lda, i6
     //   G_ji = conj(G(iNB.., jNB..))^T is the K-contiguous operand G + jNB*ldg (G is Hermitian), T_j^H likewise T_j
     if (g1.nsplit > 1)   // fixed-order sum of the split-K slices, in place into slice 0
       GLA_TRY(sum_splits<T>(w.Wp[1], NBO, w.Wp[1], NBO, g1.split_stride, g1.nsplit, kbig, nA, st));
+    if (g_ready) GLA_CUDA(cudaStreamWaitEvent(st, g_ready, 0));   // the Gram of the outer block was formed on another stream meanwhile
     const int nj = (kbig + NB - 1) / NB;
     for (int j = 0; j < nj; ++j) {
       const int rows_j = (kbig - j * NB) < NB ? (kbig - j * NB) : NB;
@@ -1284,10 +1289,20 @@ int geqr_blocked_dev(T* dA, i64 m, i64 n, i64 lda, T* dtau, i64 /*blocksize_hint
         }
       }
       // ---- far update of outer block o: Gram once, then the next outer block's columns first
-      if ((rc = gram<T>(w, 1, w.V[b], w.ldv, mo, kbig, w.G[b], NBO, st))) break;
+      //      (the Gram does not depend on W = V^H A2: with the T fork it runs on the second side stream beside that product)
+      cudaEvent_t g_ready = nullptr;
+      if (tfork && kbig > NB) {
+        if ((rc = check_cuda(cudaEventRecord(aux.ev_panel, st), __FILE__, __LINE__))) break;
+        if ((rc = check_cuda(cudaStreamWaitEvent(aux.s2, aux.ev_panel, 0), __FILE__, __LINE__))) break;
+        if ((rc = gram<T>(w, 1, w.V[b], w.ldv, mo, kbig, w.G[b], NBO, aux.s2))) break;
+        if ((rc = check_cuda(cudaEventRecord(aux.ev_t, aux.s2), __FILE__, __LINE__))) break;
+        g_ready = aux.ev_t;
+      } else if ((rc = gram<T>(w, 1, w.V[b], w.ldv, mo, kbig, w.G[b], NBO, st))) {
+        break;
+      }
       T* A2 = dA + o0 + (o0 + nbo) * lda;
       const i64 nA = (overlap && !done && nfar > NBO) ? NBO : nfar;
-      if ((rc = apply_outer<T>(w, b, mo, kbig, A2, lda, nA, st))) break;
+      if ((rc = apply_outer<T>(w, b, mo, kbig, A2, lda, nA, st, g_ready))) break;
       if (overlap && !done) {
         if ((rc = check_cuda(cudaEventRecord(aux.ev[2], st), __FILE__, __LINE__))) break;       // far A(o) done
         if ((rc = check_cuda(cudaStreamWaitEvent(sc, aux.ev[2], 0), __FILE__, __LINE__))) break;
