@@ -388,6 +388,8 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(T* __restrict__ W, i64 
   const int ty = tid >> 4, tx = tid & 15;
   const int c0 = r + nb + SW * blockIdx.x;            // first column of this CTA's slice
   const int sw = min(SW, n - c0);                     // <= 0: no slice (the panel is the last one)
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh): the chain of panel kernels and urgent updates
+  pdl_wait();                // is launch-latency bound; nothing global is touched before this wait
   // ---- loads: diagonal block (registers; identity padding beyond nb), pending operands, slice
   T s[4][4];
 #pragma unroll
@@ -590,6 +592,7 @@ static bool use_panel_path() {
 
 template <class T, bool LDL = false>
 static int chol_right_looking(CholCtx<T>& cx, i64 n) {
+  PdlScope pdl(n <= 2048);   // programmatic dependent launch where the launch chain bounds the run (common.cuh)
   {
     const int smem = (int)sizeof(PanelSmem<T>);
     GLA_TRY(ensure_dyn_smem((const void*)chol_panel_kernel<T, LDL>, smem));
@@ -601,10 +604,10 @@ static int chol_right_looking(CholCtx<T>& cx, i64 n) {
       if (dbg_skip == 2) return 0;
       const i64 ncols = n - (r + nb);
       const unsigned grid = (unsigned)(ncols > 0 ? ceil_div(ncols, SW) : 1);
-      chol_panel_kernel<T, LDL><<<grid, 256, smem, cx.st>>>(cx.W, cx.ldw, (int)n, (int)r, (int)nb, (int)rp, (int)kpend,
-                                                            cx.Uinv + (r / CB) * CB * CB, cx.info, cx.Y,
-                                                            cx.Uinv + (rp / CB) * CB * CB);
-      return check_cuda(cudaGetLastError(), __FILE__, __LINE__);
+      return check_cuda(launch_pdl(chol_panel_kernel<T, LDL>, dim3(grid), dim3(256), (size_t)smem, cx.st, cx.W, cx.ldw, (int)n,
+                                   (int)r, (int)nb, (int)rp, (int)kpend, cx.Uinv + (r / CB) * CB * CB, cx.info, cx.Y,
+                                   (const T*)(cx.Uinv + (rp / CB) * CB * CB)),
+                        __FILE__, __LINE__);
     };
     // Look-ahead: the sequential chain (panel kernels + the update of the NEXT outer block's 128 rows) runs on a cached
     // high-priority stream `sc`; the bulk of every trailing update (rows beyond the next outer block) runs on the caller's

@@ -178,4 +178,39 @@ int aux_ctx(AuxCtx** out);
 // small problems (hundreds of dependent launches), so the per-launch driver call is worth avoiding
 int ensure_dyn_smem(const void* func, int bytes);
 
+// Programmatic dependent launch: a kernel launched through launch_pdl may be scheduled while its predecessor in the
+// stream is still running; it must call pdl_wait() before its first global-memory access (the wait returns when the
+// predecessor grids have completed and their writes are visible).  pdl_launch_dependents() at the top of a kernel lets
+// the NEXT kernel's launch overlap this one.  The chains of small dependent kernels (T build, split sums, small products,
+// Cholesky panels) are launch-latency bound; GLA_NO_PDL=1 switches the attribute off for A/B.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+bool pdl_enabled();
+// The attribute is only set inside a PdlScope(true) of the calling thread: the drivers open one for SMALL problems, where
+// the launch chain is what bounds the run.  Measured: blocked QR n = 1024 2.86 -> 2.72 ms, n = 2048 6.77 -> 6.54 ms, Cholesky
+// n = 2048 1.33 -> 1.24 ms -- but n = 4096 QR 16.7 -> 17.3 ms, n = 16384 238 -> 243 ms, Cholesky n = 8192 11.0 -> 12.2 ms:
+// early-scheduled CTAs of the chain wait on SM slots that the concurrent bulk update of the look-ahead schedule needs.
+struct PdlScope {
+  bool prev;
+  explicit PdlScope(bool on);
+  ~PdlScope();
+};
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 }  // namespace gla

@@ -103,6 +103,16 @@ int aux_ctx(AuxCtx** out) {
   return 0;
 }
 
+namespace {
+thread_local bool pdl_scope_on = false;
+}
+bool pdl_enabled() {
+  static const bool on = getenv("GLA_NO_PDL") == nullptr;
+  return on && pdl_scope_on;
+}
+PdlScope::PdlScope(bool on) : prev(pdl_scope_on) { pdl_scope_on = on; }
+PdlScope::~PdlScope() { pdl_scope_on = prev; }
+
 int ensure_dyn_smem(const void* func, int bytes) {
   static std::mutex mu;
   static std::map<std::pair<int, const void*>, int> done;

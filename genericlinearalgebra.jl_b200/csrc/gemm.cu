@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(DmmaCfg<BM, BN, STAGES>::THREADS, 2)
   const int nk = (kend - kbeg + 15) >> 4;
   const bool producer = threadIdx.x == 0;
 
+  pdl_launch_dependents();   // (common.cuh) the next kernel of the stream may be scheduled from here on
   if (producer) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
@@ -116,6 +117,9 @@ __global__ void __launch_bounds__(DmmaCfg<BM, BN, STAGES>::THREADS, 2)
       mbar_init(&empty[s], NCW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  pdl_wait();                // the operands and C are written by the kernels before this one
+  if (producer) {
     // prologue: fill the ring
     for (int it = 0; it < STAGES && it < nk; ++it) {
       mbar_expect_tx(&full[it], Cfg::STAGE_BYTES);
@@ -947,6 +951,8 @@ template <class T>
 __global__ void sum_splits_kernel(T* __restrict__ out, i64 ldo, const T* __restrict__ part, i64 ldp, i64 stride,
                                   int nsplit, i64 M, i64 N) {
   const i64 total = M * N;
+  pdl_launch_dependents();
+  pdl_wait();
   for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
     const i64 j = e / M, i = e - j * M;
     T s = ldcg_t(part + j * ldp + i);
@@ -1078,10 +1084,8 @@ int launch_dmma(const GemmTN<double>& g, int klen, cudaStream_t st) {
   dim3 grid((unsigned)ceil_div(g.M, BM), (unsigned)ceil_div(g.N, BN), (unsigned)g.nsplit);
   const int vec_ok = ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0 && (g.ldc & 1) == 0 &&
                       ((g.split_stride & 1) == 0)) ? 1 : 0;
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmA, tmB, g.C, g.ldc, (int)g.M, (int)g.N, (int)g.K, klen,
-                                              g.split_stride, g.alpha, g.nsplit > 1 ? 0 : g.beta_one,
-                                              g.lower_only, vec_ok);
-  GLA_CUDA(cudaGetLastError());
+  GLA_CUDA(launch_pdl(kern, grid, dim3(Cfg::THREADS), (size_t)Cfg::SMEM, st, tmA, tmB, g.C, g.ldc, (int)g.M, (int)g.N, (int)g.K,
+                      klen, g.split_stride, g.alpha, g.nsplit > 1 ? 0 : g.beta_one, g.lower_only, vec_ok));
   return 0;
 }
 
@@ -1226,8 +1230,7 @@ int sum_splits(T* out, i64 ldo, const T* part, i64 ldp, i64 stride, int nsplit, 
   if (M <= 0 || N <= 0) return 0;
   i64 total = M * N;
   int grid = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-  sum_splits_kernel<T><<<grid, 256, 0, st>>>(out, ldo, part, ldp, stride, nsplit, M, N);
-  GLA_CUDA(cudaGetLastError());
+  GLA_CUDA(launch_pdl(sum_splits_kernel<T>, dim3((unsigned)grid), dim3(256), (size_t)0, st, out, ldo, part, ldp, stride, nsplit, M, N));
   return 0;
 }
 template int sum_splits<float>(float*, i64, const float*, i64, i64, int, i64, i64, cudaStream_t);

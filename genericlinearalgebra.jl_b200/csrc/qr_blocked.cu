@@ -685,6 +685,8 @@ __global__ void __launch_bounds__(256) larft_finish_kernel(const T* __restrict__
   Row* Pk = X + NB;
   T* st = reinterpret_cast<T*>(Pk + NB);
   const int tid = threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
   // this kernel sits on the panel chain of every QR: all loads of a thread (its 16 entries of G, one tau) are issued
   // before the first use -- one L2 round trip instead of seventeen dependent ones
   constexpr int PER = NB * NB / 256;
@@ -1025,8 +1027,7 @@ static int build_T(QrWork<T>& w, const T* Vc, i64 ldvc, i64 mk, int kk, const T*
   GLA_TRY(gram<T>(w, 0, Vc, ldvc, mk, kk, w.Gs, kk, st));
   const int smem = (3 * NB * (NB + 1) + NB) * (int)sizeof(T);
   GLA_TRY(ensure_dyn_smem((const void*)larft_finish_kernel<T>, (int)(smem)));
-  larft_finish_kernel<T><<<1, 256, smem, st>>>(w.Gs, 0, 1, kk, tau, Tout, NB);
-  GLA_CUDA(cudaGetLastError());
+  GLA_CUDA(launch_pdl(larft_finish_kernel<T>, dim3(1), dim3(256), (size_t)smem, st, (const T*)w.Gs, (i64)0, 1, kk, tau, Tout, (i64)NB));
   return 0;
 }
 
@@ -1199,6 +1200,7 @@ int geqr_blocked_dev(T* dA, i64 m, i64 n, i64 lda, T* dtau, i64 /*blocksize_hint
   // was never at fault.)  GLA_QR_NO_OVERLAP=1 selects the single-stream schedule for A/B measurements.
   static const bool no_overlap = getenv("GLA_QR_NO_OVERLAP") != nullptr;
   const bool overlap = !no_overlap && n > 2 * NBO && m > 2 * NBO;   // small problems: one stream, one buffer
+  PdlScope pdl(n <= 2048);   // programmatic dependent launch of the small kernels where the launch chain bounds the run (common.cuh)
   QrWork<T> w;
   GLA_TRY(w.alloc(m, NBO, n > NBO ? n - NBO : 0, overlap ? 2 : 1, st));
   w.yield_sms = overlap ? 1 : 0;
