@@ -297,6 +297,7 @@ __global__ void __launch_bounds__(DmmaCfg<BM, BN, STAGES>::THREADS, 2)
   const int nk = (kend - kbeg + 31) >> 5;
   const bool producer = threadIdx.x == 0;
 
+  pdl_launch_dependents();
   if (producer) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
@@ -305,6 +306,9 @@ __global__ void __launch_bounds__(DmmaCfg<BM, BN, STAGES>::THREADS, 2)
       mbar_init(&empty[s], NCW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  pdl_wait();   // programmatic dependent launch (common.cuh): nothing global is touched before this point
+  if (producer) {
     for (int it = 0; it < STAGES && it < nk; ++it) {
       mbar_expect_tx(&full[it], Cfg::STAGE_BYTES);
       tma_load_2d(sA + it * BM * 128, &tmA, kbeg + it * 32, m0, &full[it]);
@@ -760,6 +764,7 @@ __global__ void __launch_bounds__(ZdmmaCfg<BM, BN, STAGES>::THREADS, 2)
   const int nk = (kend - kbeg + 15) >> 4;
   const bool producer = threadIdx.x == 0;
 
+  pdl_launch_dependents();
   if (producer) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
@@ -768,6 +773,9 @@ __global__ void __launch_bounds__(ZdmmaCfg<BM, BN, STAGES>::THREADS, 2)
       mbar_init(&empty[s], NCW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  pdl_wait();   // programmatic dependent launch (common.cuh): nothing global is touched before this point
+  if (producer) {
     for (int it = 0; it < STAGES && it < nk; ++it) {
       mbar_expect_tx(&full[it], Cfg::STAGE_BYTES);
       tma_load_2d(sA + it * BM * 128, &tmA, kbeg + it * 16, m0, &full[it]);
@@ -1018,9 +1026,8 @@ int launch_tf32x3(const GemmTN<float>& g, int klen, cudaStream_t st) {
   auto kern = gemm_tn_tf32x3_kernel<BM, BN, STAGES>;
   GLA_TRY(ensure_dyn_smem((const void*)kern, (int)(Cfg::SMEM)));
   dim3 grid((unsigned)ceil_div(g.M, BM), (unsigned)ceil_div(g.N, BN), (unsigned)g.nsplit);
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmA, tmB, g.C, g.ldc, (int)g.M, (int)g.N, (int)g.K, klen, g.split_stride,
-                                              g.alpha, g.nsplit > 1 ? 0 : g.beta_one, g.lower_only);
-  GLA_CUDA(cudaGetLastError());
+  GLA_CUDA(launch_pdl(kern, grid, dim3(Cfg::THREADS), (size_t)Cfg::SMEM, st, tmA, tmB, g.C, g.ldc, (int)g.M, (int)g.N, (int)g.K,
+                      klen, g.split_stride, g.alpha, g.nsplit > 1 ? 0 : g.beta_one, g.lower_only));
   return 0;
 }
 
@@ -1205,10 +1212,8 @@ static int launch_zdmma(const GemmTN<zd>& g, int klen, cudaStream_t st) {
   auto kern = gemm_tn_zdmma_kernel<BM, BN, STAGES>;
   GLA_TRY(ensure_dyn_smem((const void*)kern, (int)(Cfg::SMEM)));
   dim3 grid((unsigned)ceil_div(g.M, BM), (unsigned)ceil_div(g.N, BN), (unsigned)g.nsplit);
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmA, tmB, g.C, g.ldc, (int)g.M, (int)g.N, (int)(2 * g.K), 2 * klen,
-                                              g.split_stride, g.alpha, g.nsplit > 1 ? 0 : g.beta_one, g.conj_a,
-                                              g.lower_only);
-  GLA_CUDA(cudaGetLastError());
+  GLA_CUDA(launch_pdl(kern, grid, dim3(Cfg::THREADS), (size_t)Cfg::SMEM, st, tmA, tmB, g.C, g.ldc, (int)g.M, (int)g.N,
+                      (int)(2 * g.K), 2 * klen, g.split_stride, g.alpha, g.nsplit > 1 ? 0 : g.beta_one, g.conj_a, g.lower_only));
   return 0;
 }
 

@@ -535,6 +535,8 @@ __global__ void __launch_bounds__(CP_THREADS, 1) qr_panel_cluster_kernel(PanelAr
   const int nb = a.nb;
   const int kk = a.mk < nb ? a.mk : nb;
 
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh; only set up for small problems)
+  pdl_wait();
   // ---- slab in: coalesced along the rows, L2-only loads (the far update of the other stream just rewrote the panel)
   for (int e = tid; e < rows * nb; e += CP_THREADS) {
     const int col = e / rows, i = e - col * rows;
@@ -952,13 +954,15 @@ static int launch_panel(T* A, i64 lda, i64 mk, int nb, T* tau, QrWork<T>& w, int
       cfg.blockDim = dim3(CP_THREADS);
       cfg.dynamicSmemBytes = smem;
       cfg.stream = st;
-      cudaLaunchAttribute attr[1];
+      cudaLaunchAttribute attr[2];
       attr[0].id = cudaLaunchAttributeClusterDimension;
       attr[0].val.clusterDim.x = (unsigned)CL;
       attr[0].val.clusterDim.y = 1;
       attr[0].val.clusterDim.z = 1;
+      attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
       cfg.attrs = attr;
-      cfg.numAttrs = 1;
+      cfg.numAttrs = 2;
       GLA_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
       if (j > 0 && zero_top) {
         const int kk = (int)(mk < nb ? mk : nb);
