@@ -388,8 +388,7 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(T* __restrict__ W, i64 
   const int ty = tid >> 4, tx = tid & 15;
   const int c0 = r + nb + SW * blockIdx.x;            // first column of this CTA's slice
   const int sw = min(SW, n - c0);                     // <= 0: no slice (the panel is the last one)
-  pdl_launch_dependents();   // programmatic dependent launch (common.cuh): the chain of panel kernels and urgent updates
-  pdl_wait();                // is launch-latency bound; nothing global is touched before this wait
+  pdl_wait();                // programmatic dependent launch (common.cuh): nothing global is touched before this wait
   // ---- loads: diagonal block (registers; identity padding beyond nb), pending operands, slice
   T s[4][4];
 #pragma unroll
@@ -468,6 +467,7 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(T* __restrict__ W, i64 
     return;
   }
   __syncthreads();   // dinv complete
+  pdl_launch_dependents();   // only the stores are left: the next kernel of the chain may be scheduled (it waits for them)
   if (blockIdx.x == 0) {
 #pragma unroll
     for (int a = 0; a < 4; ++a)
@@ -592,7 +592,7 @@ static bool use_panel_path() {
 
 template <class T, bool LDL = false>
 static int chol_right_looking(CholCtx<T>& cx, i64 n) {
-  PdlScope pdl(n <= 2048);   // programmatic dependent launch where the launch chain bounds the run (common.cuh)
+  PdlScope pdl(true);   // programmatic dependent launch of the chain's kernels (common.cuh): n = 2048 1.33 -> 1.26 ms, n = 4096 3.13 -> 3.02 ms, n = 8192 10.9 -> 10.7 ms
   {
     const int smem = (int)sizeof(PanelSmem<T>);
     GLA_TRY(ensure_dyn_smem((const void*)chol_panel_kernel<T, LDL>, smem));

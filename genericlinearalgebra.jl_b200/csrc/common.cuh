@@ -188,10 +188,13 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #endif
 bool pdl_enabled();
-// The attribute is only set inside a PdlScope(true) of the calling thread: the drivers open one for SMALL problems, where
-// the launch chain is what bounds the run.  Measured: blocked QR n = 1024 2.86 -> 2.72 ms, n = 2048 6.77 -> 6.54 ms, Cholesky
-// n = 2048 1.33 -> 1.24 ms -- but n = 4096 QR 16.7 -> 17.3 ms, n = 16384 238 -> 243 ms, Cholesky n = 8192 11.0 -> 12.2 ms:
-// early-scheduled CTAs of the chain wait on SM slots that the concurrent bulk update of the look-ahead schedule needs.
+long long pdl_max_n();   // largest problem order the drivers open a PdlScope for (GLA_PDL_MAXN, default 2048)
+// The attribute is only set inside a PdlScope(true) of the calling thread: the Cholesky driver opens one always, the
+// blocked-QR driver for n <= GLA_PDL_MAXN (default 2048), where the launch chain is what bounds the run.  Measured: blocked
+// QR n = 1024 2.86 -> 2.69 ms, n = 2048 6.77 -> 6.49 ms (neutral from n = 4096 on), Cholesky n = 2048 1.33 -> 1.26 ms,
+// n = 4096 3.13 -> 3.02 ms.  Where the trigger sits matters: at the TOP of the kernels the early-scheduled CTAs of the chain
+// sat on SM slots that the concurrent bulk update of the look-ahead schedule needs (QR n = 16384 238 -> 243 ms, Cholesky
+// n = 8192 11.0 -> 12.2 ms); the kernels now trigger after their main loop, right before the final stores.
 struct PdlScope {
   bool prev;
   explicit PdlScope(bool on);

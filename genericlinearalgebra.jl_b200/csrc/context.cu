@@ -110,6 +110,10 @@ bool pdl_enabled() {
   static const bool on = getenv("GLA_NO_PDL") == nullptr;
   return on && pdl_scope_on;
 }
+long long pdl_max_n() {
+  static const long long v = [] { const char* e = getenv("GLA_PDL_MAXN"); return e ? atoll(e) : 2048ll; }();
+  return v;
+}
 PdlScope::PdlScope(bool on) : prev(pdl_scope_on) { pdl_scope_on = on; }
 PdlScope::~PdlScope() { pdl_scope_on = prev; }
 

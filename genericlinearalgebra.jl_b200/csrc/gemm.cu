@@ -108,7 +108,6 @@ __global__ void __launch_bounds__(DmmaCfg<BM, BN, STAGES>::THREADS, 2)
   const int nk = (kend - kbeg + 15) >> 4;
   const bool producer = threadIdx.x == 0;
 
-  pdl_launch_dependents();   // (common.cuh) the next kernel of the stream may be scheduled from here on
   if (producer) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
@@ -211,6 +210,7 @@ __global__ void __launch_bounds__(DmmaCfg<BM, BN, STAGES>::THREADS, 2)
     if (lane == 0) mbar_arrive(&empty[s]);
   }
 
+  pdl_launch_dependents();   // main loop done: the next kernel of the stream may be scheduled (its pdl_wait covers our stores)
   // ---- epilogue
 #pragma unroll
   for (int P = 0; P < 2; ++P) {
@@ -297,7 +297,6 @@ __global__ void __launch_bounds__(DmmaCfg<BM, BN, STAGES>::THREADS, 2)
   const int nk = (kend - kbeg + 31) >> 5;
   const bool producer = threadIdx.x == 0;
 
-  pdl_launch_dependents();
   if (producer) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
@@ -398,6 +397,7 @@ __global__ void __launch_bounds__(DmmaCfg<BM, BN, STAGES>::THREADS, 2)
     if (lane == 0) mbar_arrive(&empty[s]);
   }
 
+  pdl_launch_dependents();   // main loop done: the next kernel of the stream may be scheduled (its pdl_wait covers our stores)
   // ---- epilogue: lane owns (i, j), (i, j + 1), (i + 8, j), (i + 8, j + 1) of every 16 x 8 block
   float* Cz = C + (i64)blockIdx.z * split_stride;
 #pragma unroll
@@ -764,7 +764,6 @@ __global__ void __launch_bounds__(ZdmmaCfg<BM, BN, STAGES>::THREADS, 2)
   const int nk = (kend - kbeg + 15) >> 4;
   const bool producer = threadIdx.x == 0;
 
-  pdl_launch_dependents();
   if (producer) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
@@ -866,6 +865,7 @@ __global__ void __launch_bounds__(ZdmmaCfg<BM, BN, STAGES>::THREADS, 2)
     if (lane == 0) mbar_arrive(&empty[s]);
   }
 
+  pdl_launch_dependents();   // main loop done: the next kernel of the stream may be scheduled (its pdl_wait covers our stores)
   // ---- epilogue: two consecutive complex rows = 32 contiguous bytes per column
 #pragma unroll
   for (int P = 0; P < 2; ++P) {

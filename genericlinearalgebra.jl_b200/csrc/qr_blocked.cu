@@ -535,8 +535,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) qr_panel_cluster_kernel(PanelAr
   const int nb = a.nb;
   const int kk = a.mk < nb ? a.mk : nb;
 
-  pdl_launch_dependents();   // programmatic dependent launch (common.cuh; only set up for small problems)
-  pdl_wait();
+  pdl_wait();   // programmatic dependent launch (common.cuh)
   // ---- slab in: coalesced along the rows, L2-only loads (the far update of the other stream just rewrote the panel)
   for (int e = tid; e < rows * nb; e += CP_THREADS) {
     const int col = e / rows, i = e - col * rows;
@@ -643,6 +642,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) qr_panel_cluster_kernel(PanelAr
   }
   if (kk > 0) finish(kk - 1);
   __syncthreads();
+  pdl_launch_dependents();   // only the stores are left
 
   // ---- panel, clean reflectors and their transpose out
   for (int e = tid; e < rows * nb; e += CP_THREADS) {
@@ -1204,7 +1204,7 @@ int geqr_blocked_dev(T* dA, i64 m, i64 n, i64 lda, T* dtau, i64 /*blocksize_hint
   // was never at fault.)  GLA_QR_NO_OVERLAP=1 selects the single-stream schedule for A/B measurements.
   static const bool no_overlap = getenv("GLA_QR_NO_OVERLAP") != nullptr;
   const bool overlap = !no_overlap && n > 2 * NBO && m > 2 * NBO;   // small problems: one stream, one buffer
-  PdlScope pdl(n <= 2048);   // programmatic dependent launch of the small kernels where the launch chain bounds the run (common.cuh)
+  PdlScope pdl(n <= pdl_max_n());   // programmatic dependent launch of the small kernels where the launch chain bounds the run (common.cuh)
   QrWork<T> w;
   GLA_TRY(w.alloc(m, NBO, n > NBO ? n - NBO : 0, overlap ? 2 : 1, st));
   w.yield_sms = overlap ? 1 : 0;
