@@ -3,6 +3,7 @@
 // caller's stream.  No C++ exception crosses this boundary and nothing here computes on the CPU.
 #include "../../include/gla_cuda.h"
 #include "gla_internal.cuh"
+#include <vector>
 
 #include <new>
 #include <stdlib.h>
@@ -181,7 +182,41 @@ int geqr_blocked_host(T* A, i64 m, i64 n, i64 lda, T* tau, i64 hint) {
   GLA_TRY(st.create());
   DevMatrix<T> dA;
   DevBuf dtau;
-  GLA_TRY(dA.upload(A, lda, m, n, st.s));
+  // Large problems: the matrix arrives in column chunks on a stream of its own (first two chunks = the first two outer
+  // blocks, then 1024 columns each) while the factorisation of the first outer block is already running; the driver waits
+  // per chunk (QrHostSink::up_*).  GLA_QR_NO_UPLOAD_OVERLAP=1: one upload ahead of everything.
+  static const bool no_up = getenv("GLA_QR_NO_UPLOAD_OVERLAP") != nullptr;
+  const bool stream_up = !no_up && n > 4 * 384 && m > 2 * 384;
+  Stream up;
+  std::vector<i64> up_col;
+  std::vector<Event> up_events;
+  std::vector<cudaEvent_t> up_ev;
+  if (!stream_up) {
+    GLA_TRY(dA.upload(A, lda, m, n, st.s));
+  } else {
+    dA.ld = round_up(m, 16 / sizeof(T) > 2 ? 16 / sizeof(T) : 2);
+    GLA_TRY(dA.buf.alloc((size_t)dA.ld * n * sizeof(T), st.s));
+    GLA_TRY(up.create());
+    Event ready;
+    GLA_TRY(ready.create());
+    GLA_CUDA(cudaEventRecord(ready.e, st.s));            // the (stream-ordered) allocation
+    GLA_CUDA(cudaStreamWaitEvent(up.s, ready.e, 0));
+    up_col.push_back(0);
+    for (i64 c = 0; c < n;) {
+      const i64 w = up_col.size() <= 2 ? 384 : 1024;
+      c = c + w < n ? c + w : n;
+      up_col.push_back(c);
+    }
+    const int nchunks = (int)up_col.size() - 1;
+    up_events.resize(nchunks);
+    up_ev.resize(nchunks);
+    for (int c = 0; c < nchunks; ++c) {
+      GLA_TRY(up_events[c].create());
+      GLA_TRY(h2d_matrix<T>(dA.p() + up_col[c] * dA.ld, dA.ld, A + up_col[c] * lda, lda, m, up_col[c + 1] - up_col[c], up.s));
+      GLA_CUDA(cudaEventRecord(up_events[c].e, up.s));
+      up_ev[c] = up_events[c].e;
+    }
+  }
   GLA_TRY(dtau.alloc(k * sizeof(T), st.s));
   GLA_CUDA(cudaMemsetAsync(dtau.p, 0, k * sizeof(T), st.s));
   Event e0, e1;
@@ -195,6 +230,11 @@ int geqr_blocked_host(T* A, i64 m, i64 n, i64 lda, T* tau, i64 hint) {
   sink.hA = A;
   sink.ldh = lda;
   sink.copy = cp.s;
+  if (stream_up) {
+    sink.up_chunks = (int)up_ev.size();
+    sink.up_col = up_col.data();
+    sink.up_ev = up_ev.data();
+  }
   GLA_TRY(geqr_blocked_dev<T>(dA.p(), m, n, dA.ld, dtau.as<T>(), hint, st.s, &sink));
   GLA_CUDA(cudaEventRecord(e1.e, st.s));
   if (sink.copied_cols < n)

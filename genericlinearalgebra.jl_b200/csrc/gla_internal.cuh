@@ -16,12 +16,19 @@ int geqr_batched_dev(T* dA, i64 m, i64 n, i64 batch, T* dtau, cudaStream_t st);
 // Host destination of a factorisation driven through the host-pointer entry point: the columns of an outer block are final
 // as soon as its panel chain is done, so they travel device -> host on `copy` WHILE the far updates of the later blocks
 // run (PCIe is otherwise idle during the factorisation).  copied_cols = columns already on their way when the call returns.
+// Upload side (optional): the matrix ARRIVES in column chunks on another stream while the first outer block is already
+// being factorised; chunk c covers the columns [up_col[c], up_col[c + 1]) and is on the device when up_ev[c] has fired.
+// The driver makes each of its streams wait for exactly the chunks a step reads, and cuts the first far update along the
+// chunk boundaries.
 template <class T>
 struct QrHostSink {
   T* hA = nullptr;
   i64 ldh = 0;
   cudaStream_t copy = nullptr;
   i64 copied_cols = 0;
+  int up_chunks = 0;
+  const i64* up_col = nullptr;
+  const cudaEvent_t* up_ev = nullptr;
 };
 template <class T>
 int geqr_blocked_dev(T* dA, i64 m, i64 n, i64 lda, T* dtau, i64 blocksize_hint, cudaStream_t st, QrHostSink<T>* sink = nullptr);

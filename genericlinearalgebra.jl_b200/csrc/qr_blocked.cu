@@ -1091,8 +1091,16 @@ static int apply_panel(QrWork<T>& w, const T* Vc, i64 ldvc, const T* VcT, i64 ld
 // A2 (mo x nA) <- Q_{nj-1}^H ... Q_0^H A2 for the whole outer block held in buffer b (kbig reflectors, Gram
 // already in w.G[b]); path 1 scratch
 template <class T>
+static int outer_nsplit(const QrWork<T>& w, int kbig, i64 nA, i64 mo) {   // split-K slices of W = V^H A2 over nA columns
+  int ns = wsplit_for<T>(kbig, nA, mo);
+  if ((i64)ns * NBO * nA > w.wp_elems[1]) ns = (int)(w.wp_elems[1] / ((i64)NBO * nA));
+  return ns;
+}
+
+// force_nsplit > 0: the slicing of a wider call this one is a piece of (same summation order, bitwise the same result)
+template <class T>
 static int apply_outer(QrWork<T>& w, int b, i64 mo, int kbig, T* A2, i64 lda, i64 nA, cudaStream_t st,
-                       cudaEvent_t g_ready = nullptr) {
+                       cudaEvent_t g_ready = nullptr, int force_nsplit = 0) {
   if (nA <= 0) {
     if (g_ready) GLA_CUDA(cudaStreamWaitEvent(st, g_ready, 0));
     return 0;
@@ -1104,9 +1112,8 @@ static int apply_outer(QrWork<T>& w, int b, i64 mo, int kbig, T* A2, i64 lda, i6
   g1.M = kbig; g1.N = nA; g1.K = mo;
   g1.conj_a = 1;
   g1.yield_sms = w.yield_sms;
-  g1.nsplit = wsplit_for<T>(kbig, nA, mo);
+  g1.nsplit = force_nsplit > 0 ? force_nsplit : outer_nsplit<T>(w, kbig, nA, mo);
   g1.split_stride = (i64)NBO * nA;
-  if ((i64)g1.nsplit * NBO * nA > w.wp_elems[1]) g1.nsplit = (int)(w.wp_elems[1] / ((i64)NBO * nA));
   if (g1.nsplit < 1) {
     set_error(GLA_ERR_INTERNAL, "W workspace too small", __FILE__, __LINE__);
     return GLA_ERR_INTERNAL;
@@ -1222,6 +1229,16 @@ int geqr_blocked_dev(T* dA, i64 m, i64 n, i64 lda, T* dtau, i64 /*blocksize_hint
     if (!rc) rc = check_cuda(cudaStreamWaitEvent(aux.s, aux.ev[0], 0), __FILE__, __LINE__);
     sc = aux.s;
   }
+  // streamed upload (QrHostSink::up_*): stream `s` waits for every chunk that starts left of column c_end
+  int up_waited_chain = 0, up_waited_far = 0;
+  auto need_cols = [&](cudaStream_t s, int& waited, i64 c_end) -> int {
+    if (!sink || !sink->up_chunks) return 0;
+    while (waited < sink->up_chunks && sink->up_col[waited] < c_end) {
+      GLA_CUDA(cudaStreamWaitEvent(s, sink->up_ev[waited], 0));
+      ++waited;
+    }
+    return 0;
+  };
   bool done = false;
   int ob = 0;
   for (i64 o0 = 0; !done && !rc; o0 += NBO, ++ob) {
@@ -1234,6 +1251,7 @@ int geqr_blocked_dev(T* dA, i64 m, i64 n, i64 lda, T* dtau, i64 /*blocksize_hint
     // zeros above the diagonal blocks of V / VT for the whole outer block: one launch on the second side stream (the
     // panel kernels write only rows at and below their diagonal block; the first forked T build of the block follows it
     // on that stream, so the chain -- and through it the far update -- is ordered after it)
+    if ((rc = need_cols(sc, up_waited_chain, o0 + nbo))) break;
     const bool zero_ahead = tfork && nbo > NB && mo > NB;
     if (zero_ahead) {
       if ((rc = check_cuda(cudaEventRecord(aux.ev_panel, sc), __FILE__, __LINE__))) break;   // V[b] is free from here on
@@ -1308,14 +1326,29 @@ int geqr_blocked_dev(T* dA, i64 m, i64 n, i64 lda, T* dtau, i64 /*blocksize_hint
       }
       T* A2 = dA + o0 + (o0 + nbo) * lda;
       const i64 nA = (overlap && !done && nfar > NBO) ? NBO : nfar;
+      if ((rc = need_cols(st, up_waited_far, o0 + nbo + nA))) break;
       if ((rc = apply_outer<T>(w, b, mo, kbig, A2, lda, nA, st, g_ready))) break;
       if (overlap && !done) {
         if ((rc = check_cuda(cudaEventRecord(aux.ev[2], st), __FILE__, __LINE__))) break;       // far A(o) done
         if ((rc = check_cuda(cudaStreamWaitEvent(sc, aux.ev[2], 0), __FILE__, __LINE__))) break;
       }
-      if (nfar > nA) {
-        if ((rc = apply_outer<T>(w, b, mo, kbig, A2 + nA * lda, lda, nfar - nA, st))) break;
+      // the rest of the far update -- cut along the chunk boundaries of a streamed upload while chunks are outstanding
+      const int ns_rest = nfar > nA ? outer_nsplit<T>(w, kbig, nfar - nA, mo) : 0;   // pieces keep the slicing of the whole
+      for (i64 c0 = nA; c0 < nfar && !rc;) {
+        i64 c1 = nfar;
+        if (sink && up_waited_far < sink->up_chunks) {
+          const i64 abs0 = o0 + nbo + c0;   // first column of this piece
+          int c = up_waited_far;
+          while (c < sink->up_chunks && sink->up_col[c + 1] <= abs0) ++c;   // chunk that holds abs0 (or the first one right of it)
+          if (c < sink->up_chunks && sink->up_col[c + 1] - (o0 + nbo) < c1) c1 = sink->up_col[c + 1] - (o0 + nbo);
+          if (c1 <= c0) c1 = nfar;
+          rc = need_cols(st, up_waited_far, o0 + nbo + c1);
+          if (rc) break;
+        }
+        rc = apply_outer<T>(w, b, mo, kbig, A2 + c0 * lda, lda, c1 - c0, st, nullptr, ns_rest);
+        c0 = c1;
       }
+      if (rc) break;
     }
   }
   if (overlap) {  // join: everything issued on the side stream is ordered before what follows on `st`
