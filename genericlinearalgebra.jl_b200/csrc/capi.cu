@@ -235,11 +235,16 @@ int geqr_blocked_host(T* A, i64 m, i64 n, i64 lda, T* tau, i64 hint) {
     sink.up_col = up_col.data();
     sink.up_ev = up_ev.data();
   }
-  GLA_TRY(geqr_blocked_dev<T>(dA.p(), m, n, dA.ld, dtau.as<T>(), hint, st.s, &sink));
+  if (int rc = geqr_blocked_dev<T>(dA.p(), m, n, dA.ld, dtau.as<T>(), hint, st.s, &sink)) {
+    if (stream_up) cudaStreamSynchronize(up.s);   // no chunk may still be in flight when the buffer is released
+    cudaStreamSynchronize(cp.s);
+    return rc;
+  }
   GLA_CUDA(cudaEventRecord(e1.e, st.s));
   if (sink.copied_cols < n)
     GLA_TRY(d2h_matrix<T>(A + sink.copied_cols * lda, lda, dA.p() + sink.copied_cols * dA.ld, dA.ld, m, n - sink.copied_cols, st.s));
   GLA_CUDA(cudaStreamSynchronize(cp.s));
+  if (stream_up) GLA_CUDA(cudaStreamSynchronize(up.s));
   GLA_CUDA(cudaMemcpyAsync(tau, dtau.p, k * sizeof(T), cudaMemcpyDeviceToHost, st.s));
   GLA_CUDA(cudaStreamSynchronize(st.s));
   float ms = 0;

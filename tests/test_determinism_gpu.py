@@ -178,3 +178,26 @@ def test_twosided_bitwise_reproducible(gla):
             ref = (dA, t1.clone(), t2.clone())
         else:
             assert torch.equal(dA, ref[0]) and torch.equal(t1, ref[1]) and torch.equal(t2, ref[2])
+
+
+@pytest.mark.parametrize("m,n", [(2304, 2304), (3000, 1700), (1000, 2600)])
+def test_host_pointer_qr_with_streamed_upload_equals_device_resident(gla, m, n):
+    """gla_dgeqr_blocked on host memory: from n > 1536 (and m > 768) the matrix arrives in column chunks while the first outer
+    block is factorised and the first far update is cut along the chunk boundaries -- with the split-K slicing of the whole,
+    so the result must be BITWISE the device-resident one.  (1000 x 2600: wide, a single outer block row range.)"""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(m + n)
+    src = torch.randn((n, m), generator=g, device="cuda", dtype=torch.float64)   # storage of a column-major m x n matrix
+    k = min(m, n)
+    dA = src.clone()
+    dtau = torch.zeros(k, device="cuda", dtype=torch.float64)
+    gla.qr_blocked_dev(dA.data_ptr(), m, n, m, dtau.data_ptr(), 0, torch.cuda.current_stream().cuda_stream, np.float64)
+    torch.cuda.synchronize()
+    for pinned in (True, False):
+        hA = torch.empty((n, m), dtype=torch.float64, pin_memory=pinned)
+        htau = torch.zeros(k, dtype=torch.float64, pin_memory=pinned)
+        hA.copy_(src)
+        torch.cuda.synchronize()
+        gla.qr_blocked_ptr(hA.data_ptr(), m, n, m, htau.data_ptr(), 0, np.float64)
+        assert torch.equal(hA.cuda(), dA)
+        assert torch.equal(htau.cuda(), dtau)
