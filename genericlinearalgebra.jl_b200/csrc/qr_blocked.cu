@@ -904,7 +904,9 @@ static int launch_panel(T* A, i64 lda, i64 mk, int nb, T* tau, QrWork<T>& w, int
     const i64 rows_max = slab_cap / ((i64)CP_LD * sizeof(T)) / 4 * 4;
     // measured (profiles/r02_qr_panel_cluster.txt): n = 1024 5.74 -> 4.30 ms, n = 2048 11.5 -> 10.4 ms, n = 4096 equal; beyond
     // 256 rows per CTA the rank-1 update of the whole slab per column costs more than the sub-panel form of qr_panel_kernel
-    static const i64 rows_cap = [] { const char* e = getenv("GLA_PANEL_CLUSTER_ROWS"); return e ? (i64)atoi(e) : (i64)320; }();
+    // (Float32 slabs cost half the shared-memory traffic per row: no cap below the capacity of 888 rows -- n = 8192 37.5 -> 34.3 ms,
+    //  n = 16384 119.2 -> 113.7 ms against the Float64 cap of 320, where 256 ... 416 measured flat)
+    static const i64 rows_cap = [] { const char* e = getenv("GLA_PANEL_CLUSTER_ROWS"); return e ? (i64)atoi(e) : (i64)(sizeof(T) == 4 ? 1024 : 320); }();
     const i64 rows_use = rows_max < rows_cap ? rows_max : rows_cap;
     auto kern = qr_panel_cluster_kernel<T>;
     // clusters of 16 CTAs (one GPC holds them): opt-in, and only if the occupancy query says such a cluster can be resident
