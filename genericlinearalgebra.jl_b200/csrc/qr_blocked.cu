@@ -18,7 +18,7 @@
 //   gemm_tn (x3)      G = Vc^H Vc (split-K), W = Vc^H A2 (split-K), A2 -= Vc (T^H W): FP64 tensor
 //                     pipe fed by TMA (gemm.cu)
 //   larft_finish      T = (I + diag(tau) striu(G))^-1 diag(tau) in one CTA (shared memory, recursive doubling)
-//   qr_panel_cluster_kernel   panels of <= 5120 rows: one thread-block cluster of up to 16 CTAs, the per-column
+//   qr_panel_cluster_kernel   panels of <= 6656 rows (Float64; Float32 14208, ComplexF64 2384): one thread-block cluster of up to 16 CTAs, the per-column
 //                     exchange through distributed shared memory (st.async onto the receiver's transaction barrier)
 //                     instead of L2
 // Q application and thin Q (ormqr_blocked_dev, orgqr_thin_dev) reuse the same outer-block machinery in both directions.
@@ -448,14 +448,14 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) qr_panel_kernel(PanelArgs<T>
 }
 
 // ------------------------------------------------------------------------------- K1c: cluster panel kernel
-// Panels of at most 16 x 320 rows: ONE thread-block cluster, CTA r holds rows [r*ROWS, ...) of the panel in shared
+// Panels of at most 16 x 416 rows (Float64): ONE thread-block cluster, CTA r holds rows [r*ROWS, ...) of the panel in shared
 // memory (row-major, padded), and the per-column exchange goes through DISTRIBUTED SHARED MEMORY instead of L2: every
 // CTA sends its 2 x 64 partials (dots of the un-normalised pivot column with every column, and its contribution to
 // pivot row j) into the same slot of every CTA's exchange buffer with st.async, which completes the bytes on a
 // transaction barrier of the receiver; every CTA waits on its own barrier and sums the slots in rank order (bitwise
 // identical scalars everywhere, deterministic).  The L2 flag exchange of qr_panel_kernel costs ~4000 cycles per column;
 // remote stores + barrier.cluster (the first version of this kernel) 1000 - 1250; this one a one-way trip.  Plain
-// right-looking steps (no 16-column sub-panels): at <= 320 rows per CTA the rank-1 update of the whole slab is cheaper
+// right-looking steps (no 16-column sub-panels): at these slab heights the rank-1 update of the whole slab is cheaper
 // than the bookkeeping of the blocked form.
 // Semantics: qrUnblocked! (src/qr.jl:86-111) with stdlib reflector! / reflectorApply! (call sites :96, :102), then the
 // clean reflector block Vc (unit diagonal, zeros above) and its transpose VcT like qr_panel_kernel.
@@ -905,8 +905,8 @@ static int launch_panel(T* A, i64 lda, i64 mk, int nb, T* tau, QrWork<T>& w, int
     // measured (profiles/r02_qr_panel_cluster.txt): n = 1024 5.74 -> 4.30 ms, n = 2048 11.5 -> 10.4 ms, n = 4096 equal; beyond
     // 256 rows per CTA the rank-1 update of the whole slab per column costs more than the sub-panel form of qr_panel_kernel
     // (Float32 slabs cost half the shared-memory traffic per row: no cap below the capacity of 888 rows -- n = 8192 37.5 -> 34.3 ms,
-    //  n = 16384 119.2 -> 113.7 ms against the Float64 cap of 320, where 256 ... 416 measured flat)
-    static const i64 rows_cap = [] { const char* e = getenv("GLA_PANEL_CLUSTER_ROWS"); return e ? (i64)atoi(e) : (i64)(sizeof(T) == 4 ? 1024 : 320); }();
+    //  n = 16384 119.2 -> 113.7 ms against a cap of 320; Float64: 320 -> 416 is worth 0.2 - 0.6 % from n = 6144 on)
+    static const i64 rows_cap = [] { const char* e = getenv("GLA_PANEL_CLUSTER_ROWS"); return e ? (i64)atoi(e) : (i64)(sizeof(T) == 4 ? 1024 : 416); }();
     const i64 rows_use = rows_max < rows_cap ? rows_max : rows_cap;
     auto kern = qr_panel_cluster_kernel<T>;
     // clusters of 16 CTAs (one GPC holds them): opt-in, and only if the occupancy query says such a cluster can be resident
