@@ -373,18 +373,31 @@ int potrf_host(T* A, i64 n, i64 lda, i64 cutoff) {
   GLA_TRY(e0.create());
   GLA_TRY(e1.create());
   GLA_CUDA(cudaEventRecord(e0.e, st.s));
-  GLA_TRY(potrf_recursive_L_dev<T>(dA.p(), n, dA.ld, cutoff, dinfo.as<int>(), st.s));
+  // the columns of L that belong to a finished outer block go home on a second stream while the chain goes on (CholHostSink)
+  Stream cp;
+  GLA_TRY(cp.create());
+  CholHostSink<T> sink;
+  sink.hA = A;
+  sink.ldh = lda;
+  sink.copy = cp.s;
+  if (int rc = potrf_recursive_L_dev<T>(dA.p(), n, dA.ld, cutoff, dinfo.as<int>(), st.s, &sink)) {
+    cudaStreamSynchronize(cp.s);
+    return rc;
+  }
   GLA_CUDA(cudaEventRecord(e1.e, st.s));
   int info = 0;
   GLA_CUDA(cudaMemcpyAsync(&info, dinfo.p, sizeof(int), cudaMemcpyDeviceToHost, st.s));
+  // like the reference (DomainError out of sqrt at src/cholesky.jl:40 with A partially overwritten), a failed call
+  // still returns the partially factorised lower triangle; the index of the minor goes out of band (gla_last_info)
+  for (i64 j = sink.copied_cols; j < n; j += TRI_BC) {   // the columns that did not travel yet (lower trapezoid only)
+    const i64 nc = n - j < TRI_BC ? n - j : TRI_BC;
+    GLA_TRY(d2h_matrix<T>(A + j + j * lda, lda, dA.p() + j + j * dA.ld, dA.ld, n - j, nc, st.s));
+  }
   GLA_CUDA(cudaStreamSynchronize(st.s));
+  GLA_CUDA(cudaStreamSynchronize(cp.s));
   float ms = 0;
   GLA_CUDA(cudaEventElapsedTime(&ms, e0.e, e1.e));
   g_last_ms = ms;
-  // like the reference (DomainError out of sqrt at src/cholesky.jl:40 with A partially overwritten), a failed call
-  // still returns the partially factorised lower triangle; the index of the minor goes out of band (gla_last_info)
-  GLA_TRY(d2h_lower<T>(A, lda, dA.p(), dA.ld, n, st.s));
-  GLA_CUDA(cudaStreamSynchronize(st.s));
   if (info != 0) {
     g_last_info = info;
     return GLA_ERR_NOT_POSDEF;

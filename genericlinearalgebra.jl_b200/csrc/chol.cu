@@ -67,6 +67,23 @@ __global__ void mirror_out_kernel(T* __restrict__ A, i64 lda, const T* __restric
   }
 }
 
+// the same for the columns [c_lo, c_hi) of A only (c_lo a multiple of 32): grid.y counts column tiles from c_lo
+template <class T>
+__global__ void mirror_out_cols_kernel(T* __restrict__ A, i64 lda, const T* __restrict__ U, i64 ldu, int n, int c_lo, int c_hi) {
+  __shared__ T tile[32][33];
+  const int bi = blockIdx.x * 32, bj = c_lo + blockIdx.y * 32;  // A tile origin
+  if (bj > bi + 31 || bj >= c_hi) return;                        // strictly upper tile of A / beyond the range
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int j = bj + threadIdx.x, i = bi + r;
+    tile[r][threadIdx.x] = (i < n && j < n) ? cj(U[(i64)i * ldu + j]) : Sc<T>::zero();
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int i = bi + threadIdx.x, j = bj + r;
+    if (i < n && j < c_hi && i >= j) A[(i64)j * lda + i] = tile[threadIdx.x][r];
+  }
+}
+
 // P (k x n, ldp) = A^H for A n x k (lda)   (conjugate transpose, K-contiguous operand of a rank-k update)
 template <class T>
 __global__ void conj_transpose_kernel(const T* __restrict__ A, i64 lda, int n, int k, T* __restrict__ P, i64 ldp) {
@@ -499,10 +516,11 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(T* __restrict__ W, i64 
 
 // the diagonal blocks factorised by chol_panel_kernel go back into the mirror (upper triangles)
 template <class T>
-__global__ void __launch_bounds__(256) put_diag_blocks_kernel(T* __restrict__ W, i64 ldw, int n, const T* __restrict__ Ud) {
-  const int r = blockIdx.x * CB;
+__global__ void __launch_bounds__(256) put_diag_blocks_kernel(T* __restrict__ W, i64 ldw, int n, const T* __restrict__ Ud, int b0 = 0) {
+  const int blk = b0 + blockIdx.x;   // diagonal block index
+  const int r = blk * CB;
   const int nb = min(CB, n - r);
-  const T* U = Ud + (i64)blockIdx.x * CB * CB;
+  const T* U = Ud + (i64)blk * CB * CB;
   for (int e = threadIdx.x; e < CB * CB; e += 256) {
     const int i = e & (CB - 1), c = e >> 6;
     if (i <= c && c < nb) W[(i64)(r + c) * ldw + r + i] = U[(i64)c * CB + i];
@@ -518,6 +536,9 @@ struct CholCtx {
   int* info;
   cudaStream_t st;
   T* Y = nullptr;   // LDL only: D U, same shape as W
+  T* dA = nullptr;  // user-layout matrix and host sink of the host-pointer path (see CholHostSink)
+  i64 lda = 0;
+  CholHostSink<T>* sink = nullptr;
 };
 
 static i64 split_point(i64 n) {
@@ -665,6 +686,19 @@ static int chol_right_looking(CholCtx<T>& cx, i64 n) {
       }
       const i64 mu = nt < OB ? nt : OB;                   // rows of the next outer block: needed by the chain right away
       GLA_CUDA(cudaEventRecord(aux->ev[1], sc));          // panels of this outer block done
+      if (!LDL && cx.sink && cx.sink->copy && cx.sink->copied_cols == r0) {
+        // rows r0 .. t0 of U are final: their diagonal blocks go back into the mirror, the matching columns of L are
+        // mirrored into the user layout and travel home while the chain goes on (nobody else touches these parts)
+        cudaStream_t cs = cx.sink->copy;
+        GLA_CUDA(cudaStreamWaitEvent(cs, aux->ev[1], 0));
+        put_diag_blocks_kernel<T><<<(unsigned)(done / CB), 256, 0, cs>>>(cx.W, cx.ldw, (int)n, cx.Uinv, (int)(r0 / CB));
+        dim3 tb(32, 8), grid((unsigned)ceil_div(n, 32), (unsigned)ceil_div(done, 32));
+        mirror_out_cols_kernel<T><<<grid, tb, 0, cs>>>(cx.dA, cx.lda, cx.W, cx.ldw, (int)n, (int)r0, (int)t0);
+        GLA_CUDA(cudaGetLastError());
+        GLA_CUDA(cudaMemcpy2DAsync(cx.sink->hA + r0 + r0 * cx.sink->ldh, cx.sink->ldh * sizeof(T), cx.dA + r0 + r0 * cx.lda,
+                                   cx.lda * sizeof(T), (n - r0) * sizeof(T), done, cudaMemcpyDeviceToHost, cs));
+        cx.sink->copied_cols = t0;
+      }
       if (bulk_pending) GLA_CUDA(cudaStreamWaitEvent(sc, aux->ev[2], 0));   // those rows carry the previous bulk update
       GLA_TRY(update(r0, done, t0, mu, sc));
       if (nt > mu) {
@@ -679,13 +713,15 @@ static int chol_right_looking(CholCtx<T>& cx, i64 n) {
       GLA_CUDA(cudaEventRecord(aux->ev[3], sc));
       GLA_CUDA(cudaStreamWaitEvent(caller, aux->ev[3], 0));
     }
-    put_diag_blocks_kernel<T><<<(unsigned)ceil_div(n, CB), 256, 0, cx.st>>>(cx.W, cx.ldw, (int)n, cx.Uinv);
+    const i64 b0 = (!LDL && cx.sink) ? cx.sink->copied_cols / CB : 0;   // blocks before b0 went back (and home) already
+    if (ceil_div(n, CB) > b0)
+      put_diag_blocks_kernel<T><<<(unsigned)(ceil_div(n, CB) - b0), 256, 0, cx.st>>>(cx.W, cx.ldw, (int)n, cx.Uinv, (int)b0);
     return check_cuda(cudaGetLastError(), __FILE__, __LINE__);
   }
 }
 
 template <class T>
-int potrf_recursive_L_dev(T* dA, i64 n, i64 lda, i64 /*cutoff*/, int* dinfo, cudaStream_t st) {
+int potrf_recursive_L_dev(T* dA, i64 n, i64 lda, i64 /*cutoff*/, int* dinfo, cudaStream_t st, CholHostSink<T>* sink) {
   if (n < 0) return -2;
   if (lda < (n > 1 ? n : 1)) return -3;
   if (n == 0) return 0;
@@ -707,9 +743,18 @@ int potrf_recursive_L_dev(T* dA, i64 n, i64 lda, i64 /*cutoff*/, int* dinfo, cud
     mirror_in_kernel<T><<<grid, tb, 0, st>>>(dA, lda, cx.W, cx.ldw, (int)n);
     rc = check_cuda(cudaGetLastError(), __FILE__, __LINE__);
   }
+  cx.dA = dA;
+  cx.lda = lda;
+  cx.sink = use_panel_path<T>() ? sink : nullptr;
   if (!rc) rc = use_panel_path<T>() ? chol_right_looking<T>(cx, n) : chol_rec<T>(cx, 0, n);
   if (!rc) {
-    mirror_out_kernel<T><<<grid, tb, 0, st>>>(dA, lda, cx.W, cx.ldw, (int)n);
+    const i64 c_lo = cx.sink ? cx.sink->copied_cols : 0;   // columns already mirrored (and on their way to the host)
+    if (c_lo == 0) {
+      mirror_out_kernel<T><<<grid, tb, 0, st>>>(dA, lda, cx.W, cx.ldw, (int)n);
+    } else if (c_lo < n) {
+      dim3 g2((unsigned)ceil_div(n, 32), (unsigned)ceil_div(n - c_lo, 32));
+      mirror_out_cols_kernel<T><<<g2, tb, 0, st>>>(dA, lda, cx.W, cx.ldw, (int)n, (int)c_lo, (int)n);
+    }
     rc = check_cuda(cudaGetLastError(), __FILE__, __LINE__);
   }
   cudaFreeAsync(block, st);
@@ -803,7 +848,7 @@ int herk_lower_dev(T* dC, i64 n, i64 ldc, const T* dA, i64 k, i64 lda, typename 
 }
 
 #define INST(T)                                                                  \
-  template int potrf_recursive_L_dev<T>(T*, i64, i64, i64, int*, cudaStream_t);  \
+  template int potrf_recursive_L_dev<T>(T*, i64, i64, i64, int*, cudaStream_t, CholHostSink<T>*);  \
   template int herk_lower_dev<T>(T*, i64, i64, const T*, i64, i64, typename Sc<T>::real, cudaStream_t); \
   template int ldlt_dev<T>(T*, i64, i64, int, int*, cudaStream_t);
 INST(float)

@@ -30,6 +30,16 @@ struct QrHostSink {
   const i64* up_col = nullptr;
   const cudaEvent_t* up_ev = nullptr;
 };
+// Host destination of a Cholesky factorisation driven through the host-pointer entry point: the rows of U = L^H of an outer
+// block are final when its panel kernels are done, so the matching COLUMNS of L (rows r .. n) are mirrored into the user
+// layout and sent home on `copy` while the chain goes on.  copied_cols = columns already on their way when the call returns.
+template <class T>
+struct CholHostSink {
+  T* hA = nullptr;
+  i64 ldh = 0;
+  cudaStream_t copy = nullptr;
+  i64 copied_cols = 0;
+};
 template <class T>
 int geqr_blocked_dev(T* dA, i64 m, i64 n, i64 lda, T* dtau, i64 blocksize_hint, cudaStream_t st, QrHostSink<T>* sink = nullptr);
 i64 geqr_blocked_workspace_bytes(i64 m, i64 n, i64 elem_bytes);
@@ -58,7 +68,7 @@ int tsqr_allreduce_dev(void* comm, int nranks, const double* dRloc, i64 n, doubl
 
 // K6: Cholesky (chol.cu)
 template <class T>
-int potrf_recursive_L_dev(T* dA, i64 n, i64 lda, i64 cutoff, int* dinfo, cudaStream_t st);
+int potrf_recursive_L_dev(T* dA, i64 n, i64 lda, i64 cutoff, int* dinfo, cudaStream_t st, CholHostSink<T>* sink = nullptr);
 // ldlt!(Hermitian(A, uplo)) without pivoting (src/ldlt.jl:80-162); real element types
 template <class T>
 int ldlt_dev(T* dA, i64 n, i64 lda, int upper, int* dinfo, cudaStream_t st);
