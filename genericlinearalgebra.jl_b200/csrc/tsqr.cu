@@ -264,6 +264,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 2)
 // the current one is reduced; its loads are 16-byte vector loads straight into the registers.  Measured: 10.2 ms against
 // 11.0 ms for the CTA-per-chunk kernel at 8,388,608 x 64 (a column step still costs ~2000 cycles of latency per warp).
 // For n <= 32 half of the payload registers are dead: 24-row chunks and twelve warps per SM there (tw_config below).
+// Measured and not taken: every lane storing its column into a [row pair][lane] buffer at the end of a step (16 conflict-free
+// full-warp STS.128) instead of the owner lane publishing alone in a diverged branch -- 10.70 against 10.24 ms (the extra
+// shared-memory store traffic costs more than the 16 single-lane stores).
 // two configurations: 8 warps x 32-row chunks (two warps per sub-partition, 255 registers: 128 payload registers + the
 // temporaries of a step) and 12 warps x 24-row chunks (three per sub-partition, 168 registers, 96 of them payload).
 constexpr int TW_WARPS = 8;
