@@ -593,24 +593,40 @@ __global__ void __launch_bounds__(CP_THREADS, 1) qr_panel_cluster_kernel(PanelAr
     // after this CTA's reads of column j -- so two parities are enough for the buffers and for the barrier phases.
     if (tid == 0 && CL > 1) cl_bar_expect(par ? xbar1 : xbar0, xbytes);
     __syncthreads();
-    if (tid < 2 * NB) {
+    {
+      // ALL threads form the value of slot v (four copies of each: the dots of this CTA for v < NB, its pivot-row entries
+      // beyond), and copy `grp` of a slot sends it to the ranks grp, grp + 4, ...: four st.async per thread instead of
+      // sixteen by a quarter of the threads (an ncu capture of the 1024-row panel: 41 % of the kernel was this phase, with
+      // twelve of the sixteen warps waiting at the barrier behind it)
+      const int v = tid & (2 * NB - 1), grp = tid >> 7;
       T val;
-      if (tid < NB) {   // warps 0-1: the dots of this CTA; warps 2-3: its pivot-row entries
-        val = sm.part[0][c];
+      if (v < NB) {
+        val = sm.part[0][v];
 #pragma unroll
-        for (int g2 = 1; g2 < CP_RG; ++g2) val = val + sm.part[g2][c];
+        for (int g2 = 1; g2 < CP_RG; ++g2) val = val + sm.part[g2][v];
       } else {
-        val = (j >= r0 && j < r1 && c < nb) ? S[(j - r0) * CP_LD + c] : Sc<T>::zero();
+        val = (j >= r0 && j < r1 && v - NB < nb) ? S[(j - r0) * CP_LD + (v - NB)] : Sc<T>::zero();
       }
       if (CL > 1) {
-        const unsigned slot = cl_smem_addr(&sm.xbuf[par][rank][tid]), bar = par ? xbar1 : xbar0;
-        for (int r = 0; r < CL; ++r)   // same slot of every CTA's exchange buffer (distributed shared memory)
+        const unsigned slot = cl_smem_addr(&sm.xbuf[par][rank][v]), bar = par ? xbar1 : xbar0;
+        for (int r = grp; r < CL; r += CP_THREADS / (2 * NB))   // same slot of every CTA's exchange buffer (distributed shared memory)
           cl_st_async(cl_mapa(slot, (unsigned)r), val, cl_mapa(bar, (unsigned)r));
-        if (!cl_bar_wait(bar, (unsigned)((j >> 1) & 1))) __trap();
-        val = sm.xbuf[par][0][tid];
-        for (int r = 1; r < CL; ++r) val = val + sm.xbuf[par][r][tid];
+        if (tid < 2 * NB) {
+          if (!cl_bar_wait(bar, (unsigned)((j >> 1) & 1))) __trap();
+          // fixed pairwise order over the ranks (the same in every CTA: bitwise identical sums), four levels instead of
+          // a chain of fifteen dependent additions
+          T x[CL_MAX];
+#pragma unroll
+          for (int r = 0; r < CL_MAX; ++r) x[r] = r < CL ? sm.xbuf[par][r][tid] : Sc<T>::zero();
+#pragma unroll
+          for (int st2 = 1; st2 < CL_MAX; st2 <<= 1)
+#pragma unroll
+            for (int r = 0; r + st2 < CL_MAX; r += 2 * st2) x[r] = x[r] + x[r + st2];
+          sm.tot[tid] = x[0];
+        }
+      } else if (tid < 2 * NB) {
+        sm.tot[tid] = val;   // (a panel of one CTA has nothing to exchange)
       }
-      sm.tot[tid] = val;   // (a panel of one CTA has nothing to exchange)
     }
     __syncthreads();
     const T alpha = sm.tot[NB + j];
