@@ -4,7 +4,7 @@
 // stdlib reflector!/reflectorApply! call sites :96/:102)  ->  T build (src/qr.jl:64-83, with the conj
 // the reference omits at :72)  ->  trailing update A2 <- (I - V T^H V^H) A2 (src/householder.jl:119-157).
 //
-// GPU structure: panels of NB = 64 columns, grouped six at a time into outer blocks of NBO = 384 whose
+// GPU structure: panels of NB = 64 columns, grouped into outer blocks of 256 (n <= 12288) or NBO = 384 columns whose
 // reflectors hit the far trailing matrix in one K = 384 pass (apply_outer).  Per panel:
 //   qr_panel_kernel   cooperative, P CTAs each holding a row slab of the panel in shared memory;
 //                     ONE grid-wide reduction per column: every CTA publishes the partial dots
@@ -772,6 +772,19 @@ __global__ void __launch_bounds__(256) larft_finish_kernel(const T* __restrict__
 
 // ------------------------------------------------------------------------------- workspace
 constexpr int NBO = 384;  // outer block: K of the far trailing contractions (measured at n=16384: 256 -> 258.8 ms, 384 -> 254.0 ms, 512 -> 258.3 ms)
+// NBO is the CAPACITY (leading dimensions, buffer sizes); the factorisation steps through outer blocks of outer_width()
+// columns: 256 up to n = 12288, 384 beyond.  Measured at the end of round 2 (faster panel chain than when 384 was chosen):
+// 256 against 384 -- n = 1024 2.59 / 2.68 ms, n = 2048 6.20 / 6.51, n = 4096 15.9 / 16.6, n = 8192 49.4 / 51.0, n = 16384
+// 243.4 / 238.2.  GLA_QR_NBO = 128 ... 384 (multiple of 64) forces a width.
+static int outer_width(i64 n) {
+  static const int forced = [] {
+    const char* e = getenv("GLA_QR_NBO");
+    const int v = e ? atoi(e) : 0;
+    return (v >= 2 * NB && v <= NBO && v % NB == 0) ? v : 0;
+  }();
+  if (forced) return forced;
+  return n <= 12288 ? 256 : NBO;
+}
 
 // Workspace of one factorisation.  The outer-block state (V, VT, per-panel T, Gram) is DOUBLE BUFFERED by outer
 // block parity and every scratch array exists once per execution path, because the driver overlaps two paths:
@@ -1198,17 +1211,18 @@ struct AuxStream {  // high-priority side streams + the events of the look-ahead
 // device bytes geqr_blocked_dev takes from the stream-ordered pool for an m x n problem (gla_workspace_query)
 i64 geqr_blocked_workspace_bytes(i64 m, i64 n, i64 elem_bytes) {
   if (m == 0 || n == 0) return 0;
-  const bool overlap = n > 2 * NBO && m > 2 * NBO;
+  const int nbw = outer_width(n);
+  const bool overlap = n > 2 * nbw && m > 2 * nbw;
   i64 total = 0;
   if (elem_bytes == 4) {
     QrWork<float> w;
-    w.alloc(m, NBO, n > NBO ? n - NBO : 0, overlap ? 2 : 1, nullptr, &total);
+    w.alloc(m, NBO, n > nbw ? n - nbw : 0, overlap ? 2 : 1, nullptr, &total);
   } else if (elem_bytes == 8) {
     QrWork<double> w;
-    w.alloc(m, NBO, n > NBO ? n - NBO : 0, overlap ? 2 : 1, nullptr, &total);
+    w.alloc(m, NBO, n > nbw ? n - nbw : 0, overlap ? 2 : 1, nullptr, &total);
   } else {
     QrWork<zd> w;
-    w.alloc(m, NBO, n > NBO ? n - NBO : 0, overlap ? 2 : 1, nullptr, &total);
+    w.alloc(m, NBO, n > nbw ? n - nbw : 0, overlap ? 2 : 1, nullptr, &total);
   }
   return total;
 }
@@ -1228,10 +1242,11 @@ int geqr_blocked_dev(T* dA, i64 m, i64 n, i64 lda, T* dtau, i64 /*blocksize_hint
   // kernels read their fragments with explicit ld.shared, this concurrency exposed wrong tiles; the schedule itself
   // was never at fault.)  GLA_QR_NO_OVERLAP=1 selects the single-stream schedule for A/B measurements.
   static const bool no_overlap = getenv("GLA_QR_NO_OVERLAP") != nullptr;
-  const bool overlap = !no_overlap && n > 2 * NBO && m > 2 * NBO;   // small problems: one stream, one buffer
+  const int nbw = outer_width(n);   // columns per outer block (<= NBO, the capacity of the buffers)
+  const bool overlap = !no_overlap && n > 2 * nbw && m > 2 * nbw;   // small problems: one stream, one buffer
   PdlScope pdl(n <= pdl_max_n());   // programmatic dependent launch of the small kernels where the launch chain bounds the run (common.cuh)
   QrWork<T> w;
-  GLA_TRY(w.alloc(m, NBO, n > NBO ? n - NBO : 0, overlap ? 2 : 1, st));
+  GLA_TRY(w.alloc(m, NBO, n > nbw ? n - nbw : 0, overlap ? 2 : 1, st));
   w.yield_sms = overlap ? 1 : 0;
   AuxStream aux;
   cudaStream_t sc = st;  // chain stream
@@ -1259,9 +1274,9 @@ int geqr_blocked_dev(T* dA, i64 m, i64 n, i64 lda, T* dtau, i64 /*blocksize_hint
   };
   bool done = false;
   int ob = 0;
-  for (i64 o0 = 0; !done && !rc; o0 += NBO, ++ob) {
+  for (i64 o0 = 0; !done && !rc; o0 += nbw, ++ob) {
     const i64 mo = m - o0, no = n - o0;
-    const int nbo = (int)(no < NBO ? no : NBO);  // columns of this outer block
+    const int nbo = (int)(no < nbw ? no : nbw);  // columns of this outer block
     const int b = overlap ? (ob & 1) : 0;
     w.cur = b;
     int kbig = 0;
@@ -1343,7 +1358,7 @@ int geqr_blocked_dev(T* dA, i64 m, i64 n, i64 lda, T* dtau, i64 /*blocksize_hint
         break;
       }
       T* A2 = dA + o0 + (o0 + nbo) * lda;
-      const i64 nA = (overlap && !done && nfar > NBO) ? NBO : nfar;
+      const i64 nA = (overlap && !done && nfar > nbw) ? nbw : nfar;
       if ((rc = need_cols(st, up_waited_far, o0 + nbo + nA))) break;
       if ((rc = apply_outer<T>(w, b, mo, kbig, A2, lda, nA, st, g_ready))) break;
       if (overlap && !done) {
